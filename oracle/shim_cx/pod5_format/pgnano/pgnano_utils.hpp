@@ -1,0 +1,2 @@
+// Build shim (test infrastructure): intentionally empty.
+#pragma once

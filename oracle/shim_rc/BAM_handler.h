@@ -1,0 +1,3 @@
+// Build shim (test infrastructure).
+#pragma once
+namespace pgnano { class BAMHandler {}; }
