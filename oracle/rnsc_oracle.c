@@ -202,8 +202,8 @@ static int codec_nframes(int codec) { return codec == VBZ || codec == VBZ0 ? 1 :
 
 /* Whole-chunk encode. VBZ: signal_compression.cpp:37-78. VBZ0: VBZ_0.hpp:316-362. C1: C1.hpp:202-285.
  * C2: C2.hpp:195-316. C3: C3.hpp:212-354. C4: C4.hpp:274-470. C5: C5.hpp:282-474.
- * Container: u64 size prefix before every frame but the last. Returns 0 ok; 1 zstd failure
- * ("Failed to compress ..."); 3 "Not enough space in destination buffer" (C4/C5 check it, C5.hpp:420-427;
+ * Container: u64 size prefix before every frame but the last. Status codes are rnsc.h's: 0 ok;
+ * 6 zstd failure ("Failed to compress ..."); 3 "Not enough space in destination buffer" (C4/C5 check it, C5.hpp:420-427;
  * C1-C3 overrun in the reference -- reported as the same error here). */
 int orc_encode(int codec, const int16_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_size)
 {
@@ -216,7 +216,7 @@ int orc_encode(int codec, const int16_t* in, size_t n, uint8_t* out, size_t cap,
         uint8_t* cat = (uint8_t*)malloc(sizes[0] + sizes[1] + 16);
         memcpy(cat, st, sizes[0]); memcpy(cat + sizes[0], st + stride, sizes[1]);
         size_t c = z_compress(out, cap, cat, sizes[0] + sizes[1], 1);
-        if (z_iserr(c)) rc = 1; else op = c;
+        if (z_iserr(c)) rc = 6; else op = c;
         free(cat);
     } else {
         int nf = codec_nframes(codec);
@@ -224,7 +224,7 @@ int orc_encode(int codec, const int16_t* in, size_t n, uint8_t* out, size_t cap,
         for (int f = 0; f < nf && !rc; ++f) {
             size_t b = z_bound(sizes[f]); tmp[f] = (uint8_t*)malloc(b);
             cs[f] = z_compress(tmp[f], b, st + stride * f, sizes[f], 1);
-            if (z_iserr(cs[f])) rc = 1;
+            if (z_iserr(cs[f])) rc = 6;
             total += cs[f] + (f + 1 < nf ? 8 : 0);
         }
         if (!rc && total > cap) rc = 3;

@@ -1,0 +1,548 @@
+// api.cu -- host side of librnsc.so: the C ABI of include/rnsc.h over the sm_100a kernels.
+//
+// Device-resident batcher: a context owns one CUDA stream, grow-only device staging (samples, compressed
+// bytes, offset tables, per-CTA scratch) and pinned host staging. Host-buffer entry points stage the batch
+// into HBM, run the kernels and copy the result back; rnsc_dev_* entry points take device pointers and
+// only enqueue work. The zstd *frame encoder* stage of the compressors runs on host threads through the
+// image's libzstd.so.1 (same shared object the reference links), fed by the device splitter kernels --
+// the only way to be byte-identical with the reference's ZSTD_compress(.., 1) output.
+#ifdef RNSC_EMUL_BUILD
+#include "cuda_emul.h"
+#endif
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace rnsc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_OK(expr)                                                                                   \
+    do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(RNSC_ERR_NO_DEVICE, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+// ---- libzstd (host entropy stage of the encoders) ----
+struct Zstd {
+    size_t (*compress)(void*, size_t, const void*, size_t, int) = nullptr;
+    size_t (*bound)(size_t) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    unsigned (*version)(void) = nullptr;
+    bool ok = false;
+};
+Zstd& zstd()
+{
+    static Zstd z;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return;
+        z.compress = (size_t(*)(void*, size_t, const void*, size_t, int))dlsym(h, "ZSTD_compress");
+        z.bound = (size_t(*)(size_t))dlsym(h, "ZSTD_compressBound");
+        z.is_error = (unsigned (*)(size_t))dlsym(h, "ZSTD_isError");
+        z.version = (unsigned (*)(void))dlsym(h, "ZSTD_versionNumber");
+        z.ok = z.compress && z.bound && z.is_error;
+    });
+    return z;
+}
+// ZSTD_compressBound's published formula, so that sizes do not need libzstd loaded
+size_t zstd_bound(size_t n) { return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0); }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+constexpr size_t kDecodeSmem = 112 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
+
+}  // namespace
+
+struct rnsc_ctx {
+    int device = 0;
+    int sm_count = 1;
+    cudaStream_t stream = nullptr;
+    int host_threads = 0;
+    uint64_t launches = 0;
+    std::mutex mu;   // host-buffer entry points serialise on the context's staging
+    DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
+    PinBuf h_a, h_b;
+};
+
+namespace {
+
+int use_device(rnsc_ctx* c) { CUDA_OK(cudaSetDevice(c->device)); return 0; }
+
+size_t decode_arena_bytes()
+{
+    const size_t used = ((sizeof(DecodeWs) + 15) & ~(size_t)15) + ((sizeof(ChunkCtl) + 15) & ~(size_t)15);
+    return kDecodeSmem - used;
+}
+
+int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t* d_comp_off, const uint32_t* d_n, const uint64_t* d_sample_off,
+                  size_t nchunks, uint32_t max_n, int16_t* d_samples, int32_t* d_status, cudaStream_t st)
+{
+    if (nchunks == 0) return RNSC_OK;
+    const int grid = (int)std::min<size_t>((size_t)c->sm_count * 2, nchunks);
+    const size_t spill = ((size_t)stream_bound(codec, max_n) + 5 * 16 + 255) & ~(size_t)255;
+    const size_t stride = ((LIT_SCRATCH + 255) & ~(size_t)255) + spill;
+    if (c->d_scratch.reserve(stride * (size_t)c->sm_count * 2)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(scratch %zu) failed", stride * (size_t)c->sm_count * 2);
+    if (c->d_counter.reserve(256)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(counter) failed");
+    CUDA_OK(cudaMemsetAsync(c->d_counter.p, 0, 4, st));
+    DecodeParams p;
+    p.comp = d_comp; p.comp_off = d_comp_off; p.n = d_n; p.sample_off = d_sample_off; p.samples = d_samples; p.status = d_status;
+    p.nchunks = (uint32_t)nchunks; p.codec = codec; p.scratch = (uint8_t*)c->d_scratch.p; p.scratch_stride = stride;
+    p.counter = (uint32_t*)c->d_counter.p; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
+    RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, st, p);
+    c->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+bool codec_ok(int codec) { return codec >= RNSC_VBZ && codec <= RNSC_RC; }
+bool svb_codec_ok(int codec) { return codec >= RNSC_VBZ && codec <= RNSC_C5; }
+
+template <typename F>
+void parallel_for(size_t n, int threads, F&& f)
+{
+    if (threads <= 1 || n <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<size_t> next{0};
+    auto body = [&] { for (;;) { size_t i = next.fetch_add(1); if (i >= n) break; f(i); } };
+    std::vector<std::thread> pool;
+    const int nt = (int)std::min<size_t>((size_t)threads, n);
+    for (int t = 1; t < nt; ++t) pool.emplace_back(body);
+    body();
+    for (auto& t : pool) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rnsc_version(void) { return "rnsc-b200 0.1 (sm_100a)"; }
+
+int rnsc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* rnsc_status_string(int s)
+{
+    switch (s) {
+    case RNSC_OK: return "OK";
+    case RNSC_ERR_NOT_ZSTD: return "Input data not compressed by zstd";
+    case RNSC_ERR_ZSTD_DECODE: return "Input data failed to decompress using zstd";
+    case RNSC_ERR_DST_TOO_SMALL: return "Not enough space in destination buffer";
+    case RNSC_ERR_REMAINING: return "Remaining data at end of signal buffer";
+    case RNSC_ERR_CONTAINER: return "Malformed pgnano container (size prefix past end of chunk)";
+    case RNSC_ERR_ZSTD_ENCODE: return "Failed to compress data";
+    case RNSC_ERR_RC_RAW: return "Range coder output exceeds raw size (reference raw fallback is unsupported)";
+    case RNSC_ERR_BAD_ARG: return "Invalid argument";
+    case RNSC_ERR_NO_DEVICE: return "CUDA device unavailable or CUDA error";
+    case RNSC_ERR_NO_ZSTD: return "libzstd.so.1 could not be loaded";
+    default: return "Unknown status";
+    }
+}
+
+const char* rnsc_last_error(void) { return g_err.c_str(); }
+
+rnsc_ctx* rnsc_create(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { fail(RNSC_ERR_NO_DEVICE, "no CUDA device: librnsc has no CPU fallback"); return nullptr; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= count) { fail(RNSC_ERR_BAD_ARG, "device %d out of range (%d devices)", device, count); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(RNSC_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", device); return nullptr; }
+    rnsc_ctx* c = new rnsc_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed"); return nullptr; }
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
+    cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_svb_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SvbWs) + 16 + SVB_STAGE_BYTES));
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return nullptr; }
+    unsigned hc = std::thread::hardware_concurrency();
+    c->host_threads = hc ? (int)hc : 1;
+    return c;
+}
+
+void rnsc_destroy(rnsc_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux}) b->release();
+    c->h_a.release(); c->h_b.release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void rnsc_set_host_threads(rnsc_ctx* c, int n) { if (c && n > 0) c->host_threads = n; }
+uint64_t rnsc_launch_count(const rnsc_ctx* c) { return c ? c->launches : 0; }
+
+size_t rnsc_max_compressed_size(int codec, size_t n)
+{
+    if (codec == RNSC_VBZ) return zstd_bound((size_t)key_len1((uint32_t)n) + 2 * n);
+    const size_t s = 2 * n + 10 + 16;
+    return s > 1024 ? s : 1024;
+}
+size_t rnsc_max_stream_bytes(int codec, size_t n) { return (size_t)stream_bound(codec, n); }
+int rnsc_stream_count(int codec) { return svb_codec_ok(codec) ? codec_streams(codec) : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// device-resident entry points
+// ---------------------------------------------------------------------------------------------------
+int rnsc_dev_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t* d_comp_off, const uint32_t* d_n, const uint64_t* d_sample_off,
+                    size_t nchunks, uint32_t max_n, int16_t* d_samples, int32_t* d_status, void* stream)
+{
+    if (!c || !svb_codec_ok(codec) || (nchunks && (!d_comp || !d_comp_off || !d_n || !d_sample_off || !d_samples || !d_status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_decode: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    return launch_decode(c, codec, d_comp, d_comp_off, d_n, d_sample_off, nchunks, max_n, d_samples, d_status, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int rnsc_dev_exclusive_scan_u32(rnsc_ctx* c, const uint32_t* d_in, size_t count, uint64_t* d_out, void* stream)
+{
+    if (!c || !d_out || (count && !d_in)) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_exclusive_scan_u32: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, d_in, (unsigned long long)count, (unsigned long long*)d_out);
+    c->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+int rnsc_dev_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks,
+                        uint8_t* d_streams, size_t streams_cap, uint64_t* d_stream_off, void* stream)
+{
+    if (!c || !svb_codec_ok(codec) || !d_stream_off || (nchunks && (!d_samples || !d_sample_off || !d_n || !d_streams))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_svb_encode: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (c->d_sizes.reserve(5 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(sizes) failed");
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->sm_count * 8, nchunks));
+    if (nchunks) { RNSC_LAUNCH(k_svb_sizes, grid, NT, 0, st, codec, d_samples, d_sample_off, d_n, (uint32_t)nchunks, (uint32_t*)c->d_sizes.p); c->launches += 1; }
+    RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_sizes.p, (unsigned long long)(5 * nchunks), (unsigned long long*)d_stream_off);
+    c->launches += 1;
+    uint64_t total = 0;
+    CUDA_OK(cudaMemcpyAsync(&total, d_stream_off + 5 * nchunks, sizeof total, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (total > streams_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "stream buffer too small: need %llu bytes, have %zu", (unsigned long long)total, streams_cap);
+    if (nchunks) {
+        const size_t smem = ((sizeof(SvbWs) + 15) & ~(size_t)15) + SVB_STAGE_BYTES;
+        RNSC_LAUNCH(k_svb_pack, grid, NT, smem, st, codec, d_samples, d_sample_off, d_n, (uint32_t)nchunks, d_streams, (const uint64_t*)d_stream_off);
+        c->launches += 1;
+    }
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+int rnsc_dev_svb_decode(rnsc_ctx* c, int codec, const uint8_t* d_streams, const uint64_t* d_stream_off, const uint32_t* d_n, const uint64_t* d_sample_off,
+                        size_t nchunks, int16_t* d_samples, int32_t* d_status, void* stream)
+{
+    if (!c || !svb_codec_ok(codec) || (nchunks && (!d_streams || !d_stream_off || !d_n || !d_sample_off || !d_samples || !d_status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_svb_decode: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    if (!nchunks) return RNSC_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int grid = (int)std::min<size_t>((size_t)c->sm_count * 8, nchunks);
+    RNSC_LAUNCH(k_svb_unpack, grid, NT, 0, st, codec, d_streams, d_stream_off, d_n, d_sample_off, (uint32_t)nchunks, d_samples, d_status);
+    c->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+int rnsc_dev_rc_encode(rnsc_ctx* c, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks, uint8_t pore_type,
+                       uint8_t* d_comp, const uint64_t* d_slot_off, uint32_t* d_comp_size, int32_t* d_status, void* stream)
+{
+    if (!c || (nchunks && (!d_samples || !d_sample_off || !d_n || !d_comp || !d_slot_off || !d_comp_size || !d_status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_rc_encode: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    if (!nchunks) return RNSC_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int grid = (int)std::min<size_t>((size_t)c->sm_count * 8, (nchunks + RC_WARPS - 1) / RC_WARPS);
+    RNSC_LAUNCH(k_rc_encode, grid, 32 * RC_WARPS, 0, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, pore_type, d_comp, d_slot_off, d_comp_size, d_status);
+    c->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+int rnsc_dev_rc_decode(rnsc_ctx* c, const uint8_t* d_comp, const uint64_t* d_comp_off, const uint32_t* d_n, const uint64_t* d_sample_off, size_t nchunks,
+                       int16_t* d_samples, int32_t* d_status, void* stream)
+{
+    if (!c || (nchunks && (!d_comp || !d_comp_off || !d_n || !d_sample_off || !d_samples || !d_status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_rc_decode: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    if (!nchunks) return RNSC_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int grid = (int)std::min<size_t>((size_t)c->sm_count * 8, (nchunks + RC_WARPS - 1) / RC_WARPS);
+    RNSC_LAUNCH(k_rc_decode, grid, 32 * RC_WARPS, 0, st, d_comp, d_comp_off, d_n, d_sample_off, (uint32_t)nchunks, d_samples, d_status);
+    c->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer batch entry points
+// ---------------------------------------------------------------------------------------------------
+int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uint64_t* comp_off, const uint32_t* n, size_t nchunks,
+                          int16_t* samples, const uint64_t* sample_off, int32_t* status)
+{
+    if (!c || !codec_ok(codec) || (nchunks && (!comp || !comp_off || !n || !samples || !sample_off || !status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_decompress_batch: bad argument");
+    if (!nchunks) return RNSC_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    // chunk i may live anywhere in `comp`/`samples`: stage them back to back in HBM (the kernels accept
+    // any byte/sample alignment) and build dense offset tables
+    std::vector<uint64_t> coff(nchunks + 1), soff(nchunks + 1);
+    uint64_t cb = 0, sb = 0; uint32_t max_n = 0;
+    for (size_t i = 0; i < nchunks; ++i) {
+        if (comp_off[i + 1] < comp_off[i]) return fail(RNSC_ERR_BAD_ARG, "comp_off must be non-decreasing");
+        coff[i] = cb; soff[i] = sb;
+        cb += comp_off[i + 1] - comp_off[i]; sb += n[i];
+        if (n[i] > max_n) max_n = n[i];
+    }
+    coff[nchunks] = cb; soff[nchunks] = sb;
+    if (c->d_comp.reserve(cb + 64) || c->d_samples.reserve(sb * 2 + 64) || c->d_off_a.reserve((nchunks + 1) * 8) || c->d_off_b.reserve((nchunks + 1) * 8) ||
+        c->d_n.reserve(nchunks * 4 + 16) || c->d_status.reserve(nchunks * 4 + 16))
+        return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
+    cudaStream_t st = c->stream;
+    bool contiguous = true;
+    for (size_t i = 0; i < nchunks; ++i) if (comp_off[i] - comp_off[0] != coff[i]) { contiguous = false; break; }
+    if (contiguous) CUDA_OK(cudaMemcpyAsync(c->d_comp.p, comp + comp_off[0], cb, cudaMemcpyHostToDevice, st));
+    else for (size_t i = 0; i < nchunks; ++i) CUDA_OK(cudaMemcpyAsync((uint8_t*)c->d_comp.p + coff[i], comp + comp_off[i], comp_off[i + 1] - comp_off[i], cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync((uint8_t*)c->d_comp.p + cb, 0, 32, st));
+    CUDA_OK(cudaMemcpyAsync(c->d_off_a.p, coff.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c->d_off_b.p, soff.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c->d_n.p, n, nchunks * 4, cudaMemcpyHostToDevice, st));
+    int r;
+    if (codec == RNSC_RC) r = rnsc_dev_rc_decode(c, (const uint8_t*)c->d_comp.p, (const uint64_t*)c->d_off_a.p, (const uint32_t*)c->d_n.p, (const uint64_t*)c->d_off_b.p, nchunks, (int16_t*)c->d_samples.p, (int32_t*)c->d_status.p, st);
+    else r = launch_decode(c, codec, (const uint8_t*)c->d_comp.p, (const uint64_t*)c->d_off_a.p, (const uint32_t*)c->d_n.p, (const uint64_t*)c->d_off_b.p, nchunks, max_n, (int16_t*)c->d_samples.p, (int32_t*)c->d_status.p, st);
+    if (r) return r;
+    CUDA_OK(cudaMemcpyAsync(status, c->d_status.p, nchunks * 4, cudaMemcpyDeviceToHost, st));
+    bool dense = true;
+    for (size_t i = 0; i < nchunks; ++i) if (sample_off[i] - sample_off[0] != soff[i]) { dense = false; break; }
+    if (dense) CUDA_OK(cudaMemcpyAsync(samples + sample_off[0], c->d_samples.p, sb * 2, cudaMemcpyDeviceToHost, st));
+    else for (size_t i = 0; i < nchunks; ++i) if (n[i]) CUDA_OK(cudaMemcpyAsync(samples + sample_off[i], (int16_t*)c->d_samples.p + soff[i], (size_t)n[i] * 2, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return RNSC_OK;
+}
+
+int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, size_t nchunks,
+                        uint8_t* comp, size_t comp_cap, uint64_t* comp_off, int32_t* status)
+{
+    if (!c || !codec_ok(codec) || !comp_off || (nchunks && (!samples || !sample_off || !n || !comp || !status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_compress_batch: bad argument");
+    comp_off[0] = 0;
+    if (!nchunks) return RNSC_OK;
+    if (codec != RNSC_RC && !zstd().ok) return fail(RNSC_ERR_NO_ZSTD, "libzstd.so.1 not loadable: %s", dlerror());
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    cudaStream_t st = c->stream;
+    std::vector<uint64_t> soff(nchunks + 1);
+    uint64_t sb = 0;
+    for (size_t i = 0; i < nchunks; ++i) { soff[i] = sb; sb += n[i]; }
+    soff[nchunks] = sb;
+    if (c->d_samples.reserve(sb * 2 + 64) || c->d_off_b.reserve((nchunks + 1) * 8) || c->d_n.reserve(nchunks * 4 + 16) || c->d_status.reserve(nchunks * 4 + 16))
+        return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
+    bool dense = true;
+    for (size_t i = 0; i < nchunks; ++i) if (sample_off[i] - sample_off[0] != soff[i]) { dense = false; break; }
+    if (dense) CUDA_OK(cudaMemcpyAsync(c->d_samples.p, samples + sample_off[0], sb * 2, cudaMemcpyHostToDevice, st));
+    else for (size_t i = 0; i < nchunks; ++i) if (n[i]) CUDA_OK(cudaMemcpyAsync((int16_t*)c->d_samples.p + soff[i], samples + sample_off[i], (size_t)n[i] * 2, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c->d_off_b.p, soff.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c->d_n.p, n, nchunks * 4, cudaMemcpyHostToDevice, st));
+
+    if (codec == RNSC_RC) {
+        std::vector<uint64_t> slot(nchunks + 1);
+        uint64_t tot = 0;
+        for (size_t i = 0; i < nchunks; ++i) { slot[i] = tot; tot += (rnsc_max_compressed_size(RNSC_RC, n[i]) + 24 + 15) & ~(size_t)15; }
+        slot[nchunks] = tot;
+        if (c->d_comp.reserve(tot + 64) || c->d_off_a.reserve((nchunks + 1) * 8) || c->d_sizes.reserve(nchunks * 4 + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
+        CUDA_OK(cudaMemcpyAsync(c->d_off_a.p, slot.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
+        int r = rnsc_dev_rc_encode(c, (const int16_t*)c->d_samples.p, (const uint64_t*)c->d_off_b.p, (const uint32_t*)c->d_n.p, nchunks, 0, (uint8_t*)c->d_comp.p,
+                                   (const uint64_t*)c->d_off_a.p, (uint32_t*)c->d_sizes.p, (int32_t*)c->d_status.p, st);
+        if (r) return r;
+        std::vector<uint32_t> csz(nchunks);
+        CUDA_OK(cudaMemcpyAsync(csz.data(), c->d_sizes.p, nchunks * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(status, c->d_status.p, nchunks * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        uint64_t op = 0;
+        for (size_t i = 0; i < nchunks; ++i) {
+            comp_off[i] = op;
+            if (status[i] == RNSC_OK) {
+                if (op + csz[i] > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small");
+                CUDA_OK(cudaMemcpyAsync(comp + op, (uint8_t*)c->d_comp.p + slot[i], csz[i], cudaMemcpyDeviceToHost, st));
+                op += csz[i];
+            }
+        }
+        comp_off[nchunks] = op;
+        CUDA_OK(cudaStreamSynchronize(st));
+        return RNSC_OK;
+    }
+
+    // ---- splitter stage on the device ----
+    uint64_t scap = 0;
+    for (size_t i = 0; i < nchunks; ++i) scap += stream_bound(codec, n[i]);
+    if (c->d_streams.reserve(scap + 64) || c->d_stream_off.reserve((5 * nchunks + 1) * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(streams) failed");
+    int r = rnsc_dev_svb_encode(c, codec, (const int16_t*)c->d_samples.p, (const uint64_t*)c->d_off_b.p, (const uint32_t*)c->d_n.p, nchunks,
+                                (uint8_t*)c->d_streams.p, scap, (uint64_t*)c->d_stream_off.p, st);
+    if (r) return r;
+    std::vector<uint64_t> stoff(5 * nchunks + 1);
+    CUDA_OK(cudaMemcpyAsync(stoff.data(), c->d_stream_off.p, stoff.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const uint64_t total = stoff[5 * nchunks];
+    if (c->h_a.reserve(total + 64)) return fail(RNSC_ERR_NO_DEVICE, "cudaMallocHost(streams) failed");
+    CUDA_OK(cudaMemcpyAsync(c->h_a.p, c->d_streams.p, total, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    // ---- zstd frame stage on host threads (byte-identical with the reference's ZSTD_compress(.., 1)) ----
+    const uint8_t* hs = (const uint8_t*)c->h_a.p;
+    const int nf = codec_frames(codec);
+    std::vector<std::vector<uint8_t>> outs(nchunks);
+    Zstd& z = zstd();
+    parallel_for(nchunks, c->host_threads, [&](size_t i) {
+        const uint64_t* so = &stoff[5 * i];
+        std::vector<uint8_t>& o = outs[i];
+        const size_t cap = rnsc_max_compressed_size(codec, n[i]);
+        status[i] = RNSC_OK;
+        if (nf == 1) {       // keys||data are adjacent in the stream buffer: one frame straight into the destination
+            o.resize(cap);
+            size_t cs = z.compress(o.data(), cap, hs + so[0], (size_t)(so[2] - so[0]), 1);
+            if (z.is_error(cs)) { status[i] = RNSC_ERR_ZSTD_ENCODE; o.clear(); } else o.resize(cs);
+            return;
+        }
+        size_t need = 0;
+        for (int f = 0; f < nf; ++f) need += z.bound((size_t)(so[f + 1] - so[f])) + 8;
+        o.resize(need);
+        size_t op = 0;
+        for (int f = 0; f < nf; ++f) {
+            const size_t len = (size_t)(so[f + 1] - so[f]);
+            const size_t hdr = f + 1 < nf ? 8 : 0;
+            size_t cs = z.compress(o.data() + op + hdr, need - op - hdr, hs + so[f], len, 1);
+            if (z.is_error(cs)) { status[i] = RNSC_ERR_ZSTD_ENCODE; o.clear(); return; }
+            if (hdr) { uint64_t v = cs; memcpy(o.data() + op, &v, 8); }
+            op += hdr + cs;
+        }
+        // destination capacity max(2n+26,1024): C4/C5 report it (C5.hpp:420-427); C1-C3 overrun in the
+        // reference, which is reported as the same error here.
+        if (op > cap) { status[i] = RNSC_ERR_DST_TOO_SMALL; o.clear(); return; }
+        o.resize(op);
+    });
+    uint64_t op = 0;
+    for (size_t i = 0; i < nchunks; ++i) {
+        comp_off[i] = op;
+        if (op + outs[i].size() > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need more than %zu bytes", comp_cap);
+        if (!outs[i].empty()) memcpy(comp + op, outs[i].data(), outs[i].size());
+        op += outs[i].size();
+    }
+    comp_off[nchunks] = op;
+    return RNSC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-chunk entry points
+// ---------------------------------------------------------------------------------------------------
+int rnsc_compress_chunk(rnsc_ctx* c, int codec, const int16_t* samples, size_t n, uint8_t* out, size_t* inout_size)
+{
+    if (!c || !codec_ok(codec) || !out || !inout_size || (n && !samples) || n > 0xFFFFFFFFull) return fail(RNSC_ERR_BAD_ARG, "rnsc_compress_chunk: bad argument");
+    static const int16_t dummy = 0;
+    const uint64_t soff = 0; const uint32_t nn = (uint32_t)n; uint64_t coff[2]; int32_t st = 0;
+    std::vector<uint8_t> tmp(rnsc_max_compressed_size(codec, n) + 64);
+    int r = rnsc_compress_batch(c, codec, n ? samples : &dummy, &soff, &nn, 1, tmp.data(), tmp.size(), coff, &st);
+    if (r) return r;
+    if (st) return fail(st, "%s", rnsc_status_string(st));
+    if (coff[1] > *inout_size) return fail(RNSC_ERR_DST_TOO_SMALL, "Compressed signal size (%llu) is greater than provided buffer size (%zu)", (unsigned long long)coff[1], *inout_size);
+    memcpy(out, tmp.data(), coff[1]);
+    *inout_size = coff[1];
+    return RNSC_OK;
+}
+
+int rnsc_decompress_chunk(rnsc_ctx* c, int codec, const uint8_t* in, size_t in_size, size_t n, int16_t* out)
+{
+    static int16_t dummy_out[8];
+    if (!c || !codec_ok(codec) || !in || (n && !out) || n > 0xFFFFFFFFull) return fail(RNSC_ERR_BAD_ARG, "rnsc_decompress_chunk: bad argument");
+    const uint64_t coff[2] = {0, in_size}; const uint64_t soff = 0; const uint32_t nn = (uint32_t)n; int32_t st = 0;
+    int r = rnsc_decompress_batch(c, codec, in, coff, &nn, 1, n ? out : dummy_out, &soff, &st);
+    if (r) return r;
+    if (st) return fail(st, "%s", rnsc_status_string(st));
+    return RNSC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pod5-named entry points (c_api.h:678-711) on one process-wide context
+// ---------------------------------------------------------------------------------------------------
+static std::mutex g_proc_mu;
+static rnsc_ctx* g_proc_ctx = nullptr;
+static std::atomic<int> g_variant{RNSC_C5};
+static rnsc_ctx* proc_ctx()
+{
+    std::lock_guard<std::mutex> lk(g_proc_mu);
+    if (!g_proc_ctx) g_proc_ctx = rnsc_create(-1);
+    return g_proc_ctx;
+}
+int rnsc_set_pgnano_variant(int codec) { if (codec < RNSC_VBZ || codec > RNSC_C5) return fail(RNSC_ERR_BAD_ARG, "variant must be one of VBZ, VBZ0, C1..C5"); g_variant = codec; return RNSC_OK; }
+int rnsc_get_pgnano_variant(void) { return g_variant; }
+
+size_t rnsc_pod5_vbz_compressed_signal_max_size(size_t sample_count) { return rnsc_max_compressed_size(RNSC_VBZ, sample_count); }
+
+rnsc_pod5_error_t rnsc_pod5_vbz_compress_signal(const int16_t* signal, size_t signal_size, char* out, size_t* size)
+{
+    if (!signal || !out || !size) return fail(RNSC_ERR_BAD_ARG, "null passed to C API");
+    rnsc_ctx* c = proc_ctx(); if (!c) return RNSC_ERR_NO_DEVICE;
+    return rnsc_compress_chunk(c, RNSC_VBZ, signal, signal_size, (uint8_t*)out, size);
+}
+rnsc_pod5_error_t rnsc_pod5_pinanoraw_compress_signal(const int16_t* signal, size_t signal_size, char* out, size_t* size)
+{
+    if (!signal || !out || !size) return fail(RNSC_ERR_BAD_ARG, "null passed to C API");
+    rnsc_ctx* c = proc_ctx(); if (!c) return RNSC_ERR_NO_DEVICE;
+    return rnsc_compress_chunk(c, g_variant, signal, signal_size, (uint8_t*)out, size);
+}
+rnsc_pod5_error_t rnsc_pod5_vbz_decompress_signal(const char* in, size_t in_size, size_t sample_count, short* out)
+{
+    if (!in || !out) return fail(RNSC_ERR_BAD_ARG, "null passed to C API");
+    rnsc_ctx* c = proc_ctx(); if (!c) return RNSC_ERR_NO_DEVICE;
+    return rnsc_decompress_chunk(c, RNSC_VBZ, (const uint8_t*)in, in_size, sample_count, out);
+}
+rnsc_pod5_error_t rnsc_pod5_pinanoraw_decompress_signal(const char* in, size_t in_size, size_t sample_count, short* out)
+{
+    if (!in || !out) return fail(RNSC_ERR_BAD_ARG, "null passed to C API");
+    rnsc_ctx* c = proc_ctx(); if (!c) return RNSC_ERR_NO_DEVICE;
+    return rnsc_decompress_chunk(c, g_variant, (const uint8_t*)in, in_size, sample_count, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// kernels.cuh -- __global__ entry points of librnsc (sm_100a). Launch geometry lives in api.cu.
+#pragma once
+#include "zstd_decode.cuh"
+#include "svb_codec.cuh"
+#include "rc_codec.cuh"
+
+namespace rnsc {
+
+// ---------------------------------------------------------------------------------------------------
+// Fused whole-chunk decode: container -> zstd frames -> streams (shared-memory arena) -> int16.
+// Persistent CTAs pull chunk indices from a global counter. One CTA owns one chunk at a time.
+// ---------------------------------------------------------------------------------------------------
+struct DecodeParams {
+    const uint8_t* comp; const uint64_t* comp_off; const uint32_t* n; const uint64_t* sample_off;
+    int16_t* samples; int32_t* status; uint32_t nchunks; int codec;
+    uint8_t* scratch; unsigned long long scratch_stride;   // per-CTA global scratch: [literals 128K+64][stream spill]
+    uint32_t* counter; uint32_t arena_bytes;               // shared-memory arena after the workspace
+    uint32_t spill_bytes;                                  // bytes of stream spill space per CTA
+};
+
+constexpr uint32_t LIT_SCRATCH = ZSTD_BLOCK_MAX + 64;
+
+union DecodeWs { ZstdWs z; SvbWs s; };
+
+struct ChunkCtl {
+    View view[5];
+    uint32_t f_off[5], f_len[5], f_fcs[5], f_raw[5];
+    uint8_t* f_dst[5];
+    int status; uint32_t chunk;
+};
+
+template <int CODEC>
+__device__ __forceinline__ int unpack_dispatch(const View* v, uint32_t n, int16_t* out, SvbWs* ws) { return svb_unpack<CODEC>(v, n, out, ws); }
+
+__device__ inline int unpack_any(int codec, const View* v, uint32_t n, int16_t* out, SvbWs* ws)
+{
+    switch (codec) {
+    case RNSC_VBZ: return svb_unpack<RNSC_VBZ>(v, n, out, ws);
+    case RNSC_VBZ0: return svb_unpack<RNSC_VBZ0>(v, n, out, ws);
+    case RNSC_C1: return svb_unpack<RNSC_C1>(v, n, out, ws);
+    case RNSC_C2: return svb_unpack<RNSC_C2>(v, n, out, ws);
+    case RNSC_C3: return svb_unpack<RNSC_C3>(v, n, out, ws);
+    case RNSC_C4: return svb_unpack<RNSC_C4>(v, n, out, ws);
+    default: return svb_unpack<RNSC_C5>(v, n, out, ws);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2) k_decode_chunks(DecodeParams p)
+{
+    RNSC_DYN_SMEM(smem);
+    DecodeWs* ws = (DecodeWs*)smem;
+    ChunkCtl* ctl = (ChunkCtl*)(smem + ((sizeof(DecodeWs) + 15) & ~(size_t)15));
+    uint8_t* arena = (uint8_t*)ctl + ((sizeof(ChunkCtl) + 15) & ~(size_t)15);
+    const int tid = threadIdx.x;
+    uint8_t* lit = p.scratch + (size_t)blockIdx.x * p.scratch_stride;
+    uint8_t* spill = lit + LIT_SCRATCH;
+    const int nf = codec_frames(p.codec);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) ctl->chunk = atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const uint32_t c = ctl->chunk;
+        if (c >= p.nchunks) break;
+        const uint8_t* src = p.comp + p.comp_off[c];
+        const uint32_t clen = (uint32_t)(p.comp_off[c + 1] - p.comp_off[c]);
+        const uint32_t n = p.n[c];
+        // ---- container + frame headers + placement (thread 0) ----
+        if (tid == 0) {
+            int st = RNSC_OK; uint32_t pos = 0, arena_used = 0, spill_used = 0;
+            const uint64_t bound = stream_bound(p.codec, n);
+            for (int f = 0; f < nf && st == RNSC_OK; ++f) {
+                uint32_t fl;
+                if (f + 1 < nf) {
+                    if (pos + 8 > clen) { st = RNSC_ERR_CONTAINER; break; }
+                    unsigned long long v = 0; for (int i = 0; i < 8; ++i) v |= (unsigned long long)ldg8(src + pos + i) << (8 * i);
+                    pos += 8;
+                    if (v > clen - pos) { st = RNSC_ERR_CONTAINER; break; }
+                    fl = (uint32_t)v;
+                } else fl = clen - pos;
+                uint32_t hdr, known, ck; uint64_t fcs;
+                int r = zstd_parse_frame_header(src + pos, fl, &hdr, &fcs, &known, &ck);
+                if (r || !known) { st = RNSC_ERR_NOT_ZSTD; break; }       // ZSTD_getFrameContentSize must succeed
+                if (fcs > bound) { st = RNSC_ERR_REMAINING; break; }      // more stream bytes than any valid chunk of n samples
+                ctl->f_off[f] = pos; ctl->f_len[f] = fl; ctl->f_fcs[f] = (uint32_t)fcs;
+                // a frame that is exactly one raw block is used in place (zero copy)
+                uint32_t raw = 0;
+                if (hdr + 3 <= fl) {
+                    uint32_t bh = ldg8(src + pos + hdr) | (ldg8(src + pos + hdr + 1) << 8) | (ldg8(src + pos + hdr + 2) << 16);
+                    if ((bh & 1) && ((bh >> 1) & 3) == 0 && (bh >> 3) == (uint32_t)fcs && hdr + 3 + (bh >> 3) + (ck ? 4 : 0) == fl) raw = hdr + 3;
+                }
+                ctl->f_raw[f] = raw;
+                if (raw) ctl->f_dst[f] = nullptr;
+                else if (arena_used + (uint32_t)fcs <= p.arena_bytes) { ctl->f_dst[f] = arena + arena_used; arena_used += ((uint32_t)fcs + 15) & ~15u; }
+                else if (spill_used + (uint32_t)fcs <= p.spill_bytes) { ctl->f_dst[f] = spill + spill_used; spill_used += ((uint32_t)fcs + 15) & ~15u; }
+                else { st = RNSC_ERR_REMAINING; break; }
+                pos += fl;
+            }
+            ctl->status = st;
+        }
+        __syncthreads();
+        // ---- frames ----
+        for (int f = 0; f < nf && ctl->status == RNSC_OK; ++f) {
+            if (ctl->f_raw[f]) continue;
+            if (tid == 0) ws->z.err = 0;
+            __syncthreads();
+            int r = zstd_decode_frame(&ws->z, src + ctl->f_off[f], ctl->f_len[f], ctl->f_dst[f], ctl->f_fcs[f], lit);
+            if (r && tid == 0) ctl->status = r;
+            __syncthreads();
+        }
+        // ---- stream views (A.8: slices of the decompressed buffer) ----
+        if (tid == 0 && ctl->status == RNSC_OK) {
+            const uint32_t kl = key_len(p.codec, n);
+            for (int k = 0; k < 5; ++k) { ctl->view[k].p = src; ctl->view[k].len = 0; }
+            auto fptr = [&](int f) -> const uint8_t* { return ctl->f_raw[f] ? src + ctl->f_off[f] + ctl->f_raw[f] : ctl->f_dst[f]; };
+            if (nf == 1) {
+                if (ctl->f_fcs[0] < kl) ctl->status = RNSC_ERR_REMAINING;
+                else { ctl->view[0].p = fptr(0); ctl->view[0].len = kl; ctl->view[1].p = fptr(0) + kl; ctl->view[1].len = ctl->f_fcs[0] - kl; }
+            } else {
+                if (ctl->f_fcs[0] != kl) ctl->status = RNSC_ERR_REMAINING;
+                for (int f = 0; f < nf; ++f) { ctl->view[f].p = fptr(f); ctl->view[f].len = ctl->f_fcs[f]; }
+            }
+            if (n == 0) { uint32_t tot = 0; for (int f = 0; f < nf; ++f) tot += ctl->f_fcs[f]; if (tot) ctl->status = RNSC_ERR_REMAINING; }
+        }
+        __syncthreads();
+        if (ctl->status == RNSC_OK && n > 0) {
+            int r = unpack_any(p.codec, ctl->view, n, p.samples + p.sample_off[c], &ws->s);
+            if (r && tid == 0) ctl->status = r;
+        }
+        __syncthreads();
+        if (tid == 0) p.status[c] = ctl->status;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Splitter stage only: streams <-> samples (one CTA per chunk, grid-stride over chunks)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 2) k_svb_unpack(int codec, const uint8_t* streams, const uint64_t* stream_off, const uint32_t* n,
+                                                      const uint64_t* sample_off, uint32_t nchunks, int16_t* samples, int32_t* status)
+{
+    __shared__ SvbWs ws;
+    __shared__ View view[5];
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 5) { const uint64_t a = stream_off[5 * (size_t)c + threadIdx.x], b = stream_off[5 * (size_t)c + threadIdx.x + 1];
+                               view[threadIdx.x].p = streams + a; view[threadIdx.x].len = (uint32_t)(b - a); }
+        __syncthreads();
+        const uint32_t nn = n[c];
+        int r = RNSC_OK;
+        if (nn == 0) { uint32_t tot = 0; for (int k = 0; k < 5; ++k) tot += view[k].len; if (tot) r = RNSC_ERR_REMAINING; }
+        else if (view[0].len != key_len(codec, nn)) r = RNSC_ERR_REMAINING;
+        else r = unpack_any(codec, view, nn, samples + sample_off[c], &ws);
+        if (threadIdx.x == 0) status[c] = r;
+    }
+}
+
+template <bool COUNT_ONLY>
+__device__ inline void pack_any(int codec, const int16_t* in, uint32_t n, uint8_t* const* dst, uint32_t* sizes, SvbWs* ws, uint8_t* stage)
+{
+    switch (codec) {
+    case RNSC_VBZ: svb_pack<RNSC_VBZ, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
+    case RNSC_VBZ0: svb_pack<RNSC_VBZ0, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
+    case RNSC_C1: svb_pack<RNSC_C1, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
+    case RNSC_C2: svb_pack<RNSC_C2, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
+    case RNSC_C3: svb_pack<RNSC_C3, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
+    case RNSC_C4: svb_pack<RNSC_C4, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
+    default: svb_pack<RNSC_C5, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
+    }
+}
+
+// pass 1: stream sizes of every chunk (5 x u32 per chunk)
+__global__ void __launch_bounds__(NT, 2) k_svb_sizes(int codec, const int16_t* samples, const uint64_t* sample_off, const uint32_t* n,
+                                                     uint32_t nchunks, uint32_t* sizes)
+{
+    __shared__ SvbWs ws;
+    __shared__ uint32_t sz[5];
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        __syncthreads();
+        pack_any<true>(codec, samples + sample_off[c], n[c], nullptr, sz, &ws, nullptr);
+        if (threadIdx.x < 5) sizes[5 * (size_t)c + threadIdx.x] = sz[threadIdx.x];
+    }
+}
+
+// pass 2: scatter into the compact stream buffer at the scanned offsets
+__global__ void __launch_bounds__(NT, 2) k_svb_pack(int codec, const int16_t* samples, const uint64_t* sample_off, const uint32_t* n,
+                                                    uint32_t nchunks, uint8_t* streams, const uint64_t* stream_off)
+{
+    RNSC_DYN_SMEM(smem);
+    SvbWs* ws = (SvbWs*)smem;
+    uint8_t* stage = smem + ((sizeof(SvbWs) + 15) & ~(size_t)15);
+    __shared__ uint8_t* dst[5];
+    __shared__ uint32_t sz[5];
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 5) dst[threadIdx.x] = streams + stream_off[5 * (size_t)c + threadIdx.x];
+        __syncthreads();
+        pack_any<false>(codec, samples + sample_off[c], n[c], dst, sz, ws, stage);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device prefix scan that assigns output offsets: out[0] = 0, out[i+1] = out[i] + in[i].
+// One CTA walks the array tile by tile (count is ~5 x chunks: a few 100k at most).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) k_exclusive_scan_u32(const uint32_t* in, unsigned long long count, unsigned long long* out)
+{
+    __shared__ unsigned long long scratch[2][NWARP + 1];
+    unsigned long long run = 0; int flip = 0;
+    for (unsigned long long base = 0; base < count; base += NT, flip ^= 1) {
+        const unsigned long long i = base + threadIdx.x;
+        const unsigned long long v = i < count ? in[i] : 0;
+        unsigned long long tot;
+        const unsigned long long ex = block_exclusive_scan<unsigned long long>(v, scratch[flip], &tot);
+        if (i < count) out[i] = run + ex;
+        run += tot;
+    }
+    if (threadIdx.x == 0) out[count] = run;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Range coder: one warp per chunk
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * RC_WARPS) k_rc_encode(const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, uint32_t nchunks,
+                                                             uint8_t pore, uint8_t* comp, const uint64_t* slot_off, uint32_t* comp_size, int32_t* status)
+{
+    __shared__ RcModelSet models[RC_WARPS];
+    const uint32_t w = threadIdx.x >> 5;
+    for (uint32_t c = blockIdx.x * RC_WARPS + w; c < nchunks; c += gridDim.x * RC_WARPS) {
+        const uint32_t r = rc_encode_chunk(samples + sample_off[c], n[c], comp + slot_off[c], pore, &models[w]);
+        if ((threadIdx.x & 31) == 0) { comp_size[c] = r; status[c] = r ? RNSC_OK : RNSC_ERR_RC_RAW; }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32 * RC_WARPS) k_rc_decode(const uint8_t* comp, const uint64_t* comp_off, const uint32_t* n, const uint64_t* sample_off,
+                                                             uint32_t nchunks, int16_t* samples, int32_t* status)
+{
+    __shared__ RcModelSet models[RC_WARPS];
+    const uint32_t w = threadIdx.x >> 5;
+    for (uint32_t c = blockIdx.x * RC_WARPS + w; c < nchunks; c += gridDim.x * RC_WARPS) {
+        const int r = rc_decode_chunk(comp + comp_off[c], (uint32_t)(comp_off[c + 1] - comp_off[c]), n[c], samples + sample_off[c], &models[w]);
+        if ((threadIdx.x & 31) == 0) status[c] = r;
+        __syncwarp();
+    }
+}
+
+}  // namespace rnsc
