@@ -80,6 +80,12 @@ class Codec:
     def set_host_threads(self, n: int):
         self.lib.rnsc_set_host_threads(self.ctx, int(n))
 
+    def decode_class_counts(self, stream=None):
+        """(fast two-per-SM, fast one-per-SM, general decoder) chunk counts of the last whole-chunk decode."""
+        out = (C.c_uint32 * 3)()
+        self._check(self.lib.rnsc_decode_class_counts(self.ctx, out, C.c_void_p(int(stream.cuda_stream)) if stream is not None else C.c_void_p(0)))
+        return tuple(int(v) for v in out)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.rnsc_launch_count(self.ctx))

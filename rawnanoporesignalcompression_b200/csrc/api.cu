@@ -94,6 +94,33 @@ struct PinBuf {
 };
 
 constexpr size_t kDecodeSmem = 112 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
+constexpr size_t kFastSmemA = 113 * 1024;    // fast kernel, class A: two CTAs per SM
+constexpr size_t kFastSmemB = 227 * 1024;    // fast kernel, class B: one CTA per SM with the whole carve-out
+constexpr size_t kFastWs = (sizeof(FastWs<NT>) + 15) & ~(size_t)15;
+
+// Predefined sequence decoding tables (RFC 8878 3.1.1.3.2.2), entry = (newState << 16) | (nbBits << 8) | symbol,
+// laid out LL[64] OF[32] ML[64]; built once on the host with the same spread as fse_build (zstd_decode.cuh).
+void host_fse_build(uint32_t* t, const int16_t* norm, int nsym, int tl)
+{
+    const int size = 1 << tl; int high = size - 1; uint16_t next[64];
+    for (int s = 0; s < nsym; ++s) { if (norm[s] == -1) { t[high--] = (uint32_t)s; next[s] = 1; } else next[s] = (uint16_t)norm[s]; }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1; int pos = 0;
+    for (int s = 0; s < nsym; ++s)
+        for (int i = 0; i < norm[s]; ++i) { t[pos] = (uint32_t)s; pos = (pos + step) & mask; while (pos > high) pos = (pos + step) & mask; }
+    for (int u = 0; u < size; ++u) {
+        const uint32_t s = t[u] & 0xFF, ns = next[s]++;
+        int hb = 0; while ((ns >> (hb + 1)) != 0) ++hb;
+        const int nb = tl - hb;
+        t[u] = (((ns << nb) - (uint32_t)size) << 16) | ((uint32_t)nb << 8) | s;
+    }
+}
+void host_default_tables(uint32_t* tab /* 160 */)
+{
+    static const int16_t ll[36] = {4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1};
+    static const int16_t ml[53] = {1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1};
+    static const int16_t of[29] = {1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1};
+    host_fse_build(tab, ll, 36, 6); host_fse_build(tab + 64, of, 29, 5); host_fse_build(tab + 96, ml, 53, 6);
+}
 
 }  // namespace
 
@@ -105,6 +132,7 @@ struct rnsc_ctx {
     uint64_t launches = 0;
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
+    DevBuf d_plans, d_lists, d_deftab;
     PinBuf h_a, h_b;
 };
 
@@ -127,13 +155,31 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     const size_t stride = ((LIT_SCRATCH + 255) & ~(size_t)255) + spill;
     if (c->d_scratch.reserve(stride * (size_t)c->sm_count * 2)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(scratch %zu) failed", stride * (size_t)c->sm_count * 2);
     if (c->d_counter.reserve(256)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(counter) failed");
-    CUDA_OK(cudaMemsetAsync(c->d_counter.p, 0, 4, st));
+    if (c->d_plans.reserve(nchunks * sizeof(ChunkPlan)) || c->d_lists.reserve(3 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(plans) failed");
+    // counter words: [0..2] list lengths, [4] class B cursor, [5] class A cursor, [6] slow cursor
+    uint32_t* cnt = (uint32_t*)c->d_counter.p;
+    CUDA_OK(cudaMemsetAsync(cnt, 0, 32, st));
+    // 1. planner: one thread per chunk does every serial step (headers, Huffman tree descriptions, sequences)
+    PlanParams pp;
+    pp.comp = d_comp; pp.comp_off = d_comp_off; pp.n = d_n; pp.nchunks = (uint32_t)nchunks; pp.codec = codec;
+    pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
+    pp.region_a = (uint32_t)(kFastSmemA - kFastWs); pp.region_b = (uint32_t)(kFastSmemB - kFastWs); pp.deftab = (const uint32_t*)c->d_deftab.p;
+    RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
+    // 2. fast kernel over the two size classes (largest chunks first), 3. general decoder over what is left
+    FastParams fp;
+    fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
+    fp.plans = (const ChunkPlan*)c->d_plans.p;
+    fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_B * nchunks; fp.count = cnt + CLS_B; fp.counter = cnt + 4; fp.region_bytes = pp.region_b;
+    RNSC_LAUNCH(k_decode_fast<NT>, (int)std::min<size_t>((size_t)c->sm_count, nchunks), NT, kFastSmemB, st, fp);
+    fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_A * nchunks; fp.count = cnt + CLS_A; fp.counter = cnt + 5; fp.region_bytes = pp.region_a;
+    RNSC_LAUNCH(k_decode_fast<NT>, grid, NT, kFastSmemA, st, fp);
     DecodeParams p;
     p.comp = d_comp; p.comp_off = d_comp_off; p.n = d_n; p.sample_off = d_sample_off; p.samples = d_samples; p.status = d_status;
     p.nchunks = (uint32_t)nchunks; p.codec = codec; p.scratch = (uint8_t*)c->d_scratch.p; p.scratch_stride = stride;
-    p.counter = (uint32_t*)c->d_counter.p; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
+    p.counter = cnt + 6; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
+    p.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_SLOW * nchunks; p.count = cnt + CLS_SLOW;
     RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, st, p);
-    c->launches += 1;
+    c->launches += 4;
     CUDA_OK(cudaGetLastError());
     return RNSC_OK;
 }
@@ -202,7 +248,14 @@ rnsc_ctx* rnsc_create(int device)
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
     cudaError_t e2 = cudaFuncSetAttribute(k_svb_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SvbWs) + 16 + SVB_STAGE_BYTES));
+    cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemB);
+    if (e1 == cudaSuccess) e1 = e3;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return nullptr; }
+    uint32_t deftab[160];
+    host_default_tables(deftab);
+    if (c->d_deftab.reserve(sizeof deftab) || cudaMemcpy(c->d_deftab.p, deftab, sizeof deftab, cudaMemcpyHostToDevice) != cudaSuccess) {
+        c->d_deftab.release(); cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "upload of the predefined FSE tables failed"); return nullptr;
+    }
     unsigned hc = std::thread::hardware_concurrency();
     c->host_threads = hc ? (int)hc : 1;
     return c;
@@ -213,7 +266,7 @@ void rnsc_destroy(rnsc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux}) b->release();
+    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab}) b->release();
     c->h_a.release(); c->h_b.release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -240,6 +293,18 @@ int rnsc_dev_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_
     if (!c || !svb_codec_ok(codec) || (nchunks && (!d_comp || !d_comp_off || !d_n || !d_sample_off || !d_samples || !d_status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_decode: bad argument");
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     return launch_decode(c, codec, d_comp, d_comp_off, d_n, d_sample_off, nchunks, max_n, d_samples, d_status, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int rnsc_decode_class_counts(rnsc_ctx* c, uint32_t out[3], void* stream)
+{
+    if (!c || !out) return fail(RNSC_ERR_BAD_ARG, "rnsc_decode_class_counts: bad argument");
+    out[0] = out[1] = out[2] = 0;
+    if (!c->d_counter.p) return RNSC_OK;
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CUDA_OK(cudaMemcpyAsync(out, c->d_counter.p, 12, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return RNSC_OK;
 }
 
 int rnsc_dev_exclusive_scan_u32(rnsc_ctx* c, const uint32_t* d_in, size_t count, uint64_t* d_out, void* stream)

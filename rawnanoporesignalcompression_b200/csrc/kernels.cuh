@@ -3,6 +3,8 @@
 #include "zstd_decode.cuh"
 #include "svb_codec.cuh"
 #include "rc_codec.cuh"
+#include "plan.cuh"
+#include "fast_decode.cuh"
 
 namespace rnsc {
 
@@ -16,6 +18,7 @@ struct DecodeParams {
     uint8_t* scratch; unsigned long long scratch_stride;   // per-CTA global scratch: [literals 128K+64][stream spill]
     uint32_t* counter; uint32_t arena_bytes;               // shared-memory arena after the workspace
     uint32_t spill_bytes;                                  // bytes of stream spill space per CTA
+    const uint32_t* list; const uint32_t* count;           // optional: chunk indices to decode (planner's slow list)
 };
 
 constexpr uint32_t LIT_SCRATCH = ZSTD_BLOCK_MAX + 64;
@@ -57,7 +60,10 @@ __global__ void __launch_bounds__(NT, 2) k_decode_chunks(DecodeParams p)
     const int nf = codec_frames(p.codec);
     for (;;) {
         __syncthreads();
-        if (tid == 0) ctl->chunk = atomicAdd(p.counter, 1u);
+        if (tid == 0) {
+            const uint32_t i = atomicAdd(p.counter, 1u);
+            ctl->chunk = p.list ? (i < *p.count ? p.list[i] : 0xFFFFFFFFu) : i;
+        }
         __syncthreads();
         const uint32_t c = ctl->chunk;
         if (c >= p.nchunks) break;
@@ -128,6 +134,38 @@ __global__ void __launch_bounds__(NT, 2) k_decode_chunks(DecodeParams p)
         }
         __syncthreads();
         if (tid == 0) p.status[c] = ctl->status;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fast whole-chunk decode of planned chunks (plan.cuh, fast_decode.cuh). Persistent CTAs pull chunk indices of
+// one size class from the planner's list. The dynamic shared memory is [FastWs | region]; the region holds the
+// staged compressed chunk and every decoded stream.
+// ---------------------------------------------------------------------------------------------------
+template <int NTH>
+__global__ void __launch_bounds__(NTH, (NTH <= 512 ? 2 : 1)) k_decode_fast(FastParams P)
+{
+    RNSC_DYN_SMEM(smem);
+    FastWs<NTH>* ws = (FastWs<NTH>*)smem;
+    uint8_t* region = smem + ((sizeof(FastWs<NTH>) + 15) & ~(size_t)15);
+    const int tid = threadIdx.x;
+    if (tid == 0) mbar_init(&ws->mbar, 1);
+    uint32_t parity = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { const uint32_t i = atomicAdd(P.counter, 1u); ws->chunk = i < *P.count ? P.list[i] : 0xFFFFFFFFu; }
+        __syncthreads();
+        const uint32_t c = ws->chunk;
+        if (c == 0xFFFFFFFFu) break;
+        fast_decode_chunk<NTH>(ws, region, P, c, parity);
+        parity ^= 1u;
+        const uint32_t n = P.n[c];
+        if (ws->status == RNSC_OK && n > 0) {
+            const int r = unpack_any(P.codec, ws->view, n, P.samples + P.sample_off[c], &ws->svb);
+            if (r && tid == 0) ws->status = r;
+        }
+        __syncthreads();
+        if (tid == 0) P.status[c] = ws->status;
     }
 }
 

@@ -1,0 +1,285 @@
+// plan.cuh -- the PLANNER: everything in a chunk's zstd frames that is inherently serial, run as one GPU
+// thread per chunk so that the serial chains of ~10^5 chunks overlap each other instead of stalling a CTA.
+//
+// Per chunk it walks the pgnano container (A.1-A.8: u64 size prefixes) and, per frame, the zstd frame /
+// block / literals / sequences headers (RFC 8878 3.1.1), decodes the Huffman tree description (direct or
+// FSE-compressed weights) into a table *recipe*, and decodes the (few) sequences of the frame when their
+// tables are predefined or RLE. The result is a fixed-size ChunkPlan in global memory that the fast decode
+// kernel (fast_decode.cuh) consumes with no serial work left. Anything unusual (multi-block frames,
+// treeless literals, FSE-compressed sequence tables, too many sequences, inconsistent sizes) is not an error
+// here: the chunk is routed to the general CTA-cooperative decoder (zstd_decode.cuh, k_decode_chunks), which
+// owns the exact error semantics. Replaces, with the fast kernel, the reference's ZSTD_getFrameContentSize +
+// ZSTD_decompress calls (signal_compression.cpp:103,117; C5.hpp:494-565,588-655).
+#pragma once
+#include "zstd_decode.cuh"
+
+namespace rnsc {
+
+constexpr int PLAN_MAX_SEQ = 128;     // sequences of all frames of a chunk kept inline in the plan
+constexpr int PLAN_MAX_HUF = 3;       // Huffman-coded literal sections per chunk described in the plan
+constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
+constexpr uint32_t REGION_HEAD = 16;  // readable bytes in front of the staged chunk (bit-window over-read)
+
+enum : uint32_t { FK_RAW = 0, FK_RLE = 1, FK_COMP = 2 };
+enum : uint32_t { CLS_A = 0, CLS_B = 1, CLS_SLOW = 2, CLS_DONE = 3 };
+
+struct FramePlan {
+    uint32_t kind, fcs;          // block type of the frame's single block; decoded size
+    uint32_t data_off;           // RAW: chunk offset of the bytes; RLE: the byte value
+    uint32_t dst_off;            // region offset of the decoded output (RLE, COMP unless zero-copy)
+    uint32_t ltype, regen;       // literals: 0 raw, 1 RLE, 2 Huffman; count
+    uint32_t lit_off;            // raw literals: chunk offset; RLE literals: the byte value
+    uint32_t lit_dst;            // region offset of the literal buffer (Huffman/RLE literals with sequences)
+    uint32_t nstreams, huf;      // Huffman: 1 or 4 streams; index of the HufPlan
+    uint32_t nseq, seq_base;     // sequences [seq_base, seq_base + nseq) of ChunkPlan::seq
+    uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
+};
+struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decoding table
+    uint32_t log;                // table log (max code length), <= 12
+    uint16_t cls_start[14];      // first table entry of weight class w (1..log); cls_start[log+1] = 2^log
+    uint16_t cls_sym[14];        // index into sorted[] of the first symbol of class w
+    uint8_t sorted[256];         // symbols of weight > 0 ordered by (weight, symbol)
+};
+struct ChunkPlan {
+    uint32_t cls, nhuf, need, phase, stage_bytes, nseq, pad0, pad1;
+    FramePlan f[5];
+    HufPlan h[PLAN_MAX_HUF];
+    uint32_t seq[PLAN_MAX_SEQ * 3];  // (literal length, match length, offset) triples
+};
+
+struct PlanParams {
+    const uint8_t* comp; const uint64_t* comp_off; const uint32_t* n; uint32_t nchunks; int codec;
+    ChunkPlan* plans; int32_t* status;
+    uint32_t* lists;             // 3 lists of nchunks chunk indices: class A, class B, slow
+    uint32_t* counts;            // [0..2] list lengths (atomic), zeroed before the launch
+    uint32_t region_a, region_b; // bytes of dynamic region available to a class A / class B CTA
+    const uint32_t* deftab;      // predefined FSE decoding tables: LL[64] OF[32] ML[64]
+};
+
+// Per planner thread scratch in shared memory. 225 words: an odd stride, so the same field of the 32 threads
+// of a warp falls into 32 different banks.
+struct PlanScratch {
+    uint8_t weights[256]; uint32_t fse_w[64]; int16_t norm[64]; uint16_t next16[64]; uint32_t rank_start[16]; uint32_t tmp[16]; int huf_log;
+};
+static_assert(sizeof(PlanScratch) == 900, "PlanScratch layout");
+
+__device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+
+// Decodes `nseq` sequences with predefined/RLE tables. Returns 0 on success.
+__device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, uint32_t modes, const uint32_t* rle_sym,
+                                     const uint32_t* deftab, uint32_t regen, uint32_t fcs, uint32_t* out)
+{
+    const uint32_t* tll = deftab; const uint32_t* tof = deftab + 64; const uint32_t* tml = deftab + 96;
+    const int ll_log = ((modes >> 6) & 3) ? 0 : 6, of_log = ((modes >> 4) & 3) ? 0 : 5, ml_log = ((modes >> 2) & 3) ? 0 : 6;
+    BwdBits b;
+    if (bwd_init(b, bs, bs_size)) return 1;
+    uint32_t sl = bwd_read(b, ll_log), so = bwd_read(b, of_log), sm = bwd_read(b, ml_log);
+    uint32_t rep0 = 1, rep1 = 4, rep2 = 8, op = 0, lp = 0;
+    for (uint32_t i = 0; i < nseq; ++i) {
+        const uint32_t el = ll_log ? tll[sl] : rle_sym[0], eo = of_log ? tof[so] : rle_sym[1], em = ml_log ? tml[sm] : rle_sym[2];
+        const uint32_t llc = el & 0xFF, ofc = eo & 0xFF, mlc = em & 0xFF;
+        if (llc > 35 || mlc > 52 || ofc > 31) return 1;
+        const uint32_t ofv = (1u << ofc) + bwd_read(b, (int)ofc);
+        const uint32_t ml = kMLBase[mlc] + bwd_read(b, kMLBits[mlc]);
+        const uint32_t ll = kLLBase[llc] + bwd_read(b, kLLBits[llc]);
+        uint32_t offset;
+        if (ofv > 3) { offset = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = offset; }
+        else {
+            const uint32_t idx = ofv - 1 + (ll == 0);
+            if (idx == 0) offset = rep0;
+            else {
+                offset = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
+                if (offset == 0) return 1;
+                if (idx > 1) rep2 = rep1;
+                rep1 = rep0; rep0 = offset;
+            }
+        }
+        if (i + 1 < nseq) {
+            sl = (el >> 16) + bwd_read(b, (int)((el >> 8) & 0xFF));
+            sm = (em >> 16) + bwd_read(b, (int)((em >> 8) & 0xFF));
+            so = (eo >> 16) + bwd_read(b, (int)((eo >> 8) & 0xFF));
+        }
+        if (b.overflow) return 1;
+        if (lp + ll > regen || op + ll + ml > fcs || offset > op + ll) return 1;
+        op += ll + ml; lp += ll;
+        out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = offset;
+    }
+    if (b.bitpos != 0) return 1;
+    if (op + (regen - lp) != fcs) return 1;
+    return 0;
+}
+
+// Plans one compressed block (the only block of its frame). Returns 0 = planned, 1 = route to the slow path.
+__device__ inline int plan_block(const uint8_t* chunk, uint32_t boff, uint32_t size, FramePlan& fp, ChunkPlan* pl, uint32_t& nhuf, uint32_t& nseq_tot,
+                                 PlanScratch* sc, const uint32_t* deftab)
+{
+    const uint8_t* src = chunk + boff;
+    if (size < 1) return 1;
+    const uint32_t b0 = ldg8(src);
+    const uint32_t ltype = b0 & 3, sf = (b0 >> 2) & 3;
+    uint32_t lhs = 0, regen = 0, comp = 0, nstreams = 1;
+    if (ltype == 3) return 1;                       // treeless literals need a previous block's table
+    if (ltype < 2) {
+        if (sf == 0 || sf == 2) { lhs = 1; regen = b0 >> 3; }
+        else if (sf == 1) { if (size < 2) return 1; lhs = 2; regen = (b0 >> 4) | (ldg8(src + 1) << 4); }
+        else { if (size < 3) return 1; lhs = 3; regen = (b0 >> 4) | (ldg8(src + 1) << 4) | (ldg8(src + 2) << 12); }
+    } else {
+        if (size < 3) return 1;
+        uint64_t h = 0; for (uint32_t i = 0; i < 5 && i < size; ++i) h |= (uint64_t)ldg8(src + i) << (8 * i);
+        if (sf == 0 || sf == 1) { lhs = 3; regen = (uint32_t)(h >> 4) & 0x3FF; comp = (uint32_t)(h >> 14) & 0x3FF; nstreams = sf ? 4 : 1; }
+        else if (sf == 2) { lhs = 4; regen = (uint32_t)(h >> 4) & 0x3FFF; comp = (uint32_t)(h >> 18) & 0x3FFF; nstreams = 4; }
+        else { if (size < 5) return 1; lhs = 5; regen = (uint32_t)(h >> 4) & 0x3FFFF; comp = (uint32_t)(h >> 22) & 0x3FFFF; nstreams = 4; }
+    }
+    if (regen > ZSTD_BLOCK_MAX) return 1;
+    const uint32_t lit_section = lhs + (ltype == 0 ? regen : (ltype == 1 ? 1 : comp));
+    if (lit_section >= size) return 1;              // the sequences header needs at least one byte
+    // ---- sequences header ----
+    uint32_t nseq = 0, modes = 0, so = lit_section;
+    const uint32_t n0 = ldg8(src + so);
+    if (n0 == 0) { so += 1; if (so != size) return 1; }
+    else {
+        if (n0 < 128) { nseq = n0; so += 1; }
+        else if (n0 < 255) { if (so + 2 > size) return 1; nseq = ((n0 - 128) << 8) + ldg8(src + so + 1); so += 2; }
+        else { if (so + 3 > size) return 1; nseq = ldg8(src + so + 1) + (ldg8(src + so + 2) << 8) + 0x7F00; so += 3; }
+        if (so >= size) return 1;
+        modes = ldg8(src + so); so += 1;
+        if (modes & 3) return 1;
+    }
+    if (nseq == 0 && regen != fp.fcs) return 1;
+    fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = nseq_tot;
+    fp.lit_off = ltype == 0 ? boff + lhs : (ltype == 1 ? ldg8(src + lhs) : 0);
+    // ---- Huffman tree description + stream geometry ----
+    if (ltype == 2) {
+        if (nhuf >= PLAN_MAX_HUF) return 1;
+        uint32_t p = lhs, left = comp; int nw = 0;
+        const uint32_t u = huf_read_weights(sc, src + p, left, &nw);
+        if (!u) return 1;
+        p += u; left -= u;
+        uint32_t sz[4];
+        if (nstreams == 1) { sz[0] = left; fp.s_beg[0] = boff + p; }
+        else {
+            if (left < 6) return 1;
+            sz[0] = ldg8(src + p) | (ldg8(src + p + 1) << 8); sz[1] = ldg8(src + p + 2) | (ldg8(src + p + 3) << 8); sz[2] = ldg8(src + p + 4) | (ldg8(src + p + 5) << 8);
+            if (6 + sz[0] + sz[1] + sz[2] > left) return 1;
+            sz[3] = left - 6 - sz[0] - sz[1] - sz[2];
+            if (3 * ((regen + 3) / 4) > regen) return 1;
+            fp.s_beg[0] = boff + p + 6; fp.s_beg[1] = fp.s_beg[0] + sz[0]; fp.s_beg[2] = fp.s_beg[1] + sz[1]; fp.s_beg[3] = fp.s_beg[2] + sz[2];
+        }
+        for (uint32_t j = 0; j < nstreams; ++j) {
+            if (sz[j] == 0) return 1;
+            const uint32_t last = ldg8(chunk + fp.s_beg[j] + sz[j] - 1);
+            if (last == 0) return 1;
+            fp.s_tbits[j] = 8 * (sz[j] - 1) + (uint32_t)highbit32(last);
+        }
+        // table recipe: weight classes in ascending weight (= descending code length), symbols in natural order
+        HufPlan* hp = &pl->h[nhuf];
+        const int maxBits = sc->huf_log;
+        for (int k = 0; k < 16; ++k) sc->tmp[k] = 0;
+        for (int i = 0; i < nw; ++i) sc->tmp[sc->weights[i]]++;
+        uint32_t e = 0, s = 0;
+        for (int k = 1; k <= maxBits; ++k) {
+            hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s;
+            const uint32_t cnt = sc->tmp[k];
+            sc->tmp[k] = s;                          // running insert position of class k
+            e += cnt << (k - 1); s += cnt;
+        }
+        hp->cls_start[0] = 0; hp->cls_sym[0] = 0;
+        for (int k = maxBits + 1; k < 14; ++k) { hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s; }   // e == 2^maxBits
+        for (int i = 0; i < nw; ++i) { const uint32_t w = sc->weights[i]; if (w) hp->sorted[sc->tmp[w]++] = (uint8_t)i; }
+        hp->log = (uint32_t)maxBits;
+        fp.huf = nhuf++;
+    }
+    // ---- sequences (predefined / RLE tables only) ----
+    if (nseq) {
+        if (nseq_tot + nseq > PLAN_MAX_SEQ) return 1;
+        uint32_t rle[3] = {0, 0, 0};
+        uint32_t p = so;
+        for (int t = 0; t < 3; ++t) {               // order in the stream: LL, OF, ML
+            const uint32_t mode = (modes >> (6 - 2 * t)) & 3;
+            if (mode > 1) return 1;                 // FSE-compressed / repeat tables: general decoder
+            if (mode == 1) {
+                if (p >= size) return 1;
+                const uint32_t sym = ldg8(src + p); p += 1;
+                if (sym > (t == 0 ? 35u : (t == 1 ? 31u : 52u))) return 1;
+                rle[t] = sym;
+            }
+        }
+        if (p >= size) return 1;
+        if (plan_sequences(src + p, size - p, nseq, modes, rle, deftab, regen, fp.fcs, pl->seq + 3 * nseq_tot)) return 1;
+        nseq_tot += nseq;
+    }
+    return 0;
+}
+
+__device__ inline void plan_emit(const PlanParams& P, uint32_t c, uint32_t cls)
+{
+    P.plans[c].cls = cls;
+    if (cls <= CLS_SLOW) { const uint32_t i = atomicAdd(P.counts + cls, 1u); P.lists[(size_t)cls * P.nchunks + i] = c; }
+}
+
+__device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* sc, const uint32_t* deftab)
+{
+    ChunkPlan* pl = P.plans + c;
+    const uint8_t* src = P.comp + P.comp_off[c];
+    const uint32_t clen = (uint32_t)(P.comp_off[c + 1] - P.comp_off[c]);
+    const uint32_t n = P.n[c];
+    const int nf = codec_frames(P.codec);
+    const uint64_t bound = stream_bound(P.codec, n);
+    const uint32_t phase = (uint32_t)((uintptr_t)src & 15u);
+    const uint32_t stage = align16(phase + clen);
+    uint32_t region = REGION_HEAD + stage + 16, pos = 0, nhuf = 0, nseq_tot = 0;
+    int st = RNSC_OK; bool slow = false;
+    for (int f = 0; f < nf; ++f) {
+        uint32_t fl;
+        if (f + 1 < nf) {
+            if (pos + 8 > clen) { st = RNSC_ERR_CONTAINER; break; }
+            unsigned long long v = 0; for (int i = 0; i < 8; ++i) v |= (unsigned long long)ldg8(src + pos + i) << (8 * i);
+            pos += 8;
+            if (v > clen - pos) { st = RNSC_ERR_CONTAINER; break; }
+            fl = (uint32_t)v;
+        } else fl = clen - pos;
+        uint32_t hdr, known, ck; uint64_t fcs;
+        const int r = zstd_parse_frame_header(src + pos, fl, &hdr, &fcs, &known, &ck);
+        if (r || !known) { st = RNSC_ERR_NOT_ZSTD; break; }          // ZSTD_getFrameContentSize must succeed
+        if (fcs > bound) { st = RNSC_ERR_REMAINING; break; }
+        FramePlan fp;
+        fp.kind = FK_RAW; fp.fcs = (uint32_t)fcs; fp.data_off = 0; fp.dst_off = 0; fp.ltype = 0; fp.regen = 0; fp.lit_off = 0; fp.lit_dst = 0;
+        fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0;
+        for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; }
+        if (!slow) {
+            if (hdr + 3 > fl) slow = true;
+            else {
+                const uint32_t bh = ldg8(src + pos + hdr) | (ldg8(src + pos + hdr + 1) << 8) | (ldg8(src + pos + hdr + 2) << 16);
+                const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
+                const uint32_t body = type == 1 ? 1u : bsz;
+                if (!last || type == 3 || hdr + 3 + body + (ck ? 4 : 0) != fl) slow = true;
+                else if (type == 0) { if (bsz != (uint32_t)fcs) slow = true; fp.kind = FK_RAW; fp.data_off = pos + hdr + 3; }
+                else if (type == 1) { if (bsz != (uint32_t)fcs) slow = true; fp.kind = FK_RLE; fp.data_off = ldg8(src + pos + hdr + 3); }
+                else { fp.kind = FK_COMP; fp.data_off = pos + hdr + 3; if (plan_block(src, pos + hdr + 3, bsz, fp, pl, nhuf, nseq_tot, sc, deftab)) slow = true; }
+            }
+        }
+        if (!slow) {
+            // placement in the CTA's dynamic region: decoded output, then the literal buffer if sequences follow
+            const bool zero_copy = fp.kind == FK_RAW || (fp.kind == FK_COMP && fp.ltype == 0 && fp.nseq == 0);
+            if (!zero_copy) { fp.dst_off = region; region += align16(fp.fcs) + 16; }
+            if (fp.kind == FK_COMP && fp.nseq && fp.ltype != 0) { fp.lit_dst = region; region += align16(fp.regen) + 16; }
+            pl->f[f] = fp;
+        }
+        pos += fl;
+    }
+    if (st != RNSC_OK) { P.status[c] = st; plan_emit(P, c, CLS_DONE); return; }
+    pl->nhuf = nhuf; pl->need = region; pl->phase = phase; pl->stage_bytes = stage; pl->nseq = nseq_tot;
+    plan_emit(P, c, slow ? CLS_SLOW : (region <= P.region_a ? CLS_A : (region <= P.region_b ? CLS_B : CLS_SLOW)));
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS) k_plan_chunks(PlanParams P)
+{
+    __shared__ PlanScratch scratch[PLAN_THREADS];
+    __shared__ uint32_t deftab[160];
+    for (int i = threadIdx.x; i < 160; i += PLAN_THREADS) deftab[i] = P.deftab[i];
+    __syncthreads();
+    const uint32_t c = blockIdx.x * PLAN_THREADS + threadIdx.x;
+    if (c < P.nchunks) plan_chunk(P, c, &scratch[threadIdx.x], deftab);
+}
+
+}  // namespace rnsc

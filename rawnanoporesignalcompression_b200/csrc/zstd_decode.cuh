@@ -153,7 +153,8 @@ __device__ inline uint32_t bwd_read(BwdBits& b, int n)
 // Huffman: tree description (thread 0), table build (CTA), parallel stream decode (CTA)
 // ---------------------------------------------------------------------------------------------------
 // Reads the Huffman tree description into ws->weights; returns bytes consumed (0 = error) and *nw.
-__device__ inline uint32_t huf_read_weights(ZstdWs* ws, const uint8_t* src, uint32_t size, int* nw_out)
+template <typename WS>
+__device__ inline uint32_t huf_read_weights(WS* ws, const uint8_t* src, uint32_t size, int* nw_out)
 {
     uint8_t* w = ws->weights; int nw = 0;
     if (size < 1) return 0;
