@@ -96,7 +96,8 @@ struct PinBuf {
 constexpr size_t kDecodeSmem = 112 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 constexpr size_t kFastSmemA = 113 * 1024;    // fast kernel, class A: two CTAs per SM
 constexpr size_t kFastSmemB = 227 * 1024;    // fast kernel, class B: one CTA per SM with the whole carve-out
-constexpr size_t kFastWs = (sizeof(FastWs<NT>) + 15) & ~(size_t)15;
+constexpr size_t kFastWsA = (sizeof(FastWs<512>) + 15) & ~(size_t)15;
+constexpr size_t kFastWsB = (sizeof(FastWs<1024>) + 15) & ~(size_t)15;
 
 // Predefined sequence decoding tables (RFC 8878 3.1.1.3.2.2), entry = (newState << 16) | (nbBits << 8) | symbol,
 // laid out LL[64] OF[32] ML[64]; built once on the host with the same spread as fse_build (zstd_decode.cuh).
@@ -163,16 +164,16 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     PlanParams pp;
     pp.comp = d_comp; pp.comp_off = d_comp_off; pp.n = d_n; pp.nchunks = (uint32_t)nchunks; pp.codec = codec;
     pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
-    pp.region_a = (uint32_t)(kFastSmemA - kFastWs); pp.region_b = (uint32_t)(kFastSmemB - kFastWs); pp.deftab = (const uint32_t*)c->d_deftab.p;
+    pp.region_a = (uint32_t)(kFastSmemA - kFastWsA); pp.region_b = (uint32_t)(kFastSmemB - kFastWsB); pp.deftab = (const uint32_t*)c->d_deftab.p;
     RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
     // 2. fast kernel over the two size classes (largest chunks first), 3. general decoder over what is left
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
     fp.plans = (const ChunkPlan*)c->d_plans.p;
     fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_B * nchunks; fp.count = cnt + CLS_B; fp.counter = cnt + 4; fp.region_bytes = pp.region_b;
-    RNSC_LAUNCH(k_decode_fast<NT>, (int)std::min<size_t>((size_t)c->sm_count, nchunks), NT, kFastSmemB, st, fp);
+    RNSC_LAUNCH(k_decode_fast<1024>, (int)std::min<size_t>((size_t)c->sm_count, nchunks), 1024, kFastSmemB, st, fp);
     fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_A * nchunks; fp.count = cnt + CLS_A; fp.counter = cnt + 5; fp.region_bytes = pp.region_a;
-    RNSC_LAUNCH(k_decode_fast<NT>, grid, NT, kFastSmemA, st, fp);
+    RNSC_LAUNCH(k_decode_fast<512>, grid, 512, kFastSmemA, st, fp);
     DecodeParams p;
     p.comp = d_comp; p.comp_off = d_comp_off; p.n = d_n; p.sample_off = d_sample_off; p.samples = d_samples; p.status = d_status;
     p.nchunks = (uint32_t)nchunks; p.codec = codec; p.scratch = (uint8_t*)c->d_scratch.p; p.scratch_stride = stride;
@@ -248,7 +249,9 @@ rnsc_ctx* rnsc_create(int device)
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
     cudaError_t e2 = cudaFuncSetAttribute(k_svb_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SvbWs) + 16 + SVB_STAGE_BYTES));
-    cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemB);
+    cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemB);
+    if (e1 == cudaSuccess) e1 = e3;
+    e3 = cudaFuncSetAttribute(k_decode_fast<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemA);
     if (e1 == cudaSuccess) e1 = e3;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return nullptr; }
     uint32_t deftab[160];

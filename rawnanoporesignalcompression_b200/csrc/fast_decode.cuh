@@ -12,6 +12,7 @@
 #pragma once
 #include "plan.cuh"
 #include "svb_codec.cuh"
+#include "svb_unpack2.cuh"
 
 namespace rnsc {
 
@@ -31,7 +32,7 @@ struct FastWs {
     uint16_t huf[2][1 << HUF_LOG_MAX];                     // (nbBits << 8) | symbol
     uint32_t sub_start[NTH], sub_end[NTH], sub_cnt[NTH];
     uint32_t scan_a[NTH / 32 + 1];
-    SvbWs svb;
+    Unpack2Ws<NTH> u2;
     FramePlan f[5];
     HufPlan h[2];
     uint32_t seq[PLAN_MAX_SEQ * 3];
@@ -166,7 +167,7 @@ __device__ inline int fast_huffman_round(FastWs<NTH>* ws, const uint32_t* words,
         __syncthreads();
     }
     uint32_t total;
-    const uint32_t ex = block_exclusive_scan<uint32_t>(active ? my_cnt : 0u, ws->scan_a, &total);
+    const uint32_t ex = block_scan_1b<uint32_t, NTH>(active ? my_cnt : 0u, ws->scan_a, &total);
     if (active && k == 0) ws->st_base[j] = ex;
     __syncthreads();
     const uint32_t off = ex - ws->st_base[j];

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NTH, (NTH <= 512 ? 2 : 1)) k_decode_fast(FastP
         parity ^= 1u;
         const uint32_t n = P.n[c];
         if (ws->status == RNSC_OK && n > 0) {
-            const int r = unpack_any(P.codec, ws->view, n, P.samples + P.sample_off[c], &ws->svb);
+            const int r = unpack2_any<NTH>(P.codec, ws->view, n, P.samples + P.sample_off[c], &ws->u2);
             if (r && tid == 0) ws->status = r;
         }
         __syncthreads();

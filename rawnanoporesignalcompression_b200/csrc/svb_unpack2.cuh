@@ -1,0 +1,213 @@
+// svb_unpack2.cuh -- splitter inverse (streams -> int16 samples), second generation.
+//
+// Same arithmetic as svb_unpack (svb_codec.cuh; reference decode_scalar_* loops cited there), organised for
+// instruction count:
+//   * a thread owns U2_SPT = 16 consecutive samples chosen so that they are two 16-byte aligned segments of the
+//     OUTPUT: results go from registers to global memory with two 128-bit stores, no shared-memory tile;
+//   * key bits and the thread's payload bytes/nibbles are fetched as aligned 32-bit words and funnel-shifted
+//     into register windows (C4/C5), so the per-sample work is predicates, shifts and adds, no loads;
+//   * stream positions and the delta^-1 prefix sum use one-barrier CTA scans (block_scan_1b).
+// Works on generic pointers: the streams may live in shared memory (fast decoder) or global memory.
+#pragma once
+#include "block_prims.cuh"
+
+namespace rnsc {
+
+constexpr int U2_SPT = 16;
+
+template <int NTH>
+struct Unpack2Ws {
+    unsigned long long s64[2][NTH / 32];
+    uint32_t s32[2][NTH / 32];
+    int err;
+};
+
+// Exclusive CTA scan with a single barrier: every warp redundantly scans the per-warp totals. `scratch` must
+// alternate between two buffers on consecutive calls.
+template <typename T, int NTH>
+__device__ __forceinline__ T block_scan_1b(T v, T* scratch, T* total)
+{
+    constexpr int NW = NTH / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T inc = warp_inclusive_scan(v);
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    const T w = lane < NW ? scratch[lane] : T(0);
+    const T winc = warp_inclusive_scan(w);
+    const T base = __shfl_sync(0xffffffffu, winc - w, warp);
+    *total = __shfl_sync(0xffffffffu, winc, NW - 1);
+    return base + inc - v;
+}
+
+__device__ __forceinline__ uint32_t ldw(uintptr_t a) { return *(const uint32_t*)a; }
+
+// 32 bits starting at bit `bit` of the byte stream p (any alignment). Reads the two aligned words that cover
+// them: up to 7 bytes past the last byte needed, never below the aligned word holding the first.
+__device__ __forceinline__ uint32_t load_bits32(const uint8_t* p, uint32_t bit)
+{
+    const uintptr_t a = (uintptr_t)p + (bit >> 3), al = a & ~(uintptr_t)3;
+    const uint32_t sh = ((uint32_t)(a & 3) << 3) + (bit & 7);
+    return __funnelshift_r(ldw(al), ldw(al + 4), sh);
+}
+__device__ __forceinline__ void load_bits64(const uint8_t* p, uint32_t bit, uint32_t& lo, uint32_t& hi)
+{
+    const uintptr_t a = (uintptr_t)p + (bit >> 3), al = a & ~(uintptr_t)3;
+    const uint32_t sh = ((uint32_t)(a & 3) << 3) + (bit & 7);
+    const uint32_t w0 = ldw(al), w1 = ldw(al + 4), w2 = ldw(al + 8);
+    lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
+}
+
+__device__ __forceinline__ uint32_t zz_dec(uint32_t z) { return (z >> 1) ^ (0u - (z & 1u)); }   // low 16 bits are the delta
+
+// v[0] = keys, v[1..4] = payload streams in wire order. Returns an rnsc_status (same in every thread).
+template <int CODEC, int NTH>
+__device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
+{
+    constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
+    constexpr bool WIN = (CODEC == RNSC_C4 || CODEC == RNSC_C5);       // register-window fast path
+    constexpr int KB = TWO ? 2 : 1;
+    constexpr int S = U2_SPT;
+    const int tid = threadIdx.x;
+    if (tid == 0) ws->err = 0;
+    const uint8_t* keys = v[0].p;
+    const uint8_t *s1 = v[1].p, *s2 = v[2].p, *s3 = v[3].p, *s4 = v[4].p;
+    const uint32_t l1 = v[1].len, l2 = v[2].len, l3 = v[3].len, l4 = v[4].len;
+    const uint32_t ph = (uint32_t)(((uintptr_t)out >> 1) & 7);        // samples past a 16-byte boundary
+    int16_t* outa = out - ph;                                          // 16-byte aligned; virtual sample vi <-> outa[vi]
+    const uint32_t nv = n + ph;
+    uint32_t run1 = 0, run2 = 0, run3 = 0, carry = 0;
+    bool oob = false;
+    int flip = 0;
+    __syncthreads();
+    for (uint32_t tb = 0; tb < nv; tb += NTH * S, flip ^= 1) {
+        const uint32_t v0 = tb + (uint32_t)tid * S;
+        const uint32_t vlo = max(v0, ph), vhi = min(v0 + S, nv);
+        const uint32_t cnt = vhi > vlo ? vhi - vlo : 0, jlo = cnt ? vlo - v0 : 0;
+        // ---- key bits of my valid samples, at slot positions jlo.. ----
+        uint32_t kb = 0;
+        if (cnt) {
+            kb = load_bits32(keys, KB * (vlo - ph));
+            if (KB * cnt < 32) kb &= (1u << (KB * cnt)) - 1u;
+            kb <<= KB * jlo;
+        }
+        // ---- unit counts -> stream positions ----
+        uint32_t c1 = 0, c2 = 0, c3 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (TWO) {
+            const uint32_t lo = kb & 0x55555555u, hi = (kb >> 1) & 0x55555555u;
+            m1 = lo & ~hi; m2 = hi & ~lo; m3 = lo & hi;
+            const uint32_t n1 = __popc(m1), n2 = __popc(m2), n3 = __popc(m3);
+            if (CODEC == RNSC_VBZ0) c1 = n1 + 2 * n2 + 4 * n3; else { c1 = n1; c2 = n2; c3 = n3; }
+        } else {
+            const uint32_t nl = __popc(kb);
+            if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) c1 = cnt + nl;
+            else if (CODEC == RNSC_C2) { c1 = cnt; c2 = nl; }
+            else { c2 = nl; c1 = cnt - nl; }
+        }
+        unsigned long long tot64;
+        const unsigned long long ex64 = block_scan_1b<unsigned long long, NTH>(
+            (unsigned long long)c1 | ((unsigned long long)c2 << 21) | ((unsigned long long)c3 << 42), ws->s64[flip], &tot64);
+        uint32_t p1 = run1 + (uint32_t)(ex64 & 0x1FFFFF), p2 = run2 + (uint32_t)((ex64 >> 21) & 0x1FFFFF), p3 = run3 + (uint32_t)(ex64 >> 42);
+        run1 += (uint32_t)(tot64 & 0x1FFFFF); run2 += (uint32_t)((tot64 >> 21) & 0x1FFFFF); run3 += (uint32_t)(tot64 >> 42);
+        // ---- one bounds check per thread instead of one per load (over-reads stay inside the padded buffers) ----
+        bool ok;
+        if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) ok = p1 + c1 <= l1;
+        else if (CODEC == RNSC_C2) ok = p1 + c1 <= l1 && p2 + c2 <= l2;
+        else if (CODEC == RNSC_C3) ok = p1 + c1 <= l1 && p2 + c2 <= l2 && p2 + c2 <= l3;
+        else if (CODEC == RNSC_VBZ0) ok = p1 + c1 <= 2 * l1;
+        else ok = p1 + c1 <= 2 * l1 && p2 + c2 <= l2 && p3 + c3 <= l3 && p3 + c3 <= l4;
+        if (!ok) { oob = true; kb = 0; m1 = m2 = m3 = 0; }
+        // ---- gather, zigzag^-1, thread-local running sum ----
+        uint32_t val[S]; uint32_t acc = 0;
+        if (WIN) {
+            uint32_t sw[2] = {0, 0}, mlo[2] = {0, 0}, mhi[2] = {0, 0};
+            if (cnt && ok) {
+                const uint32_t n1a = __popc(m1 & 0xFFFFu), n2a = __popc(m2 & 0xFFFFu);
+                sw[0] = load_bits32(s1, 4 * p1); sw[1] = load_bits32(s1, 4 * (p1 + n1a));
+                load_bits64(s2, 8 * p2, mlo[0], mhi[0]); load_bits64(s2, 8 * (p2 + n2a), mlo[1], mhi[1]);
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int h = j >> 3;
+                const bool isS = (m1 >> (2 * j)) & 1u, isM = (m2 >> (2 * j)) & 1u;
+                uint32_t z = 0;
+                if (isS) z = (sw[h] & 15u) + (CODEC == RNSC_C5 ? 1u : 0u);
+                if (isM) z = (mlo[h] & 255u) + (CODEC == RNSC_C5 ? 17u : 0u);
+                if (isS) sw[h] >>= 4;
+                if (isM) { mlo[h] = __funnelshift_r(mlo[h], mhi[h], 8); mhi[h] >>= 8; }
+                if ((m3 >> (2 * j)) & 1u) {      // rare: large value, low and high byte streams
+                    z = (((uint32_t)ld8(s4 + p3) << 8) + ld8(s3 + p3) + (CODEC == RNSC_C5 ? 273u : 0u)) & 0xFFFFu;
+                    ++p3;
+                }
+                acc += zz_dec(z);
+                val[j] = acc;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                uint32_t z = 0;
+                if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) {
+                    const uint32_t k = (kb >> j) & 1u;
+                    if ((uint32_t)j >= jlo && (uint32_t)j < jlo + cnt) { z = ld8(s1 + p1); if (k) z |= ld8(s1 + p1 + 1) << 8; p1 += 1 + k; }
+                } else if (CODEC == RNSC_C2) {
+                    const uint32_t k = (kb >> j) & 1u;
+                    if ((uint32_t)j >= jlo && (uint32_t)j < jlo + cnt) { z = ld8(s1 + p1); ++p1; if (k) { z |= ld8(s2 + p2) << 8; ++p2; } }
+                } else if (CODEC == RNSC_C3) {
+                    const uint32_t k = (kb >> j) & 1u;
+                    if ((uint32_t)j >= jlo && (uint32_t)j < jlo + cnt) {
+                        if (k) { z = ld8(s2 + p2) | (ld8(s3 + p2) << 8); ++p2; } else { z = ld8(s1 + p1); ++p1; }
+                    }
+                } else {   // VBZ0: 0/1/2/4 nibbles of one stream
+                    const uint32_t code = (kb >> (2 * j)) & 3u, nn = code == 3 ? 4u : code;
+                    uint32_t x = 0;
+                    for (uint32_t q = 0; q < nn; ++q) x |= ((ld8(s1 + ((p1 + q) >> 1)) >> (4 * ((p1 + q) & 1))) & 15u) << (4 * q);
+                    p1 += nn;
+                    z = code == 0 ? 0u : (x + (code == 1 ? 1u : (code == 2 ? 17u : 273u))) & 0xFFFFu;
+                }
+                acc += zz_dec(z);
+                val[j] = acc;
+            }
+        }
+        // ---- delta^-1: CTA scan of the per-thread sums (mod 2^16 arithmetic survives in 32 bits) ----
+        uint32_t tot32;
+        const uint32_t ex32 = block_scan_1b<uint32_t, NTH>(acc, ws->s32[flip], &tot32);
+        const uint32_t base = carry + ex32;
+        carry += tot32;
+        if (cnt == S) {
+            uint32_t w[S / 2];
+#pragma unroll
+            for (int q = 0; q < S / 2; ++q) w[q] = __byte_perm(base + val[2 * q], base + val[2 * q + 1], 0x5410);
+            V16* dst = (V16*)(outa + v0);
+            dst[0] = V16{w[0], w[1], w[2], w[3]};
+            dst[1] = V16{w[4], w[5], w[6], w[7]};
+        } else if (cnt) {
+#pragma unroll
+            for (int j = 0; j < S; ++j) if ((uint32_t)j >= jlo && (uint32_t)j < jlo + cnt) outa[v0 + j] = (int16_t)(uint16_t)(base + val[j]);
+        }
+    }
+    // ---- the reference's "Remaining data at end of signal buffer" test (A.8) + out-of-bounds guard ----
+    bool rem;
+    if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) rem = run1 != l1;
+    else if (CODEC == RNSC_VBZ0) rem = ((run1 + 1) >> 1) != l1;
+    else if (CODEC == RNSC_C2) rem = run2 != l2;
+    else if (CODEC == RNSC_C3) rem = run2 != l3;
+    else rem = run3 != l4;
+    if (oob || (tid == 0 && rem)) ws->err = RNSC_ERR_REMAINING;
+    __syncthreads();
+    return ws->err;
+}
+
+template <int NTH>
+__device__ inline int unpack2_any(int codec, const View* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
+{
+    switch (codec) {
+    case RNSC_VBZ: return svb_unpack2<RNSC_VBZ, NTH>(v, n, out, ws);
+    case RNSC_VBZ0: return svb_unpack2<RNSC_VBZ0, NTH>(v, n, out, ws);
+    case RNSC_C1: return svb_unpack2<RNSC_C1, NTH>(v, n, out, ws);
+    case RNSC_C2: return svb_unpack2<RNSC_C2, NTH>(v, n, out, ws);
+    case RNSC_C3: return svb_unpack2<RNSC_C3, NTH>(v, n, out, ws);
+    case RNSC_C4: return svb_unpack2<RNSC_C4, NTH>(v, n, out, ws);
+    default: return svb_unpack2<RNSC_C5, NTH>(v, n, out, ws);
+    }
+}
+
+}  // namespace rnsc
