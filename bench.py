@@ -270,6 +270,7 @@ def run_rnsc(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local); sampler.start()     # clocks / throttle reasons over warm-up + timed region (all under load)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -278,7 +279,6 @@ def run_rnsc(args):
     log(f"chunk routing (fast 2/SM, fast 1/SM, general): {classes}")
     log(f"decode bit-exact vs generated samples: {bit_exact}")
 
-    sampler = ClockSampler(local); sampler.start()
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     l0 = cd.launch_count

@@ -134,6 +134,8 @@ struct rnsc_ctx {
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
     DevBuf d_plans, d_lists, d_deftab;
+    cudaStream_t side[2] = {nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
+    cudaEvent_t ev_plan = nullptr, ev_side[2] = {nullptr, nullptr};
     PinBuf h_a, h_b;
 };
 
@@ -171,15 +173,24 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
     fp.plans = (const ChunkPlan*)c->d_plans.p;
     fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_B * nchunks; fp.count = cnt + CLS_B; fp.counter = cnt + 4; fp.region_bytes = pp.region_b;
+    // Fork: class B (large chunks, one CTA per SM) stays on the caller's stream and is enqueued first; class A and the
+    // general decoder go to side streams and fill SMs as class B CTAs retire. Join before returning to the caller's stream.
+    CUDA_OK(cudaEventRecord(c->ev_plan, st));
     RNSC_LAUNCH(k_decode_fast<1024>, (int)std::min<size_t>((size_t)c->sm_count, nchunks), 1024, kFastSmemB, st, fp);
     fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_A * nchunks; fp.count = cnt + CLS_A; fp.counter = cnt + 5; fp.region_bytes = pp.region_a;
-    RNSC_LAUNCH(k_decode_fast<512>, grid, 512, kFastSmemA, st, fp);
+    CUDA_OK(cudaStreamWaitEvent(c->side[0], c->ev_plan, 0));
+    RNSC_LAUNCH(k_decode_fast<512>, grid, 512, kFastSmemA, c->side[0], fp);
+    CUDA_OK(cudaEventRecord(c->ev_side[0], c->side[0]));
     DecodeParams p;
     p.comp = d_comp; p.comp_off = d_comp_off; p.n = d_n; p.sample_off = d_sample_off; p.samples = d_samples; p.status = d_status;
     p.nchunks = (uint32_t)nchunks; p.codec = codec; p.scratch = (uint8_t*)c->d_scratch.p; p.scratch_stride = stride;
     p.counter = cnt + 6; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
     p.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_SLOW * nchunks; p.count = cnt + CLS_SLOW;
-    RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, st, p);
+    CUDA_OK(cudaStreamWaitEvent(c->side[1], c->ev_plan, 0));
+    RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, c->side[1], p);
+    CUDA_OK(cudaEventRecord(c->ev_side[1], c->side[1]));
+    CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[0], 0));
+    CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[1], 0));
     c->launches += 4;
     CUDA_OK(cudaGetLastError());
     return RNSC_OK;
@@ -247,6 +258,9 @@ rnsc_ctx* rnsc_create(int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed"); return nullptr; }
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
+    if (cudaStreamCreateWithFlags(&c->side[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->side[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_side[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_side[1], cudaEventDisableTiming) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
     cudaError_t e2 = cudaFuncSetAttribute(k_svb_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SvbWs) + 16 + SVB_STAGE_BYTES));
     cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemB);
@@ -271,6 +285,8 @@ void rnsc_destroy(rnsc_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab}) b->release();
     c->h_a.release(); c->h_b.release();
+    for (int i = 0; i < 2; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
+    if (c->ev_plan) cudaEventDestroy(c->ev_plan);
     cudaStreamDestroy(c->stream);
     delete c;
 }

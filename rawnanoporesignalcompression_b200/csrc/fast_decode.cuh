@@ -205,12 +205,32 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const FramePlan& fp,
         lit_pos[fp.nseq] = lp; out_pos[fp.nseq] = op;
     }
     __syncthreads();
-    const uint8_t* lit = fp.ltype == 0 ? chunk + fp.lit_off : region + fp.lit_dst;
-    for (uint32_t i = 0; i <= fp.nseq; ++i) {
-        const uint32_t len = i < fp.nseq ? sq[3 * i] : fp.regen - lit_pos[fp.nseq];
-        uint8_t* d = dst + out_pos[i];
-        if (fp.ltype == 1) for (uint32_t q = tid; q < len; q += NTH) d[q] = (uint8_t)fp.lit_off;
-        else { const uint8_t* s = lit + lit_pos[i]; for (uint32_t q = tid; q < len; q += NTH) d[q] = s[q]; }
+    if (fp.ltype == 2) {
+        // Huffman literals sit at dst[0 .. regen): move run i up by the match bytes in front of it, last run first.
+        // Source and destination overlap, so every block is read to registers, then written, between barriers.
+        constexpr uint32_t B = NTH * 16;
+        for (uint32_t i = fp.nseq; i >= 1; --i) {
+            const uint32_t len = i < fp.nseq ? sq[3 * i] : fp.regen - lit_pos[fp.nseq];
+            const uint8_t* s = dst + lit_pos[i]; uint8_t* d = dst + out_pos[i];
+            if (s == d) continue;
+            for (uint32_t done = 0; done < len; done += B) {
+                const uint32_t blen = min(B, len - done), b0 = len - done - blen;     // blocks from the top down
+                uint8_t t[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { const uint32_t q = tid + k * NTH; t[k] = q < blen ? s[b0 + q] : (uint8_t)0; }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { const uint32_t q = tid + k * NTH; if (q < blen) d[b0 + q] = t[k]; }
+                __syncthreads();
+            }
+        }
+    } else {
+        for (uint32_t i = 0; i <= fp.nseq; ++i) {
+            const uint32_t len = i < fp.nseq ? sq[3 * i] : fp.regen - lit_pos[fp.nseq];
+            uint8_t* d = dst + out_pos[i];
+            if (fp.ltype == 1) for (uint32_t q = tid; q < len; q += NTH) d[q] = (uint8_t)fp.lit_off;
+            else { const uint8_t* s = chunk + fp.lit_off + lit_pos[i]; for (uint32_t q = tid; q < len; q += NTH) d[q] = s[q]; }
+        }
     }
     __syncthreads();
     if (tid < 32) {
@@ -261,7 +281,7 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
             for (int f = 0; f < nf; ++f) {
                 const FramePlan& fp = ws->f[f];
                 if (fp.kind != FK_COMP || fp.ltype != 2 || fp.huf < r0 || fp.huf >= r0 + nt) continue;
-                const uint32_t q = (fp.regen + 3) / 4, out = fp.nseq ? fp.lit_dst : fp.dst_off;
+                const uint32_t q = (fp.regen + 3) / 4, out = fp.dst_off;
                 for (uint32_t j = 0; j < fp.nstreams; ++j) {
                     ws->st_tbits[nst] = fp.s_tbits[j];
                     ws->st_abit[nst] = 8 * (REGION_HEAD + phase + fp.s_beg[j]) + fp.s_tbits[j];

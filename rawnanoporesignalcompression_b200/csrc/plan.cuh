@@ -29,7 +29,7 @@ struct FramePlan {
     uint32_t dst_off;            // region offset of the decoded output (RLE, COMP unless zero-copy)
     uint32_t ltype, regen;       // literals: 0 raw, 1 RLE, 2 Huffman; count
     uint32_t lit_off;            // raw literals: chunk offset; RLE literals: the byte value
-    uint32_t lit_dst;            // region offset of the literal buffer (Huffman/RLE literals with sequences)
+    uint32_t lit_dst;            // unused (literals of a frame with sequences are decoded to the front of dst and moved in place)
     uint32_t nstreams, huf;      // Huffman: 1 or 4 streams; index of the HufPlan
     uint32_t nseq, seq_base;     // sequences [seq_base, seq_base + nseq) of ChunkPlan::seq
     uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
@@ -45,6 +45,7 @@ struct ChunkPlan {
     FramePlan f[5];
     HufPlan h[PLAN_MAX_HUF];
     uint32_t seq[PLAN_MAX_SEQ * 3];  // (literal length, match length, offset) triples
+    uint32_t fse[512 + 256 + 512];   // planner scratch: FSE-compressed LL / OF / ML decoding tables of the frame being planned
 };
 
 struct PlanParams {
@@ -59,24 +60,23 @@ struct PlanParams {
 // Per planner thread scratch in shared memory. 225 words: an odd stride, so the same field of the 32 threads
 // of a warp falls into 32 different banks.
 struct PlanScratch {
-    uint8_t weights[256]; uint32_t fse_w[64]; int16_t norm[64]; uint16_t next16[64]; uint32_t rank_start[16]; uint32_t tmp[16]; int huf_log;
+    uint8_t weights[256]; uint32_t fse_w[64]; int16_t norm[64]; uint16_t next16[64]; uint32_t rank_start[16]; uint32_t rank_cnt[16]; int huf_log;
 };
 static_assert(sizeof(PlanScratch) == 900, "PlanScratch layout");
 
 __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 
-// Decodes `nseq` sequences with predefined/RLE tables. Returns 0 on success.
-__device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, uint32_t modes, const uint32_t* rle_sym,
-                                     const uint32_t* deftab, uint32_t regen, uint32_t fcs, uint32_t* out)
+// Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
+// an FSE description). Returns 0 on success.
+__device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, const uint32_t* tll, int ll_log, const uint32_t* tof, int of_log,
+                                     const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out)
 {
-    const uint32_t* tll = deftab; const uint32_t* tof = deftab + 64; const uint32_t* tml = deftab + 96;
-    const int ll_log = ((modes >> 6) & 3) ? 0 : 6, of_log = ((modes >> 4) & 3) ? 0 : 5, ml_log = ((modes >> 2) & 3) ? 0 : 6;
     BwdBits b;
     if (bwd_init(b, bs, bs_size)) return 1;
     uint32_t sl = bwd_read(b, ll_log), so = bwd_read(b, of_log), sm = bwd_read(b, ml_log);
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8, op = 0, lp = 0;
     for (uint32_t i = 0; i < nseq; ++i) {
-        const uint32_t el = ll_log ? tll[sl] : rle_sym[0], eo = of_log ? tof[so] : rle_sym[1], em = ml_log ? tml[sm] : rle_sym[2];
+        const uint32_t el = tll[sl], eo = tof[so], em = tml[sm];
         const uint32_t llc = el & 0xFF, ofc = eo & 0xFF, mlc = em & 0xFF;
         if (llc > 35 || mlc > 52 || ofc > 31) return 1;
         const uint32_t ofv = (1u << ofc) + bwd_read(b, (int)ofc);
@@ -174,38 +174,45 @@ __device__ inline int plan_block(const uint8_t* chunk, uint32_t boff, uint32_t s
         // table recipe: weight classes in ascending weight (= descending code length), symbols in natural order
         HufPlan* hp = &pl->h[nhuf];
         const int maxBits = sc->huf_log;
-        for (int k = 0; k < 16; ++k) sc->tmp[k] = 0;
-        for (int i = 0; i < nw; ++i) sc->tmp[sc->weights[i]]++;
-        uint32_t e = 0, s = 0;
+        uint32_t e = 0, s = 0;                       // huf_read_weights left the per-weight symbol counts in rank_cnt
         for (int k = 1; k <= maxBits; ++k) {
             hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s;
-            const uint32_t cnt = sc->tmp[k];
-            sc->tmp[k] = s;                          // running insert position of class k
+            const uint32_t cnt = sc->rank_cnt[k];
+            sc->rank_cnt[k] = s;                     // running insert position of class k
             e += cnt << (k - 1); s += cnt;
         }
         hp->cls_start[0] = 0; hp->cls_sym[0] = 0;
         for (int k = maxBits + 1; k < 14; ++k) { hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s; }   // e == 2^maxBits
-        for (int i = 0; i < nw; ++i) { const uint32_t w = sc->weights[i]; if (w) hp->sorted[sc->tmp[w]++] = (uint8_t)i; }
+        for (int i = 0; i < nw; ++i) { const uint32_t w = sc->weights[i]; if (w) hp->sorted[sc->rank_cnt[w]++] = (uint8_t)i; }
         hp->log = (uint32_t)maxBits;
         fp.huf = nhuf++;
     }
-    // ---- sequences (predefined / RLE tables only) ----
+    // ---- sequences: predefined, RLE or FSE-described tables (repeat mode is invalid in a first block) ----
     if (nseq) {
         if (nseq_tot + nseq > PLAN_MAX_SEQ) return 1;
         uint32_t rle[3] = {0, 0, 0};
+        const uint32_t* tab[3]; int tlog[3];
         uint32_t p = so;
         for (int t = 0; t < 3; ++t) {               // order in the stream: LL, OF, ML
             const uint32_t mode = (modes >> (6 - 2 * t)) & 3;
-            if (mode > 1) return 1;                 // FSE-compressed / repeat tables: general decoder
-            if (mode == 1) {
+            const uint32_t max_sym = t == 0 ? 35u : (t == 1 ? 31u : 52u);
+            if (mode == 0) { tab[t] = deftab + (t == 0 ? 0 : (t == 1 ? 64 : 96)); tlog[t] = t == 1 ? 5 : 6; }
+            else if (mode == 1) {
                 if (p >= size) return 1;
                 const uint32_t sym = ldg8(src + p); p += 1;
-                if (sym > (t == 0 ? 35u : (t == 1 ? 31u : 52u))) return 1;
-                rle[t] = sym;
-            }
+                if (sym > max_sym) return 1;
+                rle[t] = sym; tab[t] = &rle[t]; tlog[t] = 0;
+            } else if (mode == 2) {
+                int tl, ns;
+                const uint32_t h = fse_read_ncount(src + p, size - p, sc->norm, (int)max_sym, t == 1 ? 8 : 9, &tl, &ns);
+                if (!h) return 1;
+                uint32_t* tt = pl->fse + (t == 0 ? 0 : (t == 1 ? 512 : 768));
+                fse_build(tt, sc->norm, ns, tl, sc->next16);
+                tab[t] = tt; tlog[t] = tl; p += h;
+            } else return 1;
         }
         if (p >= size) return 1;
-        if (plan_sequences(src + p, size - p, nseq, modes, rle, deftab, regen, fp.fcs, pl->seq + 3 * nseq_tot)) return 1;
+        if (plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, pl->seq + 3 * nseq_tot)) return 1;
         nseq_tot += nseq;
     }
     return 0;
@@ -261,8 +268,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         if (!slow) {
             // placement in the CTA's dynamic region: decoded output, then the literal buffer if sequences follow
             const bool zero_copy = fp.kind == FK_RAW || (fp.kind == FK_COMP && fp.ltype == 0 && fp.nseq == 0);
-            if (!zero_copy) { fp.dst_off = region; region += align16(fp.fcs) + 16; }
-            if (fp.kind == FK_COMP && fp.nseq && fp.ltype != 0) { fp.lit_dst = region; region += align16(fp.regen) + 16; }
+            if (!zero_copy) { fp.dst_off = region; region += align16(fp.fcs) + 16; }   // Huffman literals are decoded to the front of dst and moved in place
             pl->f[f] = fp;
         }
         pos += fl;

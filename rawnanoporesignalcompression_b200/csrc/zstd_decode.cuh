@@ -56,11 +56,22 @@ __device__ inline int highbit32(uint32_t v) { return 31 - __clz((int)v); }
 
 // LSB-first forward reader (FSE table descriptions)
 struct FwdBits { const uint8_t* p; uint32_t size; uint32_t bitpos; };
+// 32 bits starting at bit `bit` of the byte string p: the two aligned 32-bit words that cover them, funnel
+// shifted. Reads at most 3 bytes below and 7 bytes above the bytes needed (inside the chunk or its padding).
+__device__ __forceinline__ uint32_t gbits32(const uint8_t* p, uint32_t bit)
+{
+    const uintptr_t a = (uintptr_t)p + (bit >> 3), al = a & ~(uintptr_t)3;
+    const uint32_t sh = ((uint32_t)(a & 3) << 3) + (bit & 7);
+    return __funnelshift_r(ldg32((const uint32_t*)al), ldg32((const uint32_t*)(al + 4)), sh);
+}
 __device__ inline uint32_t fwd_peek(const FwdBits& b, int n)
 {
-    uint64_t v = 0; uint32_t byte = b.bitpos >> 3;
-    for (int i = 0; i < 5; ++i) if (byte + i < b.size) v |= (uint64_t)ldg8(b.p + byte + i) << (8 * i);
-    return (uint32_t)((v >> (b.bitpos & 7)) & ((1ull << n) - 1));
+    const uint32_t total = b.size * 8;
+    if (b.bitpos >= total) return 0;
+    uint32_t v = gbits32(b.p, b.bitpos);
+    const uint32_t avail = total - b.bitpos;                  // bits past the end of the section read as zero
+    if (avail < 32) v &= (1u << avail) - 1u;
+    return v & ((1u << n) - 1u);                              // n <= 10 here
 }
 
 // FSE_readNCount. Returns bytes consumed, 0 on error.
@@ -133,20 +144,13 @@ __device__ inline int bwd_init(BwdBits& b, const uint8_t* p, uint32_t size)
 __device__ inline uint32_t bwd_read(BwdBits& b, int n)
 {
     if (n == 0) return 0;
-    int lo = b.bitpos - n;
+    const int lo = b.bitpos - n;
     b.bitpos = lo;
-    uint64_t v = 0;
-    if (lo >= 0) {
-        int byte = lo >> 3;
-        // 5 bytes cover n <= 32 bits at any bit offset; bytes above the stream end are masked off below
-        for (int i = 0; i < 5; ++i) { int bi = byte + i; if (bi * 8 < lo + n) v |= (uint64_t)ldg8(b.start + bi) << (8 * i); }
-        v >>= (lo & 7);
-    } else {
-        b.overflow = 1;
-        int avail = n + lo;                       // bits that exist (>= 0 index)
-        if (avail > 0) { for (int i = 0; i < 5; ++i) if (i * 8 < avail) v |= (uint64_t)ldg8(b.start + i) << (8 * i); v <<= (-lo); }
-    }
-    return (uint32_t)(v & ((1ull << n) - 1));
+    if (lo >= 0) return gbits32(b.start, (uint32_t)lo) & (0xFFFFFFFFu >> (32 - n));     // n <= 31
+    b.overflow = 1;                                           // bits below the start of the stream read as zero
+    const int avail = n + lo;
+    if (avail <= 0) return 0;
+    return ((gbits32(b.start, 0) & (0xFFFFFFFFu >> (32 - avail))) << (-lo)) & (0xFFFFFFFFu >> (32 - n));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -185,19 +189,21 @@ __device__ inline uint32_t huf_read_weights(WS* ws, const uint8_t* src, uint32_t
             if (b.overflow) { if (nw >= 255) return 0; w[nw++] = (uint8_t)(ws->fse_w[s1] & 0xFF); break; }
         }
     }
+    // one pass: validity, total weight and the per-weight symbol counts (kept in ws->rank_cnt: a local array with
+    // a data-dependent index would be expanded into a compare/select chain per symbol)
+    uint32_t* cnt = ws->rank_cnt;
+    for (int k = 0; k < 16; ++k) cnt[k] = 0;
     uint32_t total = 0;
-    for (int i = 0; i < nw; ++i) { if (w[i] > HUF_LOG_MAX) return 0; total += w[i] ? (1u << (w[i] - 1)) : 0; }
+    for (int i = 0; i < nw; ++i) { const uint32_t wi = w[i]; if (wi > HUF_LOG_MAX) return 0; total += (1u << wi) >> 1; cnt[wi]++; }
     if (total == 0) return 0;
     int maxBits = highbit32(total) + 1;
     if (maxBits > HUF_LOG_MAX) return 0;
     uint32_t rest = (1u << maxBits) - total;
     if (rest & (rest - 1)) return 0;
-    w[nw++] = (uint8_t)(highbit32(rest) + 1);
+    const uint32_t lastw = (uint32_t)highbit32(rest) + 1;
+    w[nw++] = (uint8_t)lastw; cnt[lastw]++;
     for (int i = nw; i < 256; ++i) w[i] = 0;
     // rank starts: weight ascending == code length descending (HUF_readDTableX1 layout)
-    uint32_t cnt[HUF_LOG_MAX + 2];
-    for (int k = 0; k <= HUF_LOG_MAX + 1; ++k) cnt[k] = 0;
-    for (int i = 0; i < nw; ++i) cnt[w[i]]++;
     if (cnt[1] < 2 || (cnt[1] & 1)) return 0;
     uint32_t p = 0;
     for (int k = 1; k <= maxBits; ++k) { ws->rank_start[k] = p; p += cnt[k] << (k - 1); }

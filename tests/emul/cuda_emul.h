@@ -109,6 +109,12 @@ inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaPeekAtLastError() { return 0; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return 0; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)1; return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }

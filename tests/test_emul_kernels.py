@@ -52,3 +52,24 @@ def test_huffman_and_sequences_path(ecodec, oracle):
     for codec in (0, 2, 6):
         b = oracle.encode(codec, x)
         assert (ecodec.decompress_signal(b, x.size, codec) == x).all()
+
+
+def test_fast_path_routing_and_sequences(ecodec, oracle):
+    """C5/C4/VBZ0 chunks (single-block frames, predefined/RLE sequence tables) must take the planner + fast kernel,
+    including a full 102,400-sample chunk (one CTA per SM class) and key frames that carry LZ sequences."""
+    from rawnanoporesignalcompression_b200 import synth
+    lengths = np.array([3000, 30000, 102400 + 5000], dtype=np.int64)
+    sig = synth.generate_reads(lengths, 99, synth.R10_4_1).numpy()
+    off, n, _ = synth.chunk_table(lengths)
+    chunks = [sig[o : o + c] for o, c in zip(off, n)]
+    # long constant runs make zstd emit sequences in the key stream (code 0 repeated)
+    flat = chunks[1].copy(); flat[5000:9000] = flat[4999]; flat[20000:26000] = 7
+    chunks.append(flat)
+    for codec in (6, 5, 1):
+        comp = [oracle.encode(codec, c) for c in chunks]
+        dec, st = ecodec.decompress_batch(comp, [len(c) for c in chunks], codec)
+        assert not st.any() and all((a == b).all() for a, b in zip(dec, chunks))
+        fa, fb, slow = ecodec.decode_class_counts()
+        assert fa + fb + slow == len(chunks)
+        if codec != 1:
+            assert slow == 0 and fb >= 1, (codec, fa, fb, slow)
