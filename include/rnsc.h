@@ -119,10 +119,10 @@ int rnsc_dev_rc_decode(rnsc_ctx* ctx, const uint8_t* d_comp, const uint64_t* d_c
                        int32_t* d_status, void* stream);
 /* Exclusive prefix scan on the device (assigns compressed-output offsets): out[0]=0, out[i]=sum(in[0..i)). */
 int rnsc_dev_exclusive_scan_u32(rnsc_ctx* ctx, const uint32_t* d_in, size_t count, uint64_t* d_out /* count+1 */, void* stream);
-/* How the last whole-chunk decode of this context routed its chunks: out[0] = fast path with two CTAs per SM,
- * out[1] = fast path with one CTA per SM (large chunks), out[2] = general decoder (frames the planner does not
- * cover). Synchronises `stream` (NULL: the context's stream). Diagnostics for tests and bench.py. */
-int rnsc_decode_class_counts(rnsc_ctx* ctx, uint32_t out[3], void* stream);
+/* How the last whole-chunk decode of this context routed its chunks: out[0..2] = fast path with four / two / one CTA
+ * per SM (small / medium / large chunks), out[3] = general decoder (frames the planner does not cover).
+ * Synchronises `stream` (NULL: the context's stream). Diagnostics for tests and bench.py. */
+int rnsc_decode_class_counts(rnsc_ctx* ctx, uint32_t out[4], void* stream);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t rnsc_launch_count(const rnsc_ctx* ctx);
 

@@ -81,8 +81,8 @@ class Codec:
         self.lib.rnsc_set_host_threads(self.ctx, int(n))
 
     def decode_class_counts(self, stream=None):
-        """(fast two-per-SM, fast one-per-SM, general decoder) chunk counts of the last whole-chunk decode."""
-        out = (C.c_uint32 * 3)()
+        """(fast 4/SM, fast 2/SM, fast 1/SM, general decoder) chunk counts of the last whole-chunk decode."""
+        out = (C.c_uint32 * 4)()
         self._check(self.lib.rnsc_decode_class_counts(self.ctx, out, C.c_void_p(int(stream.cuda_stream)) if stream is not None else C.c_void_p(0)))
         return tuple(int(v) for v in out)
 

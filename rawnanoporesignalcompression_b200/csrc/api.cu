@@ -94,10 +94,9 @@ struct PinBuf {
 };
 
 constexpr size_t kDecodeSmem = 112 * 1024;   // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
-constexpr size_t kFastSmemA = 113 * 1024;    // fast kernel, class A: two CTAs per SM
-constexpr size_t kFastSmemB = 227 * 1024;    // fast kernel, class B: one CTA per SM with the whole carve-out
-constexpr size_t kFastWsA = (sizeof(FastWs<512>) + 15) & ~(size_t)15;
-constexpr size_t kFastWsB = (sizeof(FastWs<1024>) + 15) & ~(size_t)15;
+// fast kernel size classes: dynamic shared memory per CTA so that 4 / 2 / 1 CTAs fit the 228 KB of an SM (1 KB reserved per CTA)
+constexpr size_t kFastSmem[3] = {56 * 1024, 113 * 1024, 227 * 1024};
+constexpr size_t kFastWs[3] = {(sizeof(FastWs<256>) + 15) & ~(size_t)15, (sizeof(FastWs<512>) + 15) & ~(size_t)15, (sizeof(FastWs<1024>) + 15) & ~(size_t)15};
 
 // Predefined sequence decoding tables (RFC 8878 3.1.1.3.2.2), entry = (newState << 16) | (nbBits << 8) | symbol,
 // laid out LL[64] OF[32] ML[64]; built once on the host with the same spread as fse_build (zstd_decode.cuh).
@@ -134,8 +133,8 @@ struct rnsc_ctx {
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
     DevBuf d_plans, d_lists, d_deftab;
-    cudaStream_t side[2] = {nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
-    cudaEvent_t ev_plan = nullptr, ev_side[2] = {nullptr, nullptr};
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
+    cudaEvent_t ev_plan = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
     PinBuf h_a, h_b;
 };
 
@@ -158,40 +157,40 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     const size_t stride = ((LIT_SCRATCH + 255) & ~(size_t)255) + spill;
     if (c->d_scratch.reserve(stride * (size_t)c->sm_count * 2)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(scratch %zu) failed", stride * (size_t)c->sm_count * 2);
     if (c->d_counter.reserve(256)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(counter) failed");
-    if (c->d_plans.reserve(nchunks * sizeof(ChunkPlan)) || c->d_lists.reserve(3 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(plans) failed");
-    // counter words: [0..2] list lengths, [4] class B cursor, [5] class A cursor, [6] slow cursor
+    if (c->d_plans.reserve(nchunks * sizeof(ChunkPlan)) || c->d_lists.reserve(4 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(plans) failed");
+    // counter words: [0..3] list lengths (class S, A, B, general), [8..11] the work cursors of the four kernels
     uint32_t* cnt = (uint32_t*)c->d_counter.p;
-    CUDA_OK(cudaMemsetAsync(cnt, 0, 32, st));
+    CUDA_OK(cudaMemsetAsync(cnt, 0, 64, st));
     // 1. planner: one thread per chunk does every serial step (headers, Huffman tree descriptions, sequences)
     PlanParams pp;
     pp.comp = d_comp; pp.comp_off = d_comp_off; pp.n = d_n; pp.nchunks = (uint32_t)nchunks; pp.codec = codec;
     pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
-    pp.region_a = (uint32_t)(kFastSmemA - kFastWsA); pp.region_b = (uint32_t)(kFastSmemB - kFastWsB); pp.deftab = (const uint32_t*)c->d_deftab.p;
+    for (int k = 0; k < 3; ++k) pp.region[k] = (uint32_t)(kFastSmem[k] - kFastWs[k]);
+    pp.deftab = (const uint32_t*)c->d_deftab.p;
     RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
-    // 2. fast kernel over the two size classes (largest chunks first), 3. general decoder over what is left
+    // 2. fast kernel over the three size classes, 3. general decoder over what is left. Fork: class B (large chunks, one
+    // CTA per SM) stays on the caller's stream and is enqueued first; the other classes and the general decoder go to side
+    // streams and fill SMs as class B CTAs retire. Join before returning to the caller's stream.
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
     fp.plans = (const ChunkPlan*)c->d_plans.p;
-    fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_B * nchunks; fp.count = cnt + CLS_B; fp.counter = cnt + 4; fp.region_bytes = pp.region_b;
-    // Fork: class B (large chunks, one CTA per SM) stays on the caller's stream and is enqueued first; class A and the
-    // general decoder go to side streams and fill SMs as class B CTAs retire. Join before returning to the caller's stream.
+    auto set_class = [&](uint32_t cls) { fp.list = (const uint32_t*)c->d_lists.p + (size_t)cls * nchunks; fp.count = cnt + cls; fp.counter = cnt + 8 + cls; };
     CUDA_OK(cudaEventRecord(c->ev_plan, st));
-    RNSC_LAUNCH(k_decode_fast<1024>, (int)std::min<size_t>((size_t)c->sm_count, nchunks), 1024, kFastSmemB, st, fp);
-    fp.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_A * nchunks; fp.count = cnt + CLS_A; fp.counter = cnt + 5; fp.region_bytes = pp.region_a;
-    CUDA_OK(cudaStreamWaitEvent(c->side[0], c->ev_plan, 0));
-    RNSC_LAUNCH(k_decode_fast<512>, grid, 512, kFastSmemA, c->side[0], fp);
-    CUDA_OK(cudaEventRecord(c->ev_side[0], c->side[0]));
+    for (int k = 0; k < 3; ++k) CUDA_OK(cudaStreamWaitEvent(c->side[k], c->ev_plan, 0));
+    set_class(CLS_B);
+    RNSC_LAUNCH(k_decode_fast<1024>, (int)std::min<size_t>((size_t)c->sm_count, nchunks), 1024, kFastSmem[2], st, fp);
+    set_class(CLS_A);
+    RNSC_LAUNCH(k_decode_fast<512>, (int)std::min<size_t>((size_t)c->sm_count * 2, nchunks), 512, kFastSmem[1], c->side[0], fp);
+    set_class(CLS_S);
+    RNSC_LAUNCH(k_decode_fast<256>, (int)std::min<size_t>((size_t)c->sm_count * 4, nchunks), 256, kFastSmem[0], c->side[1], fp);
     DecodeParams p;
     p.comp = d_comp; p.comp_off = d_comp_off; p.n = d_n; p.sample_off = d_sample_off; p.samples = d_samples; p.status = d_status;
     p.nchunks = (uint32_t)nchunks; p.codec = codec; p.scratch = (uint8_t*)c->d_scratch.p; p.scratch_stride = stride;
-    p.counter = cnt + 6; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
+    p.counter = cnt + 8 + CLS_SLOW; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
     p.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_SLOW * nchunks; p.count = cnt + CLS_SLOW;
-    CUDA_OK(cudaStreamWaitEvent(c->side[1], c->ev_plan, 0));
-    RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, c->side[1], p);
-    CUDA_OK(cudaEventRecord(c->ev_side[1], c->side[1]));
-    CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[0], 0));
-    CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[1], 0));
-    c->launches += 4;
+    RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, c->side[2], p);
+    for (int k = 0; k < 3; ++k) { CUDA_OK(cudaEventRecord(c->ev_side[k], c->side[k])); CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[k], 0)); }
+    c->launches += 5;
     CUDA_OK(cudaGetLastError());
     return RNSC_OK;
 }
@@ -258,14 +257,16 @@ rnsc_ctx* rnsc_create(int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed"); return nullptr; }
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
-    if (cudaStreamCreateWithFlags(&c->side[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->side[1], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_side[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_side[1], cudaEventDisableTiming) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
+    bool ok = cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 3 && ok; ++k) ok = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&c->ev_side[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
     cudaError_t e2 = cudaFuncSetAttribute(k_svb_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SvbWs) + 16 + SVB_STAGE_BYTES));
-    cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemB);
+    cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[2]);
     if (e1 == cudaSuccess) e1 = e3;
-    e3 = cudaFuncSetAttribute(k_decode_fast<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemA);
+    e3 = cudaFuncSetAttribute(k_decode_fast<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[1]);
+    if (e1 == cudaSuccess) e1 = e3;
+    e3 = cudaFuncSetAttribute(k_decode_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[0]);
     if (e1 == cudaSuccess) e1 = e3;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return nullptr; }
     uint32_t deftab[160];
@@ -285,7 +286,7 @@ void rnsc_destroy(rnsc_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab}) b->release();
     c->h_a.release(); c->h_b.release();
-    for (int i = 0; i < 2; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
+    for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -314,14 +315,14 @@ int rnsc_dev_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_
     return launch_decode(c, codec, d_comp, d_comp_off, d_n, d_sample_off, nchunks, max_n, d_samples, d_status, stream ? (cudaStream_t)stream : c->stream);
 }
 
-int rnsc_decode_class_counts(rnsc_ctx* c, uint32_t out[3], void* stream)
+int rnsc_decode_class_counts(rnsc_ctx* c, uint32_t out[4], void* stream)
 {
     if (!c || !out) return fail(RNSC_ERR_BAD_ARG, "rnsc_decode_class_counts: bad argument");
-    out[0] = out[1] = out[2] = 0;
+    out[0] = out[1] = out[2] = out[3] = 0;
     if (!c->d_counter.p) return RNSC_OK;
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    CUDA_OK(cudaMemcpyAsync(out, c->d_counter.p, 12, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(out, c->d_counter.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     return RNSC_OK;
 }

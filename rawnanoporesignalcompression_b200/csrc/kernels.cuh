@@ -143,20 +143,18 @@ __global__ void __launch_bounds__(NT, 2) k_decode_chunks(DecodeParams p)
 // staged compressed chunk and every decoded stream.
 // ---------------------------------------------------------------------------------------------------
 template <int NTH>
-__global__ void __launch_bounds__(NTH, (NTH <= 512 ? 2 : 1)) k_decode_fast(FastParams P)
+__global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
 {
     RNSC_DYN_SMEM(smem);
     FastWs<NTH>* ws = (FastWs<NTH>*)smem;
     uint8_t* region = smem + ((sizeof(FastWs<NTH>) + 15) & ~(size_t)15);
     const int tid = threadIdx.x;
-    if (tid == 0) mbar_init(&ws->mbar, 1);
+    if (tid == 0) { mbar_init(&ws->mbar, 1); const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
+    __syncthreads();
     uint32_t parity = 0;
     for (;;) {
-        __syncthreads();
-        if (tid == 0) { const uint32_t i = atomicAdd(P.counter, 1u); ws->chunk = i < *P.count ? P.list[i] : 0xFFFFFFFFu; }
-        __syncthreads();
-        const uint32_t c = ws->chunk;
-        if (c == 0xFFFFFFFFu) break;
+        const uint32_t c = ws->next;            // thread 0 replaces it (prefetch) only after the first barrier of the chunk
+        if (c == FAST_NONE) break;
         fast_decode_chunk<NTH>(ws, region, P, c, parity);
         parity ^= 1u;
         const uint32_t n = P.n[c];
@@ -166,6 +164,7 @@ __global__ void __launch_bounds__(NTH, (NTH <= 512 ? 2 : 1)) k_decode_fast(FastP
         }
         __syncthreads();
         if (tid == 0) P.status[c] = ws->status;
+        __syncthreads();                        // the region and ws->status are reused by the next chunk
     }
 }
 

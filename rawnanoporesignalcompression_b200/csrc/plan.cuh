@@ -17,43 +17,65 @@ namespace rnsc {
 
 constexpr int PLAN_MAX_SEQ = 128;     // sequences of all frames of a chunk kept inline in the plan
 constexpr int PLAN_MAX_HUF = 3;       // Huffman-coded literal sections per chunk described in the plan
+constexpr int PLAN_MAX_STREAMS = 4 * PLAN_MAX_HUF;
 constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
 constexpr uint32_t REGION_HEAD = 16;  // readable bytes in front of the staged chunk (bit-window over-read)
+constexpr uint32_t PLAN_SUB_MIN = 384;   // minimum Huffman sub-sequence length in bits
 
 enum : uint32_t { FK_RAW = 0, FK_RLE = 1, FK_COMP = 2 };
-enum : uint32_t { CLS_A = 0, CLS_B = 1, CLS_SLOW = 2, CLS_DONE = 3 };
+// size classes of the fast kernel (threads per CTA x CTAs per SM): S 256x4, A 512x2, B 1024x1; then the general decoder
+enum : uint32_t { CLS_S = 0, CLS_A = 1, CLS_B = 2, CLS_SLOW = 3, CLS_DONE = 4 };
+__host__ __device__ inline uint32_t class_threads(uint32_t cls) { return cls == CLS_S ? 256u : (cls == CLS_A ? 512u : 1024u); }
 
-struct FramePlan {
+struct FramePlan {               // planner-internal description of one frame
     uint32_t kind, fcs;          // block type of the frame's single block; decoded size
     uint32_t data_off;           // RAW: chunk offset of the bytes; RLE: the byte value
     uint32_t dst_off;            // region offset of the decoded output (RLE, COMP unless zero-copy)
     uint32_t ltype, regen;       // literals: 0 raw, 1 RLE, 2 Huffman; count
     uint32_t lit_off;            // raw literals: chunk offset; RLE literals: the byte value
-    uint32_t lit_dst;            // unused (literals of a frame with sequences are decoded to the front of dst and moved in place)
+    uint32_t lit_dst;            // unused
     uint32_t nstreams, huf;      // Huffman: 1 or 4 streams; index of the HufPlan
     uint32_t nseq, seq_base;     // sequences [seq_base, seq_base + nseq) of ChunkPlan::seq
     uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
 };
 struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decoding table
     uint32_t log;                // table log (max code length), <= 12
+    uint32_t tab_off;            // region offset of the table (2^log entries of 2 bytes)
     uint16_t cls_start[14];      // first table entry of weight class w (1..log); cls_start[log+1] = 2^log
     uint16_t cls_sym[14];        // index into sorted[] of the first symbol of class w
     uint8_t sorted[256];         // symbols of weight > 0 ordered by (weight, symbol)
 };
+struct StreamPlan { uint32_t tbits, abit, count, out, tab_off, log; };   // one Huffman bitstream: payload bits, absolute bit address of the
+                                                                         // end mark in the region, symbols, region offset of the output, its table
+struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
+struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base; };   // LZ sequences of a frame; lit = region offset of raw literals or the RLE byte
+struct ViewPlan { uint32_t off, len; };                                  // stream k of the splitter inverse = region[off .. off+len)
+constexpr int SEQ_WORDS = 5;     // (literal length, match length, offset, literal position, output position)
+
+struct PlanHead {                // what the fast kernel copies to shared memory for every chunk
+    uint32_t cls, need, phase, stage_bytes;
+    uint32_t nhuf, nst, sub, nfill, nsop, nseq;
+    int32_t view_status; uint32_t pad;
+    uint32_t st_first[PLAN_MAX_STREAMS + 1];
+    StreamPlan st[PLAN_MAX_STREAMS];
+    FillOp fill[5];
+    SeqOp sop[5];
+    ViewPlan view[5];
+};
 struct ChunkPlan {
-    uint32_t cls, nhuf, need, phase, stage_bytes, nseq, pad0, pad1;
-    FramePlan f[5];
+    PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
-    uint32_t seq[PLAN_MAX_SEQ * 3];  // (literal length, match length, offset) triples
+    uint32_t seq[PLAN_MAX_SEQ * SEQ_WORDS];
+    FramePlan f[5];                  // planner scratch
     uint32_t fse[512 + 256 + 512];   // planner scratch: FSE-compressed LL / OF / ML decoding tables of the frame being planned
 };
 
 struct PlanParams {
     const uint8_t* comp; const uint64_t* comp_off; const uint32_t* n; uint32_t nchunks; int codec;
     ChunkPlan* plans; int32_t* status;
-    uint32_t* lists;             // 3 lists of nchunks chunk indices: class A, class B, slow
-    uint32_t* counts;            // [0..2] list lengths (atomic), zeroed before the launch
-    uint32_t region_a, region_b; // bytes of dynamic region available to a class A / class B CTA
+    uint32_t* lists;             // 4 lists of nchunks chunk indices: class S, A, B, slow
+    uint32_t* counts;            // [0..3] list lengths (atomic), zeroed before the launch
+    uint32_t region[3];          // bytes of dynamic region available to a class S / A / B CTA
     const uint32_t* deftab;      // predefined FSE decoding tables: LL[64] OF[32] ML[64]
 };
 
@@ -101,8 +123,8 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
         }
         if (b.overflow) return 1;
         if (lp + ll > regen || op + ll + ml > fcs || offset > op + ll) return 1;
+        out[SEQ_WORDS * i] = ll; out[SEQ_WORDS * i + 1] = ml; out[SEQ_WORDS * i + 2] = offset; out[SEQ_WORDS * i + 3] = lp; out[SEQ_WORDS * i + 4] = op;
         op += ll + ml; lp += ll;
-        out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = offset;
     }
     if (b.bitpos != 0) return 1;
     if (op + (regen - lp) != fcs) return 1;
@@ -212,7 +234,7 @@ __device__ inline int plan_block(const uint8_t* chunk, uint32_t boff, uint32_t s
             } else return 1;
         }
         if (p >= size) return 1;
-        if (plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, pl->seq + 3 * nseq_tot)) return 1;
+        if (plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, pl->seq + SEQ_WORDS * nseq_tot)) return 1;
         nseq_tot += nseq;
     }
     return 0;
@@ -220,13 +242,14 @@ __device__ inline int plan_block(const uint8_t* chunk, uint32_t boff, uint32_t s
 
 __device__ inline void plan_emit(const PlanParams& P, uint32_t c, uint32_t cls)
 {
-    P.plans[c].cls = cls;
+    P.plans[c].head.cls = cls;
     if (cls <= CLS_SLOW) { const uint32_t i = atomicAdd(P.counts + cls, 1u); P.lists[(size_t)cls * P.nchunks + i] = c; }
 }
 
 __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* sc, const uint32_t* deftab)
 {
     ChunkPlan* pl = P.plans + c;
+    PlanHead* hd = &pl->head;
     const uint8_t* src = P.comp + P.comp_off[c];
     const uint32_t clen = (uint32_t)(P.comp_off[c + 1] - P.comp_off[c]);
     const uint32_t n = P.n[c];
@@ -234,6 +257,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     const uint64_t bound = stream_bound(P.codec, n);
     const uint32_t phase = (uint32_t)((uintptr_t)src & 15u);
     const uint32_t stage = align16(phase + clen);
+    const uint32_t cbase = REGION_HEAD + phase;                    // region offset of chunk byte 0
     uint32_t region = REGION_HEAD + stage + 16, pos = 0, nhuf = 0, nseq_tot = 0;
     int st = RNSC_OK; bool slow = false;
     for (int f = 0; f < nf; ++f) {
@@ -266,16 +290,69 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
             }
         }
         if (!slow) {
-            // placement in the CTA's dynamic region: decoded output, then the literal buffer if sequences follow
+            // placement of the decoded output in the CTA's dynamic region (raw data is used in place; the literals of a
+            // frame with sequences are decoded to the front of dst and moved in place)
             const bool zero_copy = fp.kind == FK_RAW || (fp.kind == FK_COMP && fp.ltype == 0 && fp.nseq == 0);
-            if (!zero_copy) { fp.dst_off = region; region += align16(fp.fcs) + 16; }   // Huffman literals are decoded to the front of dst and moved in place
+            if (!zero_copy) { fp.dst_off = region; region += align16(fp.fcs) + 16; }
             pl->f[f] = fp;
         }
         pos += fl;
     }
     if (st != RNSC_OK) { P.status[c] = st; plan_emit(P, c, CLS_DONE); return; }
-    pl->nhuf = nhuf; pl->need = region; pl->phase = phase; pl->stage_bytes = stage; pl->nseq = nseq_tot;
-    plan_emit(P, c, slow ? CLS_SLOW : (region <= P.region_a ? CLS_A : (region <= P.region_b ? CLS_B : CLS_SLOW)));
+    if (slow) { plan_emit(P, c, CLS_SLOW); return; }
+    // ---- Huffman tables live in the region too ----
+    for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].tab_off = region; region += align16(2u << pl->h[h].log); }
+    const uint32_t cls = region <= P.region[0] ? CLS_S : (region <= P.region[1] ? CLS_A : (region <= P.region[2] ? CLS_B : CLS_SLOW));
+    if (cls == CLS_SLOW) { plan_emit(P, c, CLS_SLOW); return; }
+    const uint32_t nth = class_threads(cls);
+    // ---- the kernel's program: Huffman streams, fills, sequence ops, views ----
+    uint32_t nst = 0, ttot = 0, nfill = 0, nsop = 0;
+    int vst = RNSC_OK;
+    const uint32_t kl = key_len(P.codec, n);
+    uint32_t tot_fcs = 0;
+    for (int f = 0; f < nf; ++f) {
+        const FramePlan fp = pl->f[f];
+        uint32_t data;                                         // region offset of the frame's decoded bytes
+        if (fp.kind == FK_RAW) data = cbase + fp.data_off;
+        else if (fp.kind == FK_COMP && fp.ltype == 0 && fp.nseq == 0) data = cbase + fp.lit_off;
+        else data = fp.dst_off;
+        if (fp.kind == FK_RLE) hd->fill[nfill++] = FillOp{fp.dst_off, fp.fcs, fp.data_off};
+        else if (fp.kind == FK_COMP && fp.nseq == 0 && fp.ltype == 1) hd->fill[nfill++] = FillOp{fp.dst_off, fp.fcs, fp.lit_off};
+        if (fp.kind == FK_COMP && fp.ltype == 2) {
+            const uint32_t q = (fp.regen + 3) / 4;
+            for (uint32_t j = 0; j < fp.nstreams; ++j) {
+                StreamPlan sp;
+                sp.tbits = fp.s_tbits[j]; sp.abit = 8 * (cbase + fp.s_beg[j]) + fp.s_tbits[j];
+                sp.count = fp.nstreams == 1 ? fp.regen : (j < 3 ? q : fp.regen - 3 * q);
+                sp.out = fp.dst_off + (fp.nstreams == 1 ? 0 : j * q);
+                sp.tab_off = pl->h[fp.huf].tab_off; sp.log = pl->h[fp.huf].log;
+                if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
+                hd->st[nst++] = sp; ttot += sp.tbits;
+            }
+        }
+        if (fp.kind == FK_COMP && fp.nseq) hd->sop[nsop++] = SeqOp{fp.dst_off, fp.ltype, fp.ltype == 0 ? cbase + fp.lit_off : fp.lit_off, fp.regen, fp.nseq, fp.seq_base};
+        // A.8: stream views = slices of the decompressed buffer(s)
+        if (nf == 1) {
+            if (fp.fcs < kl) vst = RNSC_ERR_REMAINING;
+            else { hd->view[0] = ViewPlan{data, kl}; hd->view[1] = ViewPlan{data + kl, fp.fcs - kl}; }
+            for (int k = 2; k < 5; ++k) hd->view[k] = ViewPlan{cbase, 0};
+        } else {
+            if (f == 0 && fp.fcs != kl) vst = RNSC_ERR_REMAINING;
+            hd->view[f] = ViewPlan{data, fp.fcs};
+        }
+        tot_fcs += fp.fcs;
+    }
+    for (int f = nf; f < 5 && nf > 1; ++f) hd->view[f] = ViewPlan{cbase, 0};
+    if (n == 0 && tot_fcs) vst = RNSC_ERR_REMAINING;
+    if (slow) { plan_emit(P, c, CLS_SLOW); return; }
+    uint32_t sub = nst ? (ttot + (nth - nst) - 1) / (nth - nst) : PLAN_SUB_MIN;
+    if (sub < PLAN_SUB_MIN) sub = PLAN_SUB_MIN;
+    uint32_t first = 0;
+    for (uint32_t s = 0; s < nst; ++s) { hd->st_first[s] = first; first += (hd->st[s].tbits + sub - 1) / sub; }
+    for (uint32_t s = nst; s <= PLAN_MAX_STREAMS; ++s) hd->st_first[s] = first;
+    hd->need = region; hd->phase = phase; hd->stage_bytes = stage;
+    hd->nhuf = nhuf; hd->nst = nst; hd->sub = sub; hd->nfill = nfill; hd->nsop = nsop; hd->nseq = nseq_tot; hd->view_status = vst; hd->pad = 0;
+    plan_emit(P, c, cls);
 }
 
 __global__ void __launch_bounds__(PLAN_THREADS) k_plan_chunks(PlanParams P)

@@ -69,7 +69,7 @@ def test_fast_path_routing_and_sequences(ecodec, oracle):
         comp = [oracle.encode(codec, c) for c in chunks]
         dec, st = ecodec.decompress_batch(comp, [len(c) for c in chunks], codec)
         assert not st.any() and all((a == b).all() for a, b in zip(dec, chunks))
-        fa, fb, slow = ecodec.decode_class_counts()
-        assert fa + fb + slow == len(chunks)
+        fs, fa, fb, slow = ecodec.decode_class_counts()
+        assert fs + fa + fb + slow == len(chunks)
         if codec != 1:
-            assert slow == 0 and fb >= 1, (codec, fa, fb, slow)
+            assert slow == 0 and fb >= 1 and fs >= 1, (codec, fs, fa, fb, slow)
