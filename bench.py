@@ -270,6 +270,14 @@ def run_rnsc(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.phases:
+        cd.set_profiling(True)
+        for _ in range(3):
+            step()
+        for cls, ph in cd.phase_cycles().items():
+            nchk = max(1, ph["chunks"])
+            log(f"phases {cls}: chunks {ph['chunks']//3}/step; cycles per chunk: " + ", ".join(f"{k} {v/nchk:.0f}" for k, v in ph.items() if k != "chunks"))
+        cd.set_profiling(False)
     sampler = ClockSampler(local); sampler.start()     # clocks / throttle reasons over warm-up + timed region (all under load)
     for _ in range(max(args.warmup, 3)):
         step()
@@ -351,8 +359,22 @@ def run_rnsc(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(es)
         e_ok = bool((h_out == wl["d_sig"][:e_samples].cpu()).all())
+        # context for the e2e number: what the PCIe link of this box does on its own (pinned 1 GiB copies, best of 3)
+        pcie = {}
+        try:
+            nb = min(1 << 30, h_out.numel() * 2)
+            hb = h_out[: nb // 2]; db = torch.empty(nb // 2, dtype=torch.int16, device=dev)
+            for name, (dst_t, src_t) in (("h2d", (db, hb)), ("d2h", (hb, db))):
+                best = 0.0
+                for _ in range(3):
+                    torch.cuda.synchronize(); t1 = time.perf_counter(); dst_t.copy_(src_t, non_blocking=True); torch.cuda.synchronize()
+                    best = max(best, nb / (time.perf_counter() - t1) / 1e9)
+                pcie[name + "_GBps"] = round(best, 2)
+            del db
+        except Exception as ex:  # noqa: BLE001
+            pcie = {"error": str(ex)}
         e2e = {"value": round(2.0 * float(es.item()) * e_steps / float(dt.item()) / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": int(e_cb + 20 * e_ch + 16),
-               "d2h_bytes_per_step": int(2 * e_samples + 4 * e_ch), "steps": e_steps, "reads_per_rank": e_reads, "bit_exact": e_ok,
+               "d2h_bytes_per_step": int(2 * e_samples + 4 * e_ch), "steps": e_steps, "reads_per_rank": e_reads, "bit_exact": e_ok, "pcie_link": pcie,
                "call": "rnsc_decompress_batch (pinned host buffers in and out)"}
         del h_comp, h_out
 
@@ -425,6 +447,7 @@ def main():
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fast decode kernels (tuning aid) to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

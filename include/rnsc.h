@@ -123,6 +123,11 @@ int rnsc_dev_exclusive_scan_u32(rnsc_ctx* ctx, const uint32_t* d_in, size_t coun
  * per SM (small / medium / large chunks), out[3] = general decoder (frames the planner does not cover).
  * Synchronises `stream` (NULL: the context's stream). Diagnostics for tests and bench.py. */
 int rnsc_decode_class_counts(rnsc_ctx* ctx, uint32_t out[4], void* stream);
+/* Tuning aid: when on, the fast decode kernels add SM cycles per phase (thread 0 of every CTA) to 3 x 8 counters
+ * (size class S, A, B) x (stage+tables, Huffman pass 1, chain check+scan, Huffman pass 2, fills+sequences, splitter
+ * inverse, bookkeeping, chunks). rnsc_get_phase_cycles synchronises the device and returns the running totals. */
+int rnsc_set_profiling(rnsc_ctx* ctx, int on);
+int rnsc_get_phase_cycles(rnsc_ctx* ctx, uint64_t out[24]);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t rnsc_launch_count(const rnsc_ctx* ctx);
 

@@ -86,6 +86,16 @@ class Codec:
         self._check(self.lib.rnsc_decode_class_counts(self.ctx, out, C.c_void_p(int(stream.cuda_stream)) if stream is not None else C.c_void_p(0)))
         return tuple(int(v) for v in out)
 
+    def set_profiling(self, on: bool):
+        self._check(self.lib.rnsc_set_profiling(self.ctx, int(bool(on))))
+
+    def phase_cycles(self):
+        """{class: {phase: cycles}} accumulated by the fast decode kernels since set_profiling(True)."""
+        out = (C.c_uint64 * 24)()
+        self._check(self.lib.rnsc_get_phase_cycles(self.ctx, out))
+        names = ["stage_tables", "huf_pass1", "huf_scan", "huf_pass2", "fills_sequences", "unpack", "bookkeeping", "chunks"]
+        return {cls: {nm: int(out[8 * k + i]) for i, nm in enumerate(names)} for k, cls in enumerate(("S_256x4", "A_512x2", "B_1024x1"))}
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.rnsc_launch_count(self.ctx))

@@ -124,6 +124,15 @@ void host_default_tables(uint32_t* tab /* 160 */)
 
 }  // namespace
 
+// Device/pinned staging of one slice of a host-buffer batch (two lanes: copies overlap the kernels)
+struct Lane {
+    DevBuf comp, samples, off_a, off_b, n, status;
+    PinBuf h_off;
+    cudaEvent_t ev_in = nullptr, ev_dec = nullptr, ev_out = nullptr;
+    bool used = false;
+};
+constexpr uint64_t kSliceSamples = 48ull << 20;   // ~96 MiB of int16 per slice
+
 struct rnsc_ctx {
     int device = 0;
     int sm_count = 1;
@@ -132,7 +141,10 @@ struct rnsc_ctx {
     uint64_t launches = 0;
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
-    DevBuf d_plans, d_lists, d_deftab;
+    DevBuf d_plans, d_lists, d_deftab, d_prof;
+    bool profiling = false;
+    Lane lane[2];
+    cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
     cudaEvent_t ev_plan = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
     PinBuf h_a, h_b;
@@ -174,7 +186,8 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
     fp.plans = (const ChunkPlan*)c->d_plans.p;
-    auto set_class = [&](uint32_t cls) { fp.list = (const uint32_t*)c->d_lists.p + (size_t)cls * nchunks; fp.count = cnt + cls; fp.counter = cnt + 8 + cls; };
+    auto set_class = [&](uint32_t cls) { fp.list = (const uint32_t*)c->d_lists.p + (size_t)cls * nchunks; fp.count = cnt + cls; fp.counter = cnt + 8 + cls;
+                                         fp.prof = c->profiling ? (unsigned long long*)c->d_prof.p + 8 * cls : nullptr; };
     CUDA_OK(cudaEventRecord(c->ev_plan, st));
     for (int k = 0; k < 3; ++k) CUDA_OK(cudaStreamWaitEvent(c->side[k], c->ev_plan, 0));
     set_class(CLS_B);
@@ -259,6 +272,9 @@ rnsc_ctx* rnsc_create(int device)
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
     bool ok = cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < 3 && ok; ++k) ok = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&c->ev_side[k], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k) ok = cudaEventCreateWithFlags(&c->lane[k].ev_in, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->lane[k].ev_dec, cudaEventDisableTiming) == cudaSuccess &&
+                                           cudaEventCreateWithFlags(&c->lane[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
     cudaError_t e2 = cudaFuncSetAttribute(k_svb_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SvbWs) + 16 + SVB_STAGE_BYTES));
@@ -284,10 +300,18 @@ void rnsc_destroy(rnsc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab}) b->release();
+    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof}) b->release();
     c->h_a.release(); c->h_b.release();
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);
+    for (int k = 0; k < 2; ++k) {
+        Lane& L = c->lane[k];
+        for (DevBuf* b : {&L.comp, &L.samples, &L.off_a, &L.off_b, &L.n, &L.status}) b->release();
+        L.h_off.release();
+        for (cudaEvent_t e : {L.ev_in, L.ev_dec, L.ev_out}) if (e) cudaEventDestroy(e);
+    }
+    if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
+    if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -324,6 +348,26 @@ int rnsc_decode_class_counts(rnsc_ctx* c, uint32_t out[4], void* stream)
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     CUDA_OK(cudaMemcpyAsync(out, c->d_counter.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    return RNSC_OK;
+}
+
+int rnsc_set_profiling(rnsc_ctx* c, int on)
+{
+    if (!c) return fail(RNSC_ERR_BAD_ARG, "rnsc_set_profiling: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    if (on) { if (c->d_prof.reserve(24 * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(prof) failed"); CUDA_OK(cudaMemset(c->d_prof.p, 0, 24 * 8)); }
+    c->profiling = on != 0;
+    return RNSC_OK;
+}
+
+int rnsc_get_phase_cycles(rnsc_ctx* c, uint64_t out[24])
+{
+    if (!c || !out) return fail(RNSC_ERR_BAD_ARG, "rnsc_get_phase_cycles: bad argument");
+    memset(out, 0, 24 * 8);
+    if (!c->d_prof.p) return RNSC_OK;
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(out, c->d_prof.p, 24 * 8, cudaMemcpyDeviceToHost));
     return RNSC_OK;
 }
 
@@ -414,40 +458,62 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
     if (!nchunks) return RNSC_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
-    // chunk i may live anywhere in `comp`/`samples`: stage them back to back in HBM (the kernels accept
-    // any byte/sample alignment) and build dense offset tables
-    std::vector<uint64_t> coff(nchunks + 1), soff(nchunks + 1);
-    uint64_t cb = 0, sb = 0; uint32_t max_n = 0;
-    for (size_t i = 0; i < nchunks; ++i) {
-        if (comp_off[i + 1] < comp_off[i]) return fail(RNSC_ERR_BAD_ARG, "comp_off must be non-decreasing");
-        coff[i] = cb; soff[i] = sb;
-        cb += comp_off[i + 1] - comp_off[i]; sb += n[i];
-        if (n[i] > max_n) max_n = n[i];
+    for (size_t i = 0; i < nchunks; ++i) if (comp_off[i + 1] < comp_off[i]) return fail(RNSC_ERR_BAD_ARG, "comp_off must be non-decreasing");
+    // The batch is cut into slices of about kSliceSamples samples that flow through two lanes of device staging:
+    // H2D of slice i+1, decode of slice i and D2H of slice i-1 overlap (three streams chained by events). Chunk i may
+    // live anywhere in `comp`/`samples`; inside a lane the chunks are staged back to back (the kernels accept any
+    // byte/sample alignment) with dense offset tables.
+    size_t first = 0; int slice = 0; int rc = RNSC_OK;
+    while (first < nchunks && rc == RNSC_OK) {
+        size_t last = first; uint64_t cb = 0, sb = 0; uint32_t max_n = 0;
+        while (last < nchunks && (last == first || sb + n[last] <= kSliceSamples)) { cb += comp_off[last + 1] - comp_off[last]; sb += n[last]; if (n[last] > max_n) max_n = n[last]; ++last; }
+        const size_t m = last - first;
+        Lane& L = c->lane[slice & 1];
+        if (L.used) CUDA_OK(cudaEventSynchronize(L.ev_out));     // the lane's previous slice has left the device; its pinned tables are free
+        if (L.comp.reserve(cb + 64) || L.samples.reserve(sb * 2 + 64) || L.off_a.reserve((m + 1) * 8) || L.off_b.reserve((m + 1) * 8) ||
+            L.n.reserve(m * 4 + 16) || L.status.reserve(m * 4 + 16) || L.h_off.reserve(2 * (m + 1) * 8))
+            return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
+        uint64_t* coff = (uint64_t*)L.h_off.p; uint64_t* soff = coff + (m + 1);
+        bool contiguous = true, dense = true;
+        { uint64_t a = 0, b = 0;
+          for (size_t i = 0; i < m; ++i) {
+              coff[i] = a; soff[i] = b;
+              if (comp_off[first + i] - comp_off[first] != a) contiguous = false;
+              if (sample_off[first + i] - sample_off[first] != b) dense = false;
+              a += comp_off[first + i + 1] - comp_off[first + i]; b += n[first + i];
+          }
+          coff[m] = a; soff[m] = b; }
+        // ---- H2D ----
+        if (L.used) { CUDA_OK(cudaStreamWaitEvent(c->h2d, L.ev_dec, 0)); }
+        if (contiguous) CUDA_OK(cudaMemcpyAsync(L.comp.p, comp + comp_off[first], cb, cudaMemcpyHostToDevice, c->h2d));
+        else for (size_t i = 0; i < m; ++i) CUDA_OK(cudaMemcpyAsync((uint8_t*)L.comp.p + coff[i], comp + comp_off[first + i], comp_off[first + i + 1] - comp_off[first + i], cudaMemcpyHostToDevice, c->h2d));
+        CUDA_OK(cudaMemsetAsync((uint8_t*)L.comp.p + cb, 0, 32, c->h2d));
+        CUDA_OK(cudaMemcpyAsync(L.off_a.p, coff, (m + 1) * 8, cudaMemcpyHostToDevice, c->h2d));
+        CUDA_OK(cudaMemcpyAsync(L.off_b.p, soff, (m + 1) * 8, cudaMemcpyHostToDevice, c->h2d));
+        CUDA_OK(cudaMemcpyAsync(L.n.p, n + first, m * 4, cudaMemcpyHostToDevice, c->h2d));
+        CUDA_OK(cudaEventRecord(L.ev_in, c->h2d));
+        // ---- decode ----
+        cudaStream_t st = c->stream;
+        CUDA_OK(cudaStreamWaitEvent(st, L.ev_in, 0));
+        if (L.used) CUDA_OK(cudaStreamWaitEvent(st, L.ev_out, 0));
+        if (codec == RNSC_RC) rc = rnsc_dev_rc_decode(c, (const uint8_t*)L.comp.p, (const uint64_t*)L.off_a.p, (const uint32_t*)L.n.p, (const uint64_t*)L.off_b.p, m, (int16_t*)L.samples.p, (int32_t*)L.status.p, st);
+        else rc = launch_decode(c, codec, (const uint8_t*)L.comp.p, (const uint64_t*)L.off_a.p, (const uint32_t*)L.n.p, (const uint64_t*)L.off_b.p, m, max_n, (int16_t*)L.samples.p, (int32_t*)L.status.p, st);
+        if (rc) break;
+        CUDA_OK(cudaEventRecord(L.ev_dec, st));
+        // ---- D2H ----
+        CUDA_OK(cudaStreamWaitEvent(c->d2h, L.ev_dec, 0));
+        CUDA_OK(cudaMemcpyAsync(status + first, L.status.p, m * 4, cudaMemcpyDeviceToHost, c->d2h));
+        if (dense) CUDA_OK(cudaMemcpyAsync(samples + sample_off[first], L.samples.p, sb * 2, cudaMemcpyDeviceToHost, c->d2h));
+        else for (size_t i = 0; i < m; ++i) if (n[first + i]) CUDA_OK(cudaMemcpyAsync(samples + sample_off[first + i], (int16_t*)L.samples.p + soff[i], (size_t)n[first + i] * 2, cudaMemcpyDeviceToHost, c->d2h));
+        CUDA_OK(cudaEventRecord(L.ev_out, c->d2h));
+        L.used = true;
+        first = last; ++slice;
     }
-    coff[nchunks] = cb; soff[nchunks] = sb;
-    if (c->d_comp.reserve(cb + 64) || c->d_samples.reserve(sb * 2 + 64) || c->d_off_a.reserve((nchunks + 1) * 8) || c->d_off_b.reserve((nchunks + 1) * 8) ||
-        c->d_n.reserve(nchunks * 4 + 16) || c->d_status.reserve(nchunks * 4 + 16))
-        return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
-    cudaStream_t st = c->stream;
-    bool contiguous = true;
-    for (size_t i = 0; i < nchunks; ++i) if (comp_off[i] - comp_off[0] != coff[i]) { contiguous = false; break; }
-    if (contiguous) CUDA_OK(cudaMemcpyAsync(c->d_comp.p, comp + comp_off[0], cb, cudaMemcpyHostToDevice, st));
-    else for (size_t i = 0; i < nchunks; ++i) CUDA_OK(cudaMemcpyAsync((uint8_t*)c->d_comp.p + coff[i], comp + comp_off[i], comp_off[i + 1] - comp_off[i], cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemsetAsync((uint8_t*)c->d_comp.p + cb, 0, 32, st));
-    CUDA_OK(cudaMemcpyAsync(c->d_off_a.p, coff.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(c->d_off_b.p, soff.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(c->d_n.p, n, nchunks * 4, cudaMemcpyHostToDevice, st));
-    int r;
-    if (codec == RNSC_RC) r = rnsc_dev_rc_decode(c, (const uint8_t*)c->d_comp.p, (const uint64_t*)c->d_off_a.p, (const uint32_t*)c->d_n.p, (const uint64_t*)c->d_off_b.p, nchunks, (int16_t*)c->d_samples.p, (int32_t*)c->d_status.p, st);
-    else r = launch_decode(c, codec, (const uint8_t*)c->d_comp.p, (const uint64_t*)c->d_off_a.p, (const uint32_t*)c->d_n.p, (const uint64_t*)c->d_off_b.p, nchunks, max_n, (int16_t*)c->d_samples.p, (int32_t*)c->d_status.p, st);
-    if (r) return r;
-    CUDA_OK(cudaMemcpyAsync(status, c->d_status.p, nchunks * 4, cudaMemcpyDeviceToHost, st));
-    bool dense = true;
-    for (size_t i = 0; i < nchunks; ++i) if (sample_off[i] - sample_off[0] != soff[i]) { dense = false; break; }
-    if (dense) CUDA_OK(cudaMemcpyAsync(samples + sample_off[0], c->d_samples.p, sb * 2, cudaMemcpyDeviceToHost, st));
-    else for (size_t i = 0; i < nchunks; ++i) if (n[i]) CUDA_OK(cudaMemcpyAsync(samples + sample_off[i], (int16_t*)c->d_samples.p + soff[i], (size_t)n[i] * 2, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    return RNSC_OK;
+    CUDA_OK(cudaStreamSynchronize(c->h2d));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->d2h));
+    for (int k = 0; k < 2; ++k) c->lane[k].used = false;
+    return rc;
 }
 
 int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, size_t nchunks,

@@ -23,6 +23,15 @@ struct FastParams {
     const uint8_t* comp; const uint64_t* comp_off; const uint32_t* n; const uint64_t* sample_off;
     int16_t* samples; int32_t* status; int codec;
     const ChunkPlan* plans; const uint32_t* list; const uint32_t* count; uint32_t* counter;
+    unsigned long long* prof;    // optional (rnsc_set_profiling): 8 phase cycle counters of this size class, summed over CTAs
+};
+
+// Phase timing for tuning: thread 0 of every CTA adds the cycles since the previous mark to prof[phase].
+enum { PH_STAGE = 0, PH_HUF1 = 1, PH_HUFSCAN = 2, PH_HUF2 = 3, PH_SEQ = 4, PH_UNPACK = 5, PH_OTHER = 6, PH_CHUNKS = 7 };
+struct PhaseClock {
+    unsigned long long* prof; long long t;
+    __device__ __forceinline__ void start(unsigned long long* p) { prof = p; if (prof && threadIdx.x == 0) t = clock64(); }
+    __device__ __forceinline__ void mark(int phase) { if (prof && threadIdx.x == 0) { const long long n = clock64(); atomicAdd(prof + phase, (unsigned long long)(n - t)); t = n; } }
 };
 
 template <int NTH>
@@ -124,7 +133,7 @@ __device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, c
 // Decodes every Huffman stream of the chunk (ws->head.st[]) from the staged chunk into the region. Three barriers
 // in the common case. Returns 0 on success (same value in all threads).
 template <int NTH>
-__device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region)
+__device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock& pc)
 {
     constexpr int NW = NTH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,6 +156,7 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region)
         huf_walk(words, abit, tab, L, p, lim, my_cnt);
         my_end = p;
     }
+    pc.mark(PH_HUF1);
     uint32_t inc;
     for (int round = 0;; ++round) {
         inc = warp_inclusive_scan(active ? my_cnt : 0u);
@@ -170,6 +180,7 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region)
     const uint32_t ex = __shfl_sync(0xffffffffu, wex, warp) + inc - (active ? my_cnt : 0u);
     const uint32_t base = __shfl_sync(0xffffffffu, wex, (int)(t0 >> 5)) + ((t0 & 31u) ? ws->sub_inc[t0 - 1] : 0u);
     const uint32_t off = ex - base;
+    pc.mark(PH_HUFSCAN);
     bool bad = false;
     if (active && (uint32_t)tid + 1 == hd.st_first[j + 1]) bad = (my_end != T) || (off + my_cnt != sp.count);
     if (active && my_cnt && off < sp.count) {
@@ -185,7 +196,9 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region)
         }
         while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --rem; }
     }
-    return __syncthreads_or(bad);
+    const int r = __syncthreads_or(bad);
+    pc.mark(PH_HUF2);
+    return r;
 }
 
 // Executes the LZ sequences of one frame: literal runs by all threads, matches in order by warp 0.
@@ -241,7 +254,7 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, uin
 
 // Decodes chunk c into stream views (ws->view) and ws->status. Must be entered by the whole CTA after a barrier.
 template <int NTH>
-__device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, uint32_t c, uint32_t parity)
+__device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, uint32_t c, uint32_t parity, PhaseClock& pc)
 {
     const int tid = threadIdx.x;
     const ChunkPlan* pl = P.plans + c;
@@ -274,11 +287,13 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     for (uint32_t i = 0; i < hd.nfill; ++i) { uint8_t* d = region + hd.fill[i].dst_off; for (uint32_t q = tid; q < hd.fill[i].len; q += NTH) d[q] = (uint8_t)hd.fill[i].value; }
     mbar_wait(&ws->mbar, parity);
     __syncthreads();
-    if (hd.nst && fast_huffman<NTH>(ws, region)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
+    pc.mark(PH_STAGE);
+    if (hd.nst && fast_huffman<NTH>(ws, region, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
     for (uint32_t i = 0; i < hd.nsop; ++i) fast_exec_sequences<NTH>(ws, hd.sop[i], region);
     if (tid < 5) { ws->view[tid].p = region + hd.view[tid].off; ws->view[tid].len = hd.view[tid].len; }
     if (tid == 0 && hd.view_status != RNSC_OK) ws->status = hd.view_status;
     __syncthreads();
+    pc.mark(PH_SEQ);
 }
 
 }  // namespace rnsc

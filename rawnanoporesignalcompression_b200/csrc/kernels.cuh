@@ -152,10 +152,11 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
     if (tid == 0) { mbar_init(&ws->mbar, 1); const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
     __syncthreads();
     uint32_t parity = 0;
+    PhaseClock pc; pc.start(P.prof);
     for (;;) {
         const uint32_t c = ws->next;            // thread 0 replaces it (prefetch) only after the first barrier of the chunk
         if (c == FAST_NONE) break;
-        fast_decode_chunk<NTH>(ws, region, P, c, parity);
+        fast_decode_chunk<NTH>(ws, region, P, c, parity, pc);
         parity ^= 1u;
         const uint32_t n = P.n[c];
         if (ws->status == RNSC_OK && n > 0) {
@@ -163,8 +164,10 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
             if (r && tid == 0) ws->status = r;
         }
         __syncthreads();
-        if (tid == 0) P.status[c] = ws->status;
+        pc.mark(PH_UNPACK);
+        if (tid == 0) { P.status[c] = ws->status; if (P.prof) atomicAdd(P.prof + PH_CHUNKS, 1ull); }
         __syncthreads();                        // the region and ws->status are reused by the next chunk
+        pc.mark(PH_OTHER);
     }
 }
 

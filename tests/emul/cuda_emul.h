@@ -44,6 +44,7 @@ inline void __syncthreads() { emul::block_barrier(); }
 inline int __syncthreads_or(int p) { static int acc; static int res; if (threadIdx.x == 0) acc = 0; emul::block_barrier(); acc |= (p != 0); emul::block_barrier(); res = acc; emul::block_barrier(); return res; }
 inline int __syncthreads_count(int p) { static int acc; static int res; if (threadIdx.x == 0) acc = 0; emul::block_barrier(); acc += (p != 0); emul::block_barrier(); res = acc; emul::block_barrier(); return res; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { unsigned long long all[32]; emul::warp_exchange(mask, 0, all); }
+inline long long clock64() { static long long t = 0; return ++t; }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 
@@ -113,6 +114,7 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return 0; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)1; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
