@@ -184,17 +184,42 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
     bool bad = false;
     if (active && (uint32_t)tid + 1 == hd.st_first[j + 1]) bad = (my_end != T) || (off + my_cnt != sp.count);
     if (active && my_cnt && off < sp.count) {
-        uint8_t* o = region + sp.out + off;
         uint32_t p = my_start, rem = min(my_cnt, sp.count - off), hi, lo, nb, e;      // clamped: a corrupt stream cannot write outside its output
-        while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --rem; }
-        while (rem >= 4) {
-            bits_ending_at(words, abit - p, hi, lo);
-            uint32_t word = 0, adv = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { RNSC_HUF_STEP(hi, lo, tab, L, nb, e); adv += nb; word |= (e & 0xFFu) << (8 * q); }
-            *(uint32_t*)o = word; o += 4; p += adv; rem -= 4;
+        uint32_t li = sp.lit0 + off;                                                   // literal index of my first symbol
+        // Literal runs: without sequences the whole frame is one run at shift 0; with sequences run i (the literals in
+        // front of match i, then the tail) lands at its final position out_pos[i] = lit_pos[i] + sum of earlier matches.
+        const uint32_t* sq = ws->seq + SEQ_WORDS * sp.seq_base;
+        const uint32_t nseq = sp.nseq;
+        uint32_t seg = 0;
+        if (nseq) {   // last run whose first literal index is <= li (runs may be empty)
+            uint32_t lo_i = 0, hi_i = nseq;                                            // run nseq = tail, starts at lit_end
+            const uint32_t lit_end = sq[SEQ_WORDS * (nseq - 1) + 3] + sq[SEQ_WORDS * (nseq - 1)];
+            if (li >= lit_end) seg = nseq;
+            else { while (lo_i + 1 < hi_i) { const uint32_t mid = (lo_i + hi_i) >> 1; if (sq[SEQ_WORDS * mid + 3] <= li) lo_i = mid; else hi_i = mid; } seg = lo_i; }
         }
-        while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --rem; }
+        while (rem) {
+            uint32_t take = rem, shift = 0;
+            if (nseq) {
+                const uint32_t last = nseq - 1;
+                const uint32_t lit_end = sq[SEQ_WORDS * last + 3] + sq[SEQ_WORDS * last], out_end = sq[SEQ_WORDS * last + 4] + sq[SEQ_WORDS * last] + sq[SEQ_WORDS * last + 1];
+                const uint32_t run_lit = seg < nseq ? sq[SEQ_WORDS * seg + 3] : lit_end, run_out = seg < nseq ? sq[SEQ_WORDS * seg + 4] : out_end;
+                const uint32_t run_end = seg < nseq ? run_lit + sq[SEQ_WORDS * seg] : sp.regen;
+                shift = run_out - run_lit;
+                take = min(rem, run_end > li ? run_end - li : 0u);
+                if (++seg > nseq + 1) break;                                        // cannot happen for a consistent plan
+            }
+            uint8_t* o = region + sp.out + li + shift;
+            li += take; rem -= take;
+            while (((uintptr_t)o & 3u) && take) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --take; }
+            while (take >= 4) {
+                bits_ending_at(words, abit - p, hi, lo);
+                uint32_t word = 0, adv = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { RNSC_HUF_STEP(hi, lo, tab, L, nb, e); adv += nb; word |= (e & 0xFFu) << (8 * q); }
+                *(uint32_t*)o = word; o += 4; p += adv; take -= 4;
+            }
+            while (take) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --take; }
+        }
     }
     const int r = __syncthreads_or(bad);
     pc.mark(PH_HUF2);
@@ -212,25 +237,7 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, uin
     const uint32_t lit_end = sq[SEQ_WORDS * (nseq - 1) + 3] + sq[SEQ_WORDS * (nseq - 1)];                  // literals consumed by the sequences
     const uint32_t out_end = sq[SEQ_WORDS * (nseq - 1) + 4] + sq[SEQ_WORDS * (nseq - 1)] + sq[SEQ_WORDS * (nseq - 1) + 1];
     if (op.ltype == 2) {
-        // Huffman literals sit at dst[0 .. regen): move run i up by the match bytes in front of it, last run first.
-        // Source and destination overlap, so every block is read to registers, then written, between barriers.
-        constexpr uint32_t B = NTH * 16;
-        for (uint32_t i = nseq; i >= 1; --i) {
-            const uint32_t lp = i < nseq ? sq[SEQ_WORDS * i + 3] : lit_end, opos = i < nseq ? sq[SEQ_WORDS * i + 4] : out_end;
-            const uint32_t len = i < nseq ? sq[SEQ_WORDS * i] : op.regen - lit_end;
-            const uint8_t* s = dst + lp; uint8_t* d = dst + opos;
-            if (s == d || len == 0) continue;
-            for (uint32_t done = 0; done < len; done += B) {
-                const uint32_t blen = min(B, len - done), b0 = len - done - blen;     // blocks from the top down
-                uint8_t t[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) if ((uint32_t)q * NTH < blen) { const uint32_t x = tid + q * NTH; t[q] = x < blen ? s[b0 + x] : (uint8_t)0; }
-                __syncthreads();
-#pragma unroll
-                for (int q = 0; q < 16; ++q) if ((uint32_t)q * NTH < blen) { const uint32_t x = tid + q * NTH; if (x < blen) d[b0 + x] = t[q]; }
-                __syncthreads();
-            }
-        }
+        // Huffman literals were written to their final places by fast_huffman (which ended with a barrier)
     } else {
         for (uint32_t i = 0; i <= nseq; ++i) {
             const uint32_t lp = i < nseq ? sq[SEQ_WORDS * i + 3] : lit_end, opos = i < nseq ? sq[SEQ_WORDS * i + 4] : out_end;

@@ -45,8 +45,10 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
     uint16_t cls_sym[14];        // index into sorted[] of the first symbol of class w
     uint8_t sorted[256];         // symbols of weight > 0 ordered by (weight, symbol)
 };
-struct StreamPlan { uint32_t tbits, abit, count, out, tab_off, log; };   // one Huffman bitstream: payload bits, absolute bit address of the
-                                                                         // end mark in the region, symbols, region offset of the output, its table
+// One Huffman bitstream: payload bits, absolute bit address of the end mark in the region, symbols, region offset of
+// the frame's output, literal index of its first symbol, its table; and, when LZ sequences follow, where they are in
+// ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
+struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, seq_base, nseq, regen, pad0, pad1; };
 struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
 struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base; };   // LZ sequences of a frame; lit = region offset of raw literals or the RLE byte
 struct ViewPlan { uint32_t off, len; };                                  // stream k of the splitter inverse = region[off .. off+len)
@@ -324,8 +326,9 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 StreamPlan sp;
                 sp.tbits = fp.s_tbits[j]; sp.abit = 8 * (cbase + fp.s_beg[j]) + fp.s_tbits[j];
                 sp.count = fp.nstreams == 1 ? fp.regen : (j < 3 ? q : fp.regen - 3 * q);
-                sp.out = fp.dst_off + (fp.nstreams == 1 ? 0 : j * q);
+                sp.out = fp.dst_off; sp.lit0 = fp.nstreams == 1 ? 0 : j * q;
                 sp.tab_off = pl->h[fp.huf].tab_off; sp.log = pl->h[fp.huf].log;
+                sp.seq_base = fp.seq_base; sp.nseq = fp.nseq; sp.regen = fp.regen; sp.pad0 = sp.pad1 = 0;
                 if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }

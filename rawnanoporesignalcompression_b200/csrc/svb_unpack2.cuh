@@ -120,10 +120,15 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
         uint32_t val[S]; uint32_t acc = 0;
         if (WIN) {
             uint32_t sw[2] = {0, 0}, mlo[2] = {0, 0}, mhi[2] = {0, 0};
+            uint32_t zq = 0, lused = 0, lbase = 0;       // the next (up to two) large values of this thread, 16 bits each
+            auto load_large = [&](uint32_t k) -> uint32_t {
+                return k < c3 ? ((((uint32_t)ld8(s4 + p3 + k) << 8) + ld8(s3 + p3 + k) + (CODEC == RNSC_C5 ? 273u : 0u)) & 0xFFFFu) : 0u;
+            };
             if (cnt && ok) {
                 const uint32_t n1a = __popc(m1 & 0xFFFFu), n2a = __popc(m2 & 0xFFFFu);
                 sw[0] = load_bits32(s1, 4 * p1); sw[1] = load_bits32(s1, 4 * (p1 + n1a));
                 load_bits64(s2, 8 * p2, mlo[0], mhi[0]); load_bits64(s2, 8 * (p2 + n2a), mlo[1], mhi[1]);
+                if (m3) zq = load_large(0) | (load_large(1) << 16);       // rare (class >= 273): low and high byte streams
             }
 #pragma unroll
             for (int j = 0; j < S; ++j) {
@@ -134,9 +139,9 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
                 if (isM) z = (mlo[h] & 255u) + (CODEC == RNSC_C5 ? 17u : 0u);
                 if (isS) sw[h] >>= 4;
                 if (isM) { mlo[h] = __funnelshift_r(mlo[h], mhi[h], 8); mhi[h] >>= 8; }
-                if ((m3 >> (2 * j)) & 1u) {      // rare: large value, low and high byte streams
-                    z = (((uint32_t)ld8(s4 + p3) << 8) + ld8(s3 + p3) + (CODEC == RNSC_C5 ? 273u : 0u)) & 0xFFFFu;
-                    ++p3;
+                if ((m3 >> (2 * j)) & 1u) {
+                    if (lused == 2) { zq = load_large(lbase + 2) | (load_large(lbase + 3) << 16); lbase += 2; lused = 0; }
+                    z = zq & 0xFFFFu; zq >>= 16; ++lused;
                 }
                 acc += zz_dec(z);
                 val[j] = acc;
