@@ -312,14 +312,55 @@ def run_rnsc(args):
     peak, peak_src = measured_peak()
     k_ms = float(np.mean(kern_ms))
     achieved = (cbytes + 2.0 * total) / (k_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_decode_chunks", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+    roof = {"bound": "hbm", "kernel": "rnsc_dev_decode: k_plan_chunks, then k_decode_fast<256|512|1024> and k_decode_chunks concurrently (one step = one such launch group)", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(cbytes + 2 * total), "avg_launch_ms": round(k_ms, 4)}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp):      # dram__bytes_read+write of the launch group from an `ncu --set full` capture, per algorithmic byte
         try:
-            roof["traffic"] = json.load(open(tp)).get("k_decode_chunks_bytes_per_launch")
+            tj = json.load(open(tp))
+            roof["traffic"] = int(round(tj["dram_bytes_per_algorithmic_byte"] * (cbytes + 2.0 * total)))
+            roof["traffic_source"] = tj.get("source")
         except Exception:
             pass
+
+    # ---- other legs of the path, device resident, for the report (not the headline): splitter-stage encode and VBZ ----
+    extra = {}
+    if not args.no_extra:
+        def timed(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        x_reads = min(args.reads, args.extra_reads)
+        per = (wl["lengths"] + synth.DEFAULT_CHUNK_SIZE - 1) // synth.DEFAULT_CHUNK_SIZE
+        x_ch = int(per[:x_reads].sum()); x_samples = int(wl["lengths"][:x_reads].sum())
+        xs = wl["d_sig"][:x_samples]
+        for cname in (args.codec, "VBZ"):
+            cid = codec_id(cname)
+            cap = int(sum(cd.lib.rnsc_max_stream_bytes(cid, int(k)) for k in n[:x_ch]))
+            d_streams = torch.empty(cap, dtype=torch.uint8, device=dev)
+            d_soff = torch.empty(5 * x_ch + 1, dtype=torch.int64, device=dev)
+            ms = timed(lambda: cd.dev_svb_encode(cid, xs, d_off[:x_ch], d_n[:x_ch], d_streams, d_soff))
+            sbytes = int(d_soff[-1].item())
+            extra[f"{cname}_splitter_encode"] = {"value": round(2e-6 * x_samples / ms, 2), "unit": UNIT, "stream_bytes_per_sample": round(sbytes / x_samples, 4),
+                                                 "roofline_frac": round((2.0 * x_samples + sbytes) / (ms * 1e-3) / 1e9 / peak, 4)}
+            del d_streams, d_soff
+        # VBZ whole-chunk decode (frames with ~600 LZ sequences per chunk: mostly the general decoder today)
+        host = xs.cpu().numpy()
+        vcomp, vcoff, vst = cd.compress_flat(host, off[:x_ch].astype(np.uint64), n[:x_ch], 0)
+        if not vst.any():
+            dv_comp = torch.from_numpy(np.concatenate([vcomp, np.zeros(64, np.uint8)])).to(dev)
+            dv_coff = torch.from_numpy(vcoff.astype(np.int64)).to(dev)
+            dv_out = torch.empty(x_samples, dtype=torch.int16, device=dev); dv_st = torch.empty(x_ch, dtype=torch.int32, device=dev)
+            ms = timed(lambda: cd.dev_decode(0, dv_comp, dv_coff, d_n[:x_ch], d_off[:x_ch], max_n, dv_out, dv_st))
+            extra["VBZ_decode"] = {"value": round(2e-6 * x_samples / ms, 2), "unit": UNIT, "bits_per_sample": round(8.0 * int(vcoff[-1]) / x_samples, 4),
+                                   "bit_exact": bool(torch.equal(dv_out, xs)) and not bool(dv_st.any().item()), "routing": cd.decode_class_counts(torch.cuda.current_stream())}
+            del dv_comp, dv_out
+        extra["sample"] = f"first {x_reads} reads ({x_samples} samples, {x_ch} chunks)"
+        log("extra", extra)
 
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
@@ -388,7 +429,7 @@ def run_rnsc(args):
                           "compressed_bytes_per_gpu": int(cbytes), "sharding": "reads, contiguous ranges, no data-path collective",
                           "l2": "inputs (compressed set) and outputs far exceed the 126 MB L2; no flush needed"},
                "bits_per_sample": round(8.0 * all_cbytes / all_samples, 4), "bit_exact": bit_exact,
-               "gpu_launches": int(launches), "chunk_routing": {"fast_4_per_sm": classes[0], "fast_2_per_sm": classes[1], "fast_1_per_sm": classes[2], "general": classes[3]}, "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu,
+               "gpu_launches": int(launches), "other_legs": extra, "chunk_routing": {"fast_4_per_sm": classes[0], "fast_2_per_sm": classes[1], "fast_1_per_sm": classes[2], "general": classes[3]}, "clocks": clocks, "roofline": roof, "e2e": e2e, "cpu_baseline": cpu,
                "encode": {"value": round(wl["encode_gbs"], 3), "unit": UNIT,
                           "note": "whole-chunk encode through rnsc_compress_batch while building the workload: pageable host in/out, device splitter, "
                                   "host libzstd level-1 frame stage (byte-identical to the reference); untimed-region number, for orientation"}}
@@ -446,6 +487,8 @@ def main():
     ap.add_argument("--e2e-reads", type=int, default=0)
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the splitter-encode / VBZ legs")
+    ap.add_argument("--extra-reads", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print per-phase SM cycles of the fast decode kernels (tuning aid) to stderr")
     args = ap.parse_args()

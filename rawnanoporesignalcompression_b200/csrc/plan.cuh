@@ -91,18 +91,19 @@ static_assert(sizeof(PlanScratch) == 900, "PlanScratch layout");
 __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 
 // Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
-// an FSE description). Returns 0 on success.
+// an FSE description). Returns 0 on success. Single exit (the planner runs one chunk per lane).
 __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, const uint32_t* tll, int ll_log, const uint32_t* tof, int of_log,
                                      const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out)
 {
     BwdBits b;
-    if (bwd_init(b, bs, bs_size)) return 1;
-    uint32_t sl = bwd_read(b, ll_log), so = bwd_read(b, of_log), sm = bwd_read(b, ml_log);
+    bool bad = bwd_init(b, bs, bs_size) != 0;
+    uint32_t sl = 0, so = 0, sm = 0;
+    if (!bad) { sl = bwd_read(b, ll_log); so = bwd_read(b, of_log); sm = bwd_read(b, ml_log); }
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8, op = 0, lp = 0;
-    for (uint32_t i = 0; i < nseq; ++i) {
+    for (uint32_t i = 0; i < nseq && !bad; ++i) {
         const uint32_t el = tll[sl], eo = tof[so], em = tml[sm];
         const uint32_t llc = el & 0xFF, ofc = eo & 0xFF, mlc = em & 0xFF;
-        if (llc > 35 || mlc > 52 || ofc > 31) return 1;
+        if (llc > 35 || mlc > 52 || ofc > 31) { bad = true; break; }
         const uint32_t ofv = (1u << ofc) + bwd_read(b, (int)ofc);
         const uint32_t ml = kMLBase[mlc] + bwd_read(b, kMLBits[mlc]);
         const uint32_t ll = kLLBase[llc] + bwd_read(b, kLLBits[llc]);
@@ -113,7 +114,7 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
             if (idx == 0) offset = rep0;
             else {
                 offset = idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1);
-                if (offset == 0) return 1;
+                if (offset == 0) { bad = true; break; }
                 if (idx > 1) rep2 = rep1;
                 rep1 = rep0; rep0 = offset;
             }
@@ -123,80 +124,91 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
             sm = (em >> 16) + bwd_read(b, (int)((em >> 8) & 0xFF));
             so = (eo >> 16) + bwd_read(b, (int)((eo >> 8) & 0xFF));
         }
-        if (b.overflow) return 1;
-        if (lp + ll > regen || op + ll + ml > fcs || offset > op + ll) return 1;
+        if (b.overflow || lp + ll > regen || op + ll + ml > fcs || offset > op + ll) { bad = true; break; }
         out[SEQ_WORDS * i] = ll; out[SEQ_WORDS * i + 1] = ml; out[SEQ_WORDS * i + 2] = offset; out[SEQ_WORDS * i + 3] = lp; out[SEQ_WORDS * i + 4] = op;
         op += ll + ml; lp += ll;
     }
-    if (b.bitpos != 0) return 1;
-    if (op + (regen - lp) != fcs) return 1;
-    return 0;
+    if (!bad && (b.bitpos != 0 || op + (regen - lp) != fcs)) bad = true;
+    return bad ? 1 : 0;
 }
 
-// Plans one compressed block (the only block of its frame). Returns 0 = planned, 1 = route to the slow path.
-__device__ inline int plan_block(const uint8_t* chunk, uint32_t boff, uint32_t size, FramePlan& fp, ChunkPlan* pl, uint32_t& nhuf, uint32_t& nseq_tot,
+// Plans one compressed block (the only block of its frame). Returns 0 = planned, 1 = route to the slow path (or
+// `enable` false). Every lane of the warp calls it for every frame (enable = false when the lane has nothing to plan):
+// the body is single-exit so that the warp can reconverge in front of each long loop.
+__device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t boff, uint32_t size, FramePlan& fp, ChunkPlan* pl, uint32_t& nhuf, uint32_t& nseq_tot,
                                  PlanScratch* sc, const uint32_t* deftab)
 {
     const uint8_t* src = chunk + boff;
-    if (size < 1) return 1;
-    const uint32_t b0 = ldg8(src);
+    bool bad = !enable || size < 1;
+    const uint32_t b0 = bad ? 0 : ldg8(src);
     const uint32_t ltype = b0 & 3, sf = (b0 >> 2) & 3;
     uint32_t lhs = 0, regen = 0, comp = 0, nstreams = 1;
-    if (ltype == 3) return 1;                       // treeless literals need a previous block's table
-    if (ltype < 2) {
-        if (sf == 0 || sf == 2) { lhs = 1; regen = b0 >> 3; }
-        else if (sf == 1) { if (size < 2) return 1; lhs = 2; regen = (b0 >> 4) | (ldg8(src + 1) << 4); }
-        else { if (size < 3) return 1; lhs = 3; regen = (b0 >> 4) | (ldg8(src + 1) << 4) | (ldg8(src + 2) << 12); }
-    } else {
-        if (size < 3) return 1;
-        uint64_t h = 0; for (uint32_t i = 0; i < 5 && i < size; ++i) h |= (uint64_t)ldg8(src + i) << (8 * i);
-        if (sf == 0 || sf == 1) { lhs = 3; regen = (uint32_t)(h >> 4) & 0x3FF; comp = (uint32_t)(h >> 14) & 0x3FF; nstreams = sf ? 4 : 1; }
-        else if (sf == 2) { lhs = 4; regen = (uint32_t)(h >> 4) & 0x3FFF; comp = (uint32_t)(h >> 18) & 0x3FFF; nstreams = 4; }
-        else { if (size < 5) return 1; lhs = 5; regen = (uint32_t)(h >> 4) & 0x3FFFF; comp = (uint32_t)(h >> 22) & 0x3FFFF; nstreams = 4; }
+    if (ltype == 3) bad = true;                     // treeless literals need a previous block's table
+    if (!bad) {
+        if (ltype < 2) {
+            if (sf == 0 || sf == 2) { lhs = 1; regen = b0 >> 3; }
+            else if (sf == 1) { if (size < 2) bad = true; else { lhs = 2; regen = (b0 >> 4) | (ldg8(src + 1) << 4); } }
+            else { if (size < 3) bad = true; else { lhs = 3; regen = (b0 >> 4) | (ldg8(src + 1) << 4) | (ldg8(src + 2) << 12); } }
+        } else if (size < 3) bad = true;
+        else {
+            uint64_t h = 0; for (uint32_t i = 0; i < 5 && i < size; ++i) h |= (uint64_t)ldg8(src + i) << (8 * i);
+            if (sf == 0 || sf == 1) { lhs = 3; regen = (uint32_t)(h >> 4) & 0x3FF; comp = (uint32_t)(h >> 14) & 0x3FF; nstreams = sf ? 4 : 1; }
+            else if (sf == 2) { lhs = 4; regen = (uint32_t)(h >> 4) & 0x3FFF; comp = (uint32_t)(h >> 18) & 0x3FFF; nstreams = 4; }
+            else { if (size < 5) bad = true; lhs = 5; regen = (uint32_t)(h >> 4) & 0x3FFFF; comp = (uint32_t)(h >> 22) & 0x3FFFF; nstreams = 4; }
+        }
     }
-    if (regen > ZSTD_BLOCK_MAX) return 1;
+    if (regen > ZSTD_BLOCK_MAX) bad = true;
     const uint32_t lit_section = lhs + (ltype == 0 ? regen : (ltype == 1 ? 1 : comp));
-    if (lit_section >= size) return 1;              // the sequences header needs at least one byte
+    if (!bad && lit_section >= size) bad = true;    // the sequences header needs at least one byte
     // ---- sequences header ----
     uint32_t nseq = 0, modes = 0, so = lit_section;
-    const uint32_t n0 = ldg8(src + so);
-    if (n0 == 0) { so += 1; if (so != size) return 1; }
-    else {
-        if (n0 < 128) { nseq = n0; so += 1; }
-        else if (n0 < 255) { if (so + 2 > size) return 1; nseq = ((n0 - 128) << 8) + ldg8(src + so + 1); so += 2; }
-        else { if (so + 3 > size) return 1; nseq = ldg8(src + so + 1) + (ldg8(src + so + 2) << 8) + 0x7F00; so += 3; }
-        if (so >= size) return 1;
-        modes = ldg8(src + so); so += 1;
-        if (modes & 3) return 1;
-    }
-    if (nseq == 0 && regen != fp.fcs) return 1;
-    fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = nseq_tot;
-    fp.lit_off = ltype == 0 ? boff + lhs : (ltype == 1 ? ldg8(src + lhs) : 0);
-    // ---- Huffman tree description + stream geometry ----
-    if (ltype == 2) {
-        if (nhuf >= PLAN_MAX_HUF) return 1;
-        uint32_t p = lhs, left = comp; int nw = 0;
-        const uint32_t u = huf_read_weights(sc, src + p, left, &nw);
-        if (!u) return 1;
-        p += u; left -= u;
-        uint32_t sz[4];
-        if (nstreams == 1) { sz[0] = left; fp.s_beg[0] = boff + p; }
+    if (!bad) {
+        const uint32_t n0 = ldg8(src + so);
+        if (n0 == 0) { so += 1; if (so != size) bad = true; }
         else {
-            if (left < 6) return 1;
-            sz[0] = ldg8(src + p) | (ldg8(src + p + 1) << 8); sz[1] = ldg8(src + p + 2) | (ldg8(src + p + 3) << 8); sz[2] = ldg8(src + p + 4) | (ldg8(src + p + 5) << 8);
-            if (6 + sz[0] + sz[1] + sz[2] > left) return 1;
-            sz[3] = left - 6 - sz[0] - sz[1] - sz[2];
-            if (3 * ((regen + 3) / 4) > regen) return 1;
-            fp.s_beg[0] = boff + p + 6; fp.s_beg[1] = fp.s_beg[0] + sz[0]; fp.s_beg[2] = fp.s_beg[1] + sz[1]; fp.s_beg[3] = fp.s_beg[2] + sz[2];
+            if (n0 < 128) { nseq = n0; so += 1; }
+            else if (n0 < 255) { if (so + 2 > size) bad = true; else { nseq = ((n0 - 128) << 8) + ldg8(src + so + 1); so += 2; } }
+            else { if (so + 3 > size) bad = true; else { nseq = ldg8(src + so + 1) + (ldg8(src + so + 2) << 8) + 0x7F00; so += 3; } }
+            if (!bad && so >= size) bad = true;
+            if (!bad) { modes = ldg8(src + so); so += 1; if (modes & 3) bad = true; }
         }
-        for (uint32_t j = 0; j < nstreams; ++j) {
-            if (sz[j] == 0) return 1;
+    }
+    if (!bad && nseq == 0 && regen != fp.fcs) bad = true;
+    if (!bad) {
+        fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = nseq_tot;
+        fp.lit_off = ltype == 0 ? boff + lhs : (ltype == 1 ? ldg8(src + lhs) : 0);
+    }
+    // ---- Huffman tree description + stream geometry (every lane walks through huf_read_weights) ----
+    bool huf = !bad && ltype == 2;
+    if (huf && nhuf >= PLAN_MAX_HUF) { bad = true; huf = false; }
+    int nw = 0;
+    const uint32_t u = huf_read_weights<PlanScratch, true>(sc, src + lhs, huf ? comp : 0u, &nw);
+    if (huf && !u) { bad = true; huf = false; }
+    if (huf) {
+        uint32_t p = lhs + u, left = comp - u;
+        uint32_t sz[4] = {0, 0, 0, 0};
+        if (nstreams == 1) { sz[0] = left; fp.s_beg[0] = boff + p; }
+        else if (left < 6) bad = true;
+        else {
+            sz[0] = ldg8(src + p) | (ldg8(src + p + 1) << 8); sz[1] = ldg8(src + p + 2) | (ldg8(src + p + 3) << 8); sz[2] = ldg8(src + p + 4) | (ldg8(src + p + 5) << 8);
+            if (6 + sz[0] + sz[1] + sz[2] > left || 3 * ((regen + 3) / 4) > regen) bad = true;
+            else {
+                sz[3] = left - 6 - sz[0] - sz[1] - sz[2];
+                fp.s_beg[0] = boff + p + 6; fp.s_beg[1] = fp.s_beg[0] + sz[0]; fp.s_beg[2] = fp.s_beg[1] + sz[1]; fp.s_beg[3] = fp.s_beg[2] + sz[2];
+            }
+        }
+        for (uint32_t j = 0; j < nstreams && !bad; ++j) {
+            if (sz[j] == 0) { bad = true; break; }
             const uint32_t last = ldg8(chunk + fp.s_beg[j] + sz[j] - 1);
-            if (last == 0) return 1;
+            if (last == 0) { bad = true; break; }
             fp.s_tbits[j] = 8 * (sz[j] - 1) + (uint32_t)highbit32(last);
         }
-        // table recipe: weight classes in ascending weight (= descending code length), symbols in natural order
-        HufPlan* hp = &pl->h[nhuf];
+        if (bad) huf = false;
+    }
+    warp_converge<true>();
+    // table recipe: weight classes in ascending weight (= descending code length), symbols in natural order
+    HufPlan* hp = &pl->h[huf ? nhuf : 0];
+    if (huf) {
         const int maxBits = sc->huf_log;
         uint32_t e = 0, s = 0;                       // huf_read_weights left the per-weight symbol counts in rank_cnt
         for (int k = 1; k <= maxBits; ++k) {
@@ -207,39 +219,44 @@ __device__ inline int plan_block(const uint8_t* chunk, uint32_t boff, uint32_t s
         }
         hp->cls_start[0] = 0; hp->cls_sym[0] = 0;
         for (int k = maxBits + 1; k < 14; ++k) { hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s; }   // e == 2^maxBits
-        for (int i = 0; i < nw; ++i) { const uint32_t w = sc->weights[i]; if (w) hp->sorted[sc->rank_cnt[w]++] = (uint8_t)i; }
         hp->log = (uint32_t)maxBits;
-        fp.huf = nhuf++;
     }
+    warp_converge<true>();
+    {
+        const int lim = huf ? nw : 0;
+        for (int i = 0; i < lim; ++i) { const uint32_t w = sc->weights[i]; if (w) hp->sorted[sc->rank_cnt[w]++] = (uint8_t)i; }
+    }
+    if (huf) fp.huf = nhuf++;
+    warp_converge<true>();
     // ---- sequences: predefined, RLE or FSE-described tables (repeat mode is invalid in a first block) ----
-    if (nseq) {
-        if (nseq_tot + nseq > PLAN_MAX_SEQ) return 1;
+    if (!bad && nseq) {
+        if (nseq_tot + nseq > PLAN_MAX_SEQ) bad = true;
         uint32_t rle[3] = {0, 0, 0};
-        const uint32_t* tab[3]; int tlog[3];
+        const uint32_t* tab[3] = {deftab, deftab, deftab}; int tlog[3] = {0, 0, 0};
         uint32_t p = so;
-        for (int t = 0; t < 3; ++t) {               // order in the stream: LL, OF, ML
+        for (int t = 0; t < 3 && !bad; ++t) {       // order in the stream: LL, OF, ML
             const uint32_t mode = (modes >> (6 - 2 * t)) & 3;
             const uint32_t max_sym = t == 0 ? 35u : (t == 1 ? 31u : 52u);
             if (mode == 0) { tab[t] = deftab + (t == 0 ? 0 : (t == 1 ? 64 : 96)); tlog[t] = t == 1 ? 5 : 6; }
             else if (mode == 1) {
-                if (p >= size) return 1;
+                if (p >= size) { bad = true; break; }
                 const uint32_t sym = ldg8(src + p); p += 1;
-                if (sym > max_sym) return 1;
+                if (sym > max_sym) { bad = true; break; }
                 rle[t] = sym; tab[t] = &rle[t]; tlog[t] = 0;
             } else if (mode == 2) {
-                int tl, ns;
+                int tl = 0, ns = 0;
                 const uint32_t h = fse_read_ncount(src + p, size - p, sc->norm, (int)max_sym, t == 1 ? 8 : 9, &tl, &ns);
-                if (!h) return 1;
+                if (!h) { bad = true; break; }
                 uint32_t* tt = pl->fse + (t == 0 ? 0 : (t == 1 ? 512 : 768));
                 fse_build(tt, sc->norm, ns, tl, sc->next16);
                 tab[t] = tt; tlog[t] = tl; p += h;
-            } else return 1;
+            } else { bad = true; break; }
         }
-        if (p >= size) return 1;
-        if (plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, pl->seq + SEQ_WORDS * nseq_tot)) return 1;
-        nseq_tot += nseq;
+        if (!bad && p >= size) bad = true;
+        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, pl->seq + SEQ_WORDS * nseq_tot)) bad = true;
+        if (!bad) nseq_tot += nseq;
     }
-    return 0;
+    return bad ? 1 : 0;
 }
 
 __device__ inline void plan_emit(const PlanParams& P, uint32_t c, uint32_t cls)
@@ -262,43 +279,56 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     const uint32_t cbase = REGION_HEAD + phase;                    // region offset of chunk byte 0
     uint32_t region = REGION_HEAD + stage + 16, pos = 0, nhuf = 0, nseq_tot = 0;
     int st = RNSC_OK; bool slow = false;
+    // Uniform frame loop: every lane runs all nf iterations (a lane whose chunk already failed just idles through
+    // them), so that the warp can reconverge at the marked points.
     for (int f = 0; f < nf; ++f) {
-        uint32_t fl;
-        if (f + 1 < nf) {
-            if (pos + 8 > clen) { st = RNSC_ERR_CONTAINER; break; }
-            unsigned long long v = 0; for (int i = 0; i < 8; ++i) v |= (unsigned long long)ldg8(src + pos + i) << (8 * i);
-            pos += 8;
-            if (v > clen - pos) { st = RNSC_ERR_CONTAINER; break; }
-            fl = (uint32_t)v;
-        } else fl = clen - pos;
-        uint32_t hdr, known, ck; uint64_t fcs;
-        const int r = zstd_parse_frame_header(src + pos, fl, &hdr, &fcs, &known, &ck);
-        if (r || !known) { st = RNSC_ERR_NOT_ZSTD; break; }          // ZSTD_getFrameContentSize must succeed
-        if (fcs > bound) { st = RNSC_ERR_REMAINING; break; }
+        warp_converge<true>();
+        uint32_t fl = 0, hdr = 0, known = 0, ck = 0; uint64_t fcs = 0;
+        if (st == RNSC_OK) {
+            if (f + 1 < nf) {
+                if (pos + 8 > clen) st = RNSC_ERR_CONTAINER;
+                else {
+                    unsigned long long v = 0; for (int i = 0; i < 8; ++i) v |= (unsigned long long)ldg8(src + pos + i) << (8 * i);
+                    pos += 8;
+                    if (v > clen - pos) st = RNSC_ERR_CONTAINER; else fl = (uint32_t)v;
+                }
+            } else fl = clen - pos;
+        }
+        if (st == RNSC_OK) {
+            const int r = zstd_parse_frame_header(src + pos, fl, &hdr, &fcs, &known, &ck);
+            if (r || !known) st = RNSC_ERR_NOT_ZSTD;                  // ZSTD_getFrameContentSize must succeed
+            else if (fcs > bound) st = RNSC_ERR_REMAINING;
+        }
+        const bool live = st == RNSC_OK && !slow;
         FramePlan fp;
         fp.kind = FK_RAW; fp.fcs = (uint32_t)fcs; fp.data_off = 0; fp.dst_off = 0; fp.ltype = 0; fp.regen = 0; fp.lit_off = 0; fp.lit_dst = 0;
         fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0;
         for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; }
-        if (!slow) {
+        bool comp_block = false; uint32_t bsz = 0;
+        if (live) {
             if (hdr + 3 > fl) slow = true;
             else {
                 const uint32_t bh = ldg8(src + pos + hdr) | (ldg8(src + pos + hdr + 1) << 8) | (ldg8(src + pos + hdr + 2) << 16);
-                const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
+                const uint32_t last = bh & 1, type = (bh >> 1) & 3;
+                bsz = bh >> 3;
                 const uint32_t body = type == 1 ? 1u : bsz;
                 if (!last || type == 3 || hdr + 3 + body + (ck ? 4 : 0) != fl) slow = true;
                 else if (type == 0) { if (bsz != (uint32_t)fcs) slow = true; fp.kind = FK_RAW; fp.data_off = pos + hdr + 3; }
                 else if (type == 1) { if (bsz != (uint32_t)fcs) slow = true; fp.kind = FK_RLE; fp.data_off = ldg8(src + pos + hdr + 3); }
-                else { fp.kind = FK_COMP; fp.data_off = pos + hdr + 3; if (plan_block(src, pos + hdr + 3, bsz, fp, pl, nhuf, nseq_tot, sc, deftab)) slow = true; }
+                else { fp.kind = FK_COMP; fp.data_off = pos + hdr + 3; comp_block = true; }
             }
         }
-        if (!slow) {
+        comp_block = comp_block && !slow;
+        const int pb = plan_block(comp_block, src, pos + hdr + 3, bsz, fp, pl, nhuf, nseq_tot, sc, deftab);
+        if (comp_block && pb) slow = true;
+        if (st == RNSC_OK && !slow) {
             // placement of the decoded output in the CTA's dynamic region (raw data is used in place; the literals of a
-            // frame with sequences are decoded to the front of dst and moved in place)
+            // frame with sequences are written straight to their final positions)
             const bool zero_copy = fp.kind == FK_RAW || (fp.kind == FK_COMP && fp.ltype == 0 && fp.nseq == 0);
             if (!zero_copy) { fp.dst_off = region; region += align16(fp.fcs) + 16; }
             pl->f[f] = fp;
         }
-        pos += fl;
+        if (st == RNSC_OK) pos += fl;
     }
     if (st != RNSC_OK) { P.status[c] = st; plan_emit(P, c, CLS_DONE); return; }
     if (slow) { plan_emit(P, c, CLS_SLOW); return; }

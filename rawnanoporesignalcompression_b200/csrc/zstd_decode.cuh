@@ -156,60 +156,83 @@ __device__ inline uint32_t bwd_read(BwdBits& b, int n)
 // ---------------------------------------------------------------------------------------------------
 // Huffman: tree description (thread 0), table build (CTA), parallel stream decode (CTA)
 // ---------------------------------------------------------------------------------------------------
-// Reads the Huffman tree description into ws->weights; returns bytes consumed (0 = error) and *nw.
-template <typename WS>
+// Warp reconvergence point for code that runs one independent problem per LANE (the planner): `SYNC` instantiations
+// must be executed by all lanes of the warp the same number of times (single-exit, flag-driven control flow), so
+// that the long loops that follow run converged instead of once per diverged lane.
+template <bool SYNC> __device__ __forceinline__ void warp_converge() { if (SYNC) __syncwarp(); }
+
+// Reads the Huffman tree description into ws->weights; returns bytes consumed (0 = error or size == 0) and *nw.
+// Single exit; with SYNC every lane of the warp must call it (pass size = 0 to skip the work).
+template <typename WS, bool SYNC = false>
 __device__ inline uint32_t huf_read_weights(WS* ws, const uint8_t* src, uint32_t size, int* nw_out)
 {
     uint8_t* w = ws->weights; int nw = 0;
-    if (size < 1) return 0;
-    uint32_t hb = ldg8(src), used;
-    if (hb >= 128) {
-        nw = (int)hb - 127;
-        used = 1 + (uint32_t)((nw + 1) / 2);
-        if (used > size) return 0;
-        for (int i = 0; i < nw; ++i) { uint32_t by = ldg8(src + 1 + i / 2); w[i] = (uint8_t)((i & 1) ? (by & 15) : (by >> 4)); }
-    } else {
-        used = 1 + hb;
-        if (used > size || hb < 1) return 0;
-        int tl, ns;
-        uint32_t h = fse_read_ncount(src + 1, hb, ws->norm, 12, 6, &tl, &ns);
-        if (!h) return 0;
-        fse_build(ws->fse_w, ws->norm, ns, tl, ws->next16);
+    bool ok = size >= 1;
+    const uint32_t hb = ok ? ldg8(src) : 0;
+    const bool direct = hb >= 128;
+    uint32_t used = 0;
+    // ---- direct representation: one 4-bit weight per symbol ----
+    if (ok && direct) { nw = (int)hb - 127; used = 1 + (uint32_t)((nw + 1) / 2); if (used > size) ok = false; }
+    {
+        const int lim = (ok && direct) ? nw : 0;
+        for (int i = 0; i < lim; ++i) { const uint32_t by = ldg8(src + 1 + i / 2); w[i] = (uint8_t)((i & 1) ? (by & 15) : (by >> 4)); }
+    }
+    // ---- FSE-compressed weights ----
+    int tl = 0, ns = 0; uint32_t h = 0;
+    if (ok && !direct) { used = 1 + hb; if (used > size || hb < 1) ok = false; }
+    if (ok && !direct) { h = fse_read_ncount(src + 1, hb, ws->norm, 12, 6, &tl, &ns); if (!h) ok = false; }
+    warp_converge<SYNC>();
+    if (ok && !direct) fse_build(ws->fse_w, ws->norm, ns, tl, ws->next16);
+    warp_converge<SYNC>();
+    if (ok && !direct) {
         BwdBits b;
-        if (bwd_init(b, src + 1 + h, hb - h)) return 0;
-        uint32_t s1 = bwd_read(b, tl), s2 = bwd_read(b, tl);
-        for (;;) {
-            if (nw >= 254) return 0;
-            uint32_t e = ws->fse_w[s1]; w[nw++] = (uint8_t)(e & 0xFF);
-            s1 = (e >> 16) + bwd_read(b, (int)((e >> 8) & 0xFF));
-            if (b.overflow) { if (nw >= 255) return 0; w[nw++] = (uint8_t)(ws->fse_w[s2] & 0xFF); break; }
-            if (nw >= 254) return 0;
-            e = ws->fse_w[s2]; w[nw++] = (uint8_t)(e & 0xFF);
-            s2 = (e >> 16) + bwd_read(b, (int)((e >> 8) & 0xFF));
-            if (b.overflow) { if (nw >= 255) return 0; w[nw++] = (uint8_t)(ws->fse_w[s1] & 0xFF); break; }
+        if (bwd_init(b, src + 1 + h, hb - h)) ok = false;
+        else {
+            uint32_t s1 = bwd_read(b, tl), s2 = bwd_read(b, tl);
+            for (;;) {
+                if (nw >= 254) { ok = false; break; }
+                uint32_t e = ws->fse_w[s1]; w[nw++] = (uint8_t)(e & 0xFF);
+                s1 = (e >> 16) + bwd_read(b, (int)((e >> 8) & 0xFF));
+                if (b.overflow) { if (nw >= 255) ok = false; else w[nw++] = (uint8_t)(ws->fse_w[s2] & 0xFF); break; }
+                if (nw >= 254) { ok = false; break; }
+                e = ws->fse_w[s2]; w[nw++] = (uint8_t)(e & 0xFF);
+                s2 = (e >> 16) + bwd_read(b, (int)((e >> 8) & 0xFF));
+                if (b.overflow) { if (nw >= 255) ok = false; else w[nw++] = (uint8_t)(ws->fse_w[s1] & 0xFF); break; }
+            }
         }
     }
-    // one pass: validity, total weight and the per-weight symbol counts (kept in ws->rank_cnt: a local array with
-    // a data-dependent index would be expanded into a compare/select chain per symbol)
+    warp_converge<SYNC>();
+    // ---- one pass: validity, total weight and the per-weight symbol counts (kept in ws->rank_cnt: a local array
+    //      with a data-dependent index would be expanded into a compare/select chain per symbol) ----
     uint32_t* cnt = ws->rank_cnt;
-    for (int k = 0; k < 16; ++k) cnt[k] = 0;
     uint32_t total = 0;
-    for (int i = 0; i < nw; ++i) { const uint32_t wi = w[i]; if (wi > HUF_LOG_MAX) return 0; total += (1u << wi) >> 1; cnt[wi]++; }
-    if (total == 0) return 0;
-    int maxBits = highbit32(total) + 1;
-    if (maxBits > HUF_LOG_MAX) return 0;
-    uint32_t rest = (1u << maxBits) - total;
-    if (rest & (rest - 1)) return 0;
-    const uint32_t lastw = (uint32_t)highbit32(rest) + 1;
-    w[nw++] = (uint8_t)lastw; cnt[lastw]++;
-    for (int i = nw; i < 256; ++i) w[i] = 0;
-    // rank starts: weight ascending == code length descending (HUF_readDTableX1 layout)
-    if (cnt[1] < 2 || (cnt[1] & 1)) return 0;
-    uint32_t p = 0;
-    for (int k = 1; k <= maxBits; ++k) { ws->rank_start[k] = p; p += cnt[k] << (k - 1); }
-    ws->huf_log = maxBits;
-    *nw_out = nw;
-    return used;
+    if (ok) {
+        for (int k = 0; k < 16; ++k) cnt[k] = 0;
+        bool big = false;
+        for (int i = 0; i < nw; ++i) { uint32_t wi = w[i]; if (wi > HUF_LOG_MAX) { big = true; wi = 0; } total += (1u << wi) >> 1; cnt[wi]++; }
+        if (big || total == 0) ok = false;
+    }
+    int maxBits = 0;
+    if (ok) {
+        maxBits = highbit32(total) + 1;
+        const uint32_t rest = (1u << maxBits) - total;
+        if (maxBits > HUF_LOG_MAX || (rest & (rest - 1))) ok = false;
+        else {
+            const uint32_t lastw = (uint32_t)highbit32(rest) + 1;
+            w[nw++] = (uint8_t)lastw; cnt[lastw]++;
+            if (cnt[1] < 2 || (cnt[1] & 1)) ok = false;
+        }
+    }
+    warp_converge<SYNC>();
+    if (ok) {
+        for (int i = nw; i < 256; ++i) w[i] = 0;
+        // rank starts: weight ascending == code length descending (HUF_readDTableX1 layout)
+        uint32_t p = 0;
+        for (int k = 1; k <= maxBits; ++k) { ws->rank_start[k] = p; p += cnt[k] << (k - 1); }
+        ws->huf_log = maxBits;
+        *nw_out = nw;
+    }
+    return ok ? used : 0;
 }
 
 // CTA: fill ws->huf from ws->weights / ws->rank_start. Symbols of equal weight take consecutive runs of
