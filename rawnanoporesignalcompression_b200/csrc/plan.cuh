@@ -15,7 +15,7 @@
 
 namespace rnsc {
 
-constexpr int PLAN_MAX_SEQ = 128;     // sequences of all frames of a chunk kept inline in the plan
+constexpr int PLAN_MAX_SEQ = 256;     // sequences of all frames of a chunk kept inline in the plan
 constexpr int PLAN_MAX_HUF = 3;       // Huffman-coded literal sections per chunk described in the plan
 constexpr int PLAN_MAX_STREAMS = 4 * PLAN_MAX_HUF;
 constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
