@@ -141,7 +141,7 @@ struct rnsc_ctx {
     uint64_t launches = 0;
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
-    DevBuf d_plans, d_lists, d_deftab, d_prof;
+    DevBuf d_plans, d_lists, d_deftab, d_prof, d_seqpool;
     bool profiling = false;
     Lane lane[2];
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -170,7 +170,10 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     if (c->d_scratch.reserve(stride * (size_t)c->sm_count * 2)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(scratch %zu) failed", stride * (size_t)c->sm_count * 2);
     if (c->d_counter.reserve(256)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(counter) failed");
     if (c->d_plans.reserve(nchunks * sizeof(ChunkPlan)) || c->d_lists.reserve(4 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(plans) failed");
-    // counter words: [0..3] list lengths (class S, A, B, general), [8..11] the work cursors of the four kernels
+    // sequence pool: bump-allocated by the planner; ~1000 sequences per chunk on average covers VBZ (C5 needs ~15)
+    const size_t pool_cap = nchunks * 1024 + 4096;
+    if (c->d_seqpool.reserve(pool_cap * SEQ_WORDS * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(sequence pool) failed");
+    // counter words: [0..3] list lengths (class S, A, B, general), [4] sequence pool cursor, [8..11] the work cursors of the four kernels
     uint32_t* cnt = (uint32_t*)c->d_counter.p;
     CUDA_OK(cudaMemsetAsync(cnt, 0, 64, st));
     // 1. planner: one thread per chunk does every serial step (headers, Huffman tree descriptions, sequences)
@@ -179,13 +182,14 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
     for (int k = 0; k < 3; ++k) pp.region[k] = (uint32_t)(kFastSmem[k] - kFastWs[k]);
     pp.deftab = (const uint32_t*)c->d_deftab.p;
+    pp.seq_pool = (uint32_t*)c->d_seqpool.p; pp.pool_cap = (uint32_t)std::min<size_t>(pool_cap, 0xFFFFFFFFu); pp.pool_cursor = cnt + 4;
     RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
     // 2. fast kernel over the three size classes, 3. general decoder over what is left. Fork: class B (large chunks, one
     // CTA per SM) stays on the caller's stream and is enqueued first; the other classes and the general decoder go to side
     // streams and fill SMs as class B CTAs retire. Join before returning to the caller's stream.
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
-    fp.plans = (const ChunkPlan*)c->d_plans.p;
+    fp.plans = (const ChunkPlan*)c->d_plans.p; fp.seq_pool = (const uint32_t*)c->d_seqpool.p;
     auto set_class = [&](uint32_t cls) { fp.list = (const uint32_t*)c->d_lists.p + (size_t)cls * nchunks; fp.count = cnt + cls; fp.counter = cnt + 8 + cls;
                                          fp.prof = c->profiling ? (unsigned long long*)c->d_prof.p + 8 * cls : nullptr; };
     CUDA_OK(cudaEventRecord(c->ev_plan, st));
@@ -300,7 +304,7 @@ void rnsc_destroy(rnsc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof}) b->release();
+    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool}) b->release();
     c->h_a.release(); c->h_b.release();
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);

@@ -23,6 +23,7 @@ struct FastParams {
     const uint8_t* comp; const uint64_t* comp_off; const uint32_t* n; const uint64_t* sample_off;
     int16_t* samples; int32_t* status; int codec;
     const ChunkPlan* plans; const uint32_t* list; const uint32_t* count; uint32_t* counter;
+    const uint32_t* seq_pool;    // the planner's sequence pool (SEQ_WORDS words per entry)
     unsigned long long* prof;    // optional (rnsc_set_profiling): 8 phase cycle counters of this size class, summed over CTAs
 };
 
@@ -41,7 +42,9 @@ struct FastWs {
     Unpack2Ws<NTH> u2;
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
-    uint32_t seq[PLAN_MAX_SEQ * SEQ_WORDS];
+    uint32_t seq[PLAN_MAX_SEQ * SEQ_WORDS];    // copy of the chunk's sequences when there are at most PLAN_MAX_SEQ of them
+    const uint32_t* sq[5];                     // sequences of SeqOp i: in ws->seq or in the global pool
+    uint32_t nlong[2], longq[128];             // long matches of the current dependency level, copied warp-wide
     View view[5];
     int status; uint32_t next;
     alignas(8) unsigned long long mbar;
@@ -188,8 +191,8 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
         uint32_t li = sp.lit0 + off;                                                   // literal index of my first symbol
         // Literal runs: without sequences the whole frame is one run at shift 0; with sequences run i (the literals in
         // front of match i, then the tail) lands at its final position out_pos[i] = lit_pos[i] + sum of earlier matches.
-        const uint32_t* sq = ws->seq + SEQ_WORDS * sp.seq_base;
-        const uint32_t nseq = sp.nseq;
+        const uint32_t* sq = sp.sop < 5 ? ws->sq[sp.sop] : ws->seq;
+        const uint32_t nseq = sp.sop < 5 ? hd.sop[sp.sop].nseq : 0u;
         uint32_t seg = 0;
         if (nseq) {   // last run whose first literal index is <= li (runs may be empty)
             uint32_t lo_i = 0, hi_i = nseq;                                            // run nseq = tail, starts at lit_end
@@ -226,19 +229,18 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
     return r;
 }
 
-// Executes the LZ sequences of one frame: literal runs by all threads, matches in order by warp 0.
+// Executes the LZ sequences of one frame. Literal runs: Huffman literals were already written in place by
+// fast_huffman; raw / RLE literal runs are copied / filled by all threads. Matches: level by level of the planner's
+// dependency depth -- all matches of a level are independent of each other, one thread copies one match.
 template <int NTH>
-__device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, uint8_t* region)
+__device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, const uint32_t* sq, uint8_t* region)
 {
     const int tid = threadIdx.x;
-    const uint32_t* sq = ws->seq + SEQ_WORDS * op.seq_base;       // (ll, ml, offset, literal position, output position)
     uint8_t* dst = region + op.dst_off;
     const uint32_t nseq = op.nseq;
-    const uint32_t lit_end = sq[SEQ_WORDS * (nseq - 1) + 3] + sq[SEQ_WORDS * (nseq - 1)];                  // literals consumed by the sequences
-    const uint32_t out_end = sq[SEQ_WORDS * (nseq - 1) + 4] + sq[SEQ_WORDS * (nseq - 1)] + sq[SEQ_WORDS * (nseq - 1) + 1];
-    if (op.ltype == 2) {
-        // Huffman literals were written to their final places by fast_huffman (which ended with a barrier)
-    } else {
+    if (op.ltype != 2) {
+        const uint32_t lit_end = sq[SEQ_WORDS * (nseq - 1) + 3] + sq[SEQ_WORDS * (nseq - 1)];                  // literals consumed by the sequences
+        const uint32_t out_end = sq[SEQ_WORDS * (nseq - 1) + 4] + sq[SEQ_WORDS * (nseq - 1)] + sq[SEQ_WORDS * (nseq - 1) + 1];
         for (uint32_t i = 0; i <= nseq; ++i) {
             const uint32_t lp = i < nseq ? sq[SEQ_WORDS * i + 3] : lit_end, opos = i < nseq ? sq[SEQ_WORDS * i + 4] : out_end;
             const uint32_t len = i < nseq ? sq[SEQ_WORDS * i] : op.regen - lit_end;
@@ -248,15 +250,36 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, uin
         }
         __syncthreads();
     }
-    if (tid < 32) {
-        for (uint32_t i = 0; i < nseq; ++i) {
-            const uint32_t ml = sq[SEQ_WORDS * i + 1], of = sq[SEQ_WORDS * i + 2], o = sq[SEQ_WORDS * i + 4] + sq[SEQ_WORDS * i];
-            if (of >= 32) { for (uint32_t k0 = 0; k0 < ml; k0 += 32) { const uint32_t q = k0 + tid; if (q < ml) dst[o + q] = dst[o + q - of]; __syncwarp(); } }
-            else { const uint8_t* sp = dst + o - of; for (uint32_t q = tid; q < ml; q += 32) dst[o + q] = sp[q % of]; }
-            __syncwarp();
+    // short matches: one thread each; long ones are queued and copied by a whole warp each
+    constexpr uint32_t LONG = 24, QCAP = 128;
+    if (tid == 0) ws->nlong[0] = 0;
+    __syncthreads();
+    for (uint32_t lvl = 0; lvl <= op.max_depth; ++lvl) {
+        const uint32_t par = lvl & 1u;
+        if (tid == 0) ws->nlong[par ^ 1u] = 0;
+        for (uint32_t i = tid; i < nseq; i += NTH) {
+            if (sq[SEQ_WORDS * i + 5] != lvl) continue;
+            const uint32_t ml = sq[SEQ_WORDS * i + 1], of = sq[SEQ_WORDS * i + 2];
+            if (ml > LONG) { const uint32_t k = atomicAdd(&ws->nlong[par], 1u); if (k < QCAP) { ws->longq[k] = i; continue; } }
+            uint8_t* d = dst + sq[SEQ_WORDS * i + 4] + sq[SEQ_WORDS * i];
+            const uint8_t* s = d - of;
+            for (uint32_t q = 0; q < ml; ++q) d[q] = s[q];             // ascending byte order: correct for overlapping (offset < length) matches
+        }
+        __syncthreads();
+        const uint32_t nl = min(ws->nlong[par], QCAP);
+        if (nl) {
+            const uint32_t lane = tid & 31u;
+            for (uint32_t k = tid >> 5; k < nl; k += NTH / 32) {
+                const uint32_t i = ws->longq[k];
+                const uint32_t ml = sq[SEQ_WORDS * i + 1], of = sq[SEQ_WORDS * i + 2];
+                uint8_t* d = dst + sq[SEQ_WORDS * i + 4] + sq[SEQ_WORDS * i];
+                const uint8_t* sp = d - of;
+                if (of >= 32) { for (uint32_t k0 = 0; k0 < ml; k0 += 32) { const uint32_t q = k0 + lane; if (q < ml) d[q] = sp[q]; __syncwarp(); } }
+                else { for (uint32_t q = lane; q < ml; q += 32) d[q] = sp[q % of]; }
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
 }
 
 // Decodes chunk c into stream views (ws->view) and ws->status. Must be entered by the whole CTA after a barrier.
@@ -278,7 +301,17 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
         const uint32_t nhuf = pl->head.nhuf, nseq = pl->head.nseq;
         s = (const uint32_t*)pl->h; d = (uint32_t*)ws->h;
         for (uint32_t i = tid; i < (uint32_t)sizeof(HufPlan) / 4 * nhuf; i += NTH) d[i] = s[i];
-        for (uint32_t i = tid; i < SEQ_WORDS * nseq; i += NTH) ws->seq[i] = pl->seq[i];
+        // sequences: copied to shared memory when few (the usual case), read from the global pool otherwise
+        if (nseq <= PLAN_MAX_SEQ) {
+            uint32_t base = 0;
+            for (uint32_t k = 0; k < pl->head.nsop; ++k) {
+                const uint32_t cnt = pl->head.sop[k].nseq;
+                const uint32_t* g = P.seq_pool + (size_t)SEQ_WORDS * pl->head.sop[k].seq_base;
+                for (uint32_t i = tid; i < SEQ_WORDS * cnt; i += NTH) ws->seq[SEQ_WORDS * base + i] = g[i];
+                if (tid == 0) ws->sq[k] = ws->seq + SEQ_WORDS * base;
+                base += cnt;
+            }
+        } else if (tid < 5 && (uint32_t)tid < pl->head.nsop) ws->sq[tid] = P.seq_pool + (size_t)SEQ_WORDS * pl->head.sop[tid].seq_base;
     }
     __syncthreads();
     // prefetch the next chunk index while this one is decoded
@@ -296,7 +329,7 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     __syncthreads();
     pc.mark(PH_STAGE);
     if (hd.nst && fast_huffman<NTH>(ws, region, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
-    for (uint32_t i = 0; i < hd.nsop; ++i) fast_exec_sequences<NTH>(ws, hd.sop[i], region);
+    for (uint32_t i = 0; i < hd.nsop; ++i) fast_exec_sequences<NTH>(ws, hd.sop[i], ws->sq[i], region);
     if (tid < 5) { ws->view[tid].p = region + hd.view[tid].off; ws->view[tid].len = hd.view[tid].len; }
     if (tid == 0 && hd.view_status != RNSC_OK) ws->status = hd.view_status;
     __syncthreads();

@@ -15,7 +15,7 @@
 
 namespace rnsc {
 
-constexpr int PLAN_MAX_SEQ = 256;     // sequences of all frames of a chunk kept inline in the plan
+constexpr int PLAN_MAX_SEQ = 256;     // chunks with at most this many sequences get them copied to shared memory
 constexpr int PLAN_MAX_HUF = 3;       // Huffman-coded literal sections per chunk described in the plan
 constexpr int PLAN_MAX_STREAMS = 4 * PLAN_MAX_HUF;
 constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
@@ -35,7 +35,8 @@ struct FramePlan {               // planner-internal description of one frame
     uint32_t lit_off;            // raw literals: chunk offset; RLE literals: the byte value
     uint32_t lit_dst;            // unused
     uint32_t nstreams, huf;      // Huffman: 1 or 4 streams; index of the HufPlan
-    uint32_t nseq, seq_base;     // sequences [seq_base, seq_base + nseq) of ChunkPlan::seq
+    uint32_t nseq, seq_base;     // sequences [seq_base, seq_base + nseq) of the sequence pool
+    uint32_t max_depth, pad;     // longest chain of matches that read each other's output
     uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
 };
 struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decoding table
@@ -48,11 +49,12 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
 // One Huffman bitstream: payload bits, absolute bit address of the end mark in the region, symbols, region offset of
 // the frame's output, literal index of its first symbol, its table; and, when LZ sequences follow, where they are in
 // ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
-struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, seq_base, nseq, regen, pad0, pad1; };
+struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pad0, pad1, pad2; };   // sop: index of the frame's SeqOp or ~0
 struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
-struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base; };   // LZ sequences of a frame; lit = region offset of raw literals or the RLE byte
+struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base, max_depth, pad; };   // LZ sequences of a frame (entries [seq_base, +nseq) of the
+                                                                                   // sequence pool); lit = region offset of raw literals or the RLE byte
 struct ViewPlan { uint32_t off, len; };                                  // stream k of the splitter inverse = region[off .. off+len)
-constexpr int SEQ_WORDS = 5;     // (literal length, match length, offset, literal position, output position)
+constexpr int SEQ_WORDS = 6;     // (literal length, match length, offset, literal position, output position, dependency depth)
 
 struct PlanHead {                // what the fast kernel copies to shared memory for every chunk
     uint32_t cls, need, phase, stage_bytes;
@@ -67,7 +69,6 @@ struct PlanHead {                // what the fast kernel copies to shared memory
 struct ChunkPlan {
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
-    uint32_t seq[PLAN_MAX_SEQ * SEQ_WORDS];
     FramePlan f[5];                  // planner scratch
     uint32_t fse[512 + 256 + 512];   // planner scratch: FSE-compressed LL / OF / ML decoding tables of the frame being planned
 };
@@ -79,6 +80,7 @@ struct PlanParams {
     uint32_t* counts;            // [0..3] list lengths (atomic), zeroed before the launch
     uint32_t region[3];          // bytes of dynamic region available to a class S / A / B CTA
     const uint32_t* deftab;      // predefined FSE decoding tables: LL[64] OF[32] ML[64]
+    uint32_t* seq_pool; uint32_t pool_cap; uint32_t* pool_cursor;   // bump-allocated sequence storage (SEQ_WORDS words per entry)
 };
 
 // Per planner thread scratch in shared memory. 225 words: an odd stride, so the same field of the 32 threads
@@ -93,7 +95,7 @@ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 // Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
 // an FSE description). Returns 0 on success. Single exit (the planner runs one chunk per lane).
 __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, const uint32_t* tll, int ll_log, const uint32_t* tof, int of_log,
-                                     const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out)
+                                     const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out, uint32_t* max_depth)
 {
     BwdBits b;
     bool bad = bwd_init(b, bs, bs_size) != 0;
@@ -129,6 +131,19 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
         op += ll + ml; lp += ll;
     }
     if (!bad && (b.bitpos != 0 || op + (regen - lp) != fcs)) bad = true;
+    // Dependency depth of every match: 0 if its source lies in literals (or in itself), else 1 + the deepest earlier
+    // match whose output it reads. The kernel executes matches level by level, all matches of a level in parallel.
+    uint32_t maxd = 0;
+    for (uint32_t i = 0; i < nseq && !bad; ++i) {
+        const uint32_t ms = out[SEQ_WORDS * i + 4] + out[SEQ_WORDS * i], ml = out[SEQ_WORDS * i + 1], of = out[SEQ_WORDS * i + 2];
+        const uint32_t a = ms - of, e = min(ms, a + ml);                     // source bytes outside the match itself
+        uint32_t lo = 0, hi = i;                                             // first earlier match whose end is > a (ends increase with the index)
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const uint32_t me = out[SEQ_WORDS * mid + 4] + out[SEQ_WORDS * mid] + out[SEQ_WORDS * mid + 1]; if (me > a) hi = mid; else lo = mid + 1; }
+        uint32_t d = 0;
+        for (uint32_t k = lo; k < i && out[SEQ_WORDS * k + 4] + out[SEQ_WORDS * k] < e; ++k) if (out[SEQ_WORDS * k + 1]) d = max(d, out[SEQ_WORDS * k + 5] + 1);
+        out[SEQ_WORDS * i + 5] = d; maxd = max(maxd, d);
+    }
+    *max_depth = maxd;
     return bad ? 1 : 0;
 }
 
@@ -136,7 +151,7 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
 // `enable` false). Every lane of the warp calls it for every frame (enable = false when the lane has nothing to plan):
 // the body is single-exit so that the warp can reconverge in front of each long loop.
 __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t boff, uint32_t size, FramePlan& fp, ChunkPlan* pl, uint32_t& nhuf, uint32_t& nseq_tot,
-                                 PlanScratch* sc, const uint32_t* deftab)
+                                 PlanScratch* sc, const uint32_t* deftab, const PlanParams& P)
 {
     const uint8_t* src = chunk + boff;
     bool bad = !enable || size < 1;
@@ -175,7 +190,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     }
     if (!bad && nseq == 0 && regen != fp.fcs) bad = true;
     if (!bad) {
-        fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = nseq_tot;
+        fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = 0; fp.max_depth = 0; fp.pad = 0;
         fp.lit_off = ltype == 0 ? boff + lhs : (ltype == 1 ? ldg8(src + lhs) : 0);
     }
     // ---- Huffman tree description + stream geometry (every lane walks through huf_read_weights) ----
@@ -230,7 +245,9 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     warp_converge<true>();
     // ---- sequences: predefined, RLE or FSE-described tables (repeat mode is invalid in a first block) ----
     if (!bad && nseq) {
-        if (nseq_tot + nseq > PLAN_MAX_SEQ) bad = true;
+        const uint32_t base = atomicAdd(P.pool_cursor, nseq);                // bump allocation in the sequence pool
+        if (base + nseq > P.pool_cap) bad = true;
+        fp.seq_base = base;
         uint32_t rle[3] = {0, 0, 0};
         const uint32_t* tab[3] = {deftab, deftab, deftab}; int tlog[3] = {0, 0, 0};
         uint32_t p = so;
@@ -253,7 +270,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
             } else { bad = true; break; }
         }
         if (!bad && p >= size) bad = true;
-        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, pl->seq + SEQ_WORDS * nseq_tot)) bad = true;
+        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, P.seq_pool + (size_t)SEQ_WORDS * base, &fp.max_depth)) bad = true;
         if (!bad) nseq_tot += nseq;
     }
     return bad ? 1 : 0;
@@ -302,7 +319,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         const bool live = st == RNSC_OK && !slow;
         FramePlan fp;
         fp.kind = FK_RAW; fp.fcs = (uint32_t)fcs; fp.data_off = 0; fp.dst_off = 0; fp.ltype = 0; fp.regen = 0; fp.lit_off = 0; fp.lit_dst = 0;
-        fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0;
+        fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0; fp.max_depth = 0; fp.pad = 0;
         for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; }
         bool comp_block = false; uint32_t bsz = 0;
         if (live) {
@@ -319,7 +336,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
             }
         }
         comp_block = comp_block && !slow;
-        const int pb = plan_block(comp_block, src, pos + hdr + 3, bsz, fp, pl, nhuf, nseq_tot, sc, deftab);
+        const int pb = plan_block(comp_block, src, pos + hdr + 3, bsz, fp, pl, nhuf, nseq_tot, sc, deftab, P);
         if (comp_block && pb) slow = true;
         if (st == RNSC_OK && !slow) {
             // placement of the decoded output in the CTA's dynamic region (raw data is used in place; the literals of a
@@ -350,6 +367,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         else data = fp.dst_off;
         if (fp.kind == FK_RLE) hd->fill[nfill++] = FillOp{fp.dst_off, fp.fcs, fp.data_off};
         else if (fp.kind == FK_COMP && fp.nseq == 0 && fp.ltype == 1) hd->fill[nfill++] = FillOp{fp.dst_off, fp.fcs, fp.lit_off};
+        const uint32_t my_sop = (fp.kind == FK_COMP && fp.nseq) ? nsop : 0xFFFFFFFFu;
         if (fp.kind == FK_COMP && fp.ltype == 2) {
             const uint32_t q = (fp.regen + 3) / 4;
             for (uint32_t j = 0; j < fp.nstreams; ++j) {
@@ -358,12 +376,12 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 sp.count = fp.nstreams == 1 ? fp.regen : (j < 3 ? q : fp.regen - 3 * q);
                 sp.out = fp.dst_off; sp.lit0 = fp.nstreams == 1 ? 0 : j * q;
                 sp.tab_off = pl->h[fp.huf].tab_off; sp.log = pl->h[fp.huf].log;
-                sp.seq_base = fp.seq_base; sp.nseq = fp.nseq; sp.regen = fp.regen; sp.pad0 = sp.pad1 = 0;
+                sp.sop = my_sop; sp.regen = fp.regen; sp.pad0 = sp.pad1 = sp.pad2 = 0;
                 if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }
         }
-        if (fp.kind == FK_COMP && fp.nseq) hd->sop[nsop++] = SeqOp{fp.dst_off, fp.ltype, fp.ltype == 0 ? cbase + fp.lit_off : fp.lit_off, fp.regen, fp.nseq, fp.seq_base};
+        if (fp.kind == FK_COMP && fp.nseq) hd->sop[nsop++] = SeqOp{fp.dst_off, fp.ltype, fp.ltype == 0 ? cbase + fp.lit_off : fp.lit_off, fp.regen, fp.nseq, fp.seq_base, fp.max_depth, 0};
         // A.8: stream views = slices of the decompressed buffer(s)
         if (nf == 1) {
             if (fp.fcs < kl) vst = RNSC_ERR_REMAINING;
