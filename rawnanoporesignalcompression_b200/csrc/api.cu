@@ -141,7 +141,7 @@ struct rnsc_ctx {
     uint64_t launches = 0;
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
-    DevBuf d_plans, d_lists, d_deftab, d_prof, d_seqpool;
+    DevBuf d_plans, d_lists, d_deftab, d_prof, d_seqpool, d_origin;
     bool profiling = false;
     Lane lane[2];
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -190,7 +190,12 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
     fp.plans = (const ChunkPlan*)c->d_plans.p; fp.seq_pool = (const uint32_t*)c->d_seqpool.p;
+    // match resolver scratch: one origin word per matched byte, a matched byte count is below the class's region size
+    size_t origin_words[3], origin_base[3], origin_total = 0;
+    for (int k = 0; k < 3; ++k) { origin_words[k] = kFastSmem[k]; origin_base[k] = origin_total; origin_total += origin_words[k] * (size_t)c->sm_count * (4 >> k); }
+    if (c->d_origin.reserve(origin_total * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(origin scratch) failed");
     auto set_class = [&](uint32_t cls) { fp.list = (const uint32_t*)c->d_lists.p + (size_t)cls * nchunks; fp.count = cnt + cls; fp.counter = cnt + 8 + cls;
+                                         fp.origin = (uint32_t*)c->d_origin.p + origin_base[cls]; fp.origin_stride = origin_words[cls];
                                          fp.prof = c->profiling ? (unsigned long long*)c->d_prof.p + 8 * cls : nullptr; };
     CUDA_OK(cudaEventRecord(c->ev_plan, st));
     for (int k = 0; k < 3; ++k) CUDA_OK(cudaStreamWaitEvent(c->side[k], c->ev_plan, 0));
@@ -304,7 +309,7 @@ void rnsc_destroy(rnsc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool}) b->release();
+    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin}) b->release();
     c->h_a.release(); c->h_b.release();
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);

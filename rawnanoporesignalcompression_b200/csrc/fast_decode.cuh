@@ -24,6 +24,7 @@ struct FastParams {
     int16_t* samples; int32_t* status; int codec;
     const ChunkPlan* plans; const uint32_t* list; const uint32_t* count; uint32_t* counter;
     const uint32_t* seq_pool;    // the planner's sequence pool (SEQ_WORDS words per entry)
+    uint32_t* origin; unsigned long long origin_stride;   // per-CTA global scratch (words) of the match resolver
     unsigned long long* prof;    // optional (rnsc_set_profiling): 8 phase cycle counters of this size class, summed over CTAs
 };
 
@@ -42,9 +43,7 @@ struct FastWs {
     Unpack2Ws<NTH> u2;
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
-    uint32_t seq[PLAN_MAX_SEQ * SEQ_WORDS];    // copy of the chunk's sequences when there are at most PLAN_MAX_SEQ of them
-    const uint32_t* sq[5];                     // sequences of SeqOp i: in ws->seq or in the global pool
-    uint32_t nlong[2], longq[128];             // long matches of the current dependency level, copied warp-wide
+    uint32_t nlong, longq[128], long_ms[128], long_ml[128], long_of[128], long_mb[128];   // long matches of the frame being resolved (a warp each)
     View view[5];
     int status; uint32_t next;
     alignas(8) unsigned long long mbar;
@@ -190,38 +189,45 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
         uint32_t p = my_start, rem = min(my_cnt, sp.count - off), hi, lo, nb, e;      // clamped: a corrupt stream cannot write outside its output
         uint32_t li = sp.lit0 + off;                                                   // literal index of my first symbol
         // Literal runs: without sequences the whole frame is one run at shift 0; with sequences run i (the literals in
-        // front of match i, then the tail) lands at its final position out_pos[i] = lit_pos[i] + sum of earlier matches.
-        const uint32_t* sq = sp.sop < 5 ? ws->sq[sp.sop] : ws->seq;
-        const uint32_t nseq = sp.sop < 5 ? hd.sop[sp.sop].nseq : 0u;
-        uint32_t seg = 0;
-        if (nseq) {   // last run whose first literal index is <= li (runs may be empty)
-            uint32_t lo_i = 0, hi_i = nseq;                                            // run nseq = tail, starts at lit_end
-            const uint32_t lit_end = sq[SEQ_WORDS * (nseq - 1) + 3] + sq[SEQ_WORDS * (nseq - 1)];
-            if (li >= lit_end) seg = nseq;
-            else { while (lo_i + 1 < hi_i) { const uint32_t mid = (lo_i + hi_i) >> 1; if (sq[SEQ_WORDS * mid + 3] <= li) lo_i = mid; else hi_i = mid; } seg = lo_i; }
+        // front of match i; run nseq = the tail) starts at literal index run[i].x and lands run[i].y bytes further
+        // (the match bytes in front of it). The run table was built in the region at chunk start.
+        const uint32_t nruns = sp.sop < 5 ? hd.sop[sp.sop].nruns : 0u;
+        const uint2* run = (const uint2*)(region + (sp.sop < 5 ? hd.sop[sp.sop].meta_off : 0u));
+        uint32_t seg = 0, run_end = sp.regen, shift = 0;
+        if (nruns) {   // the run that holds literal li: the last one whose first literal index is <= li
+            uint32_t lo_i = 0, hi_i = nruns;
+            while (lo_i + 1 < hi_i) { const uint32_t mid = (lo_i + hi_i) >> 1; if (run[mid].x <= li) lo_i = mid; else hi_i = mid; }
+            seg = lo_i; shift = run[seg].y;
+            if (seg + 1 < nruns) run_end = run[seg + 1].x;
         }
-        while (rem) {
-            uint32_t take = rem, shift = 0;
-            if (nseq) {
-                const uint32_t last = nseq - 1;
-                const uint32_t lit_end = sq[SEQ_WORDS * last + 3] + sq[SEQ_WORDS * last], out_end = sq[SEQ_WORDS * last + 4] + sq[SEQ_WORDS * last] + sq[SEQ_WORDS * last + 1];
-                const uint32_t run_lit = seg < nseq ? sq[SEQ_WORDS * seg + 3] : lit_end, run_out = seg < nseq ? sq[SEQ_WORDS * seg + 4] : out_end;
-                const uint32_t run_end = seg < nseq ? run_lit + sq[SEQ_WORDS * seg] : sp.regen;
-                shift = run_out - run_lit;
-                take = min(rem, run_end > li ? run_end - li : 0u);
-                if (++seg > nseq + 1) break;                                        // cannot happen for a consistent plan
-            }
+        if (li + rem <= run_end) {      // all my literals belong to one run (always, without sequences)
             uint8_t* o = region + sp.out + li + shift;
-            li += take; rem -= take;
-            while (((uintptr_t)o & 3u) && take) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --take; }
-            while (take >= 4) {
+            while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --rem; }
+            while (rem >= 4) {
                 bits_ending_at(words, abit - p, hi, lo);
                 uint32_t word = 0, adv = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { RNSC_HUF_STEP(hi, lo, tab, L, nb, e); adv += nb; word |= (e & 0xFFu) << (8 * q); }
-                *(uint32_t*)o = word; o += 4; p += adv; take -= 4;
+                *(uint32_t*)o = word; o += 4; p += adv; rem -= 4;
             }
-            while (take) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --take; }
+            while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --rem; }
+        } else {
+            // runs can be a few literals long (the key region of a VBZ frame): one symbol at a time from a buffered
+            // 64-bit window, switching the output position whenever a run ends (the next run is fetched ahead)
+            uint8_t* o = region + sp.out + li + shift;
+            uint2 nxt = seg + 1 < nruns ? run[seg + 1] : make_uint2(sp.regen, 0u);
+            int avail = 0;
+            while (rem) {
+                if (avail < (int)HUF_LOG_MAX) { bits_ending_at(words, abit - p, hi, lo); avail = 64; }
+                RNSC_HUF_STEP(hi, lo, tab, L, nb, e);
+                p += nb; avail -= (int)nb;
+                *o++ = (uint8_t)e; ++li; --rem;
+                if (li == run_end) {
+                    ++seg; o = region + sp.out + li + nxt.y;
+                    nxt = seg + 1 < nruns ? run[seg + 1] : make_uint2(sp.regen, 0u);
+                    run_end = nxt.x;
+                }
+            }
         }
     }
     const int r = __syncthreads_or(bad);
@@ -229,57 +235,109 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
     return r;
 }
 
-// Executes the LZ sequences of one frame. Literal runs: Huffman literals were already written in place by
-// fast_huffman; raw / RLE literal runs are copied / filled by all threads. Matches: level by level of the planner's
-// dependency depth -- all matches of a level are independent of each other, one thread copies one match.
+// Executes the LZ sequences of one frame.
+// Literal runs: Huffman literals were already written in place by fast_huffman; raw / RLE literal runs are copied /
+// filled here. Matches: resolved byte-parallel by POINTER JUMPING instead of in sequence order. Every matched byte gets
+// an origin word (global scratch): the output position of a literal, or the index of the matched byte it copies
+// (classified through the run table: a position is either inside a literal run or in the matched span behind it).
+// Chains (a match copying an earlier match, overlapping run-length matches) halve every round; then every matched
+// byte is read from its literal. One thread per short match, a whole warp per long one.
 template <int NTH>
-__device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, const uint32_t* sq, uint8_t* region)
+__device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, const uint32_t* sq, uint8_t* region, uint32_t* origin)
 {
     const int tid = threadIdx.x;
     uint8_t* dst = region + op.dst_off;
-    const uint32_t nseq = op.nseq;
+    const uint32_t nseq = op.nseq, nruns = op.nruns, regen = op.regen;
+    const uint2* run = (const uint2*)(region + op.meta_off);
     if (op.ltype != 2) {
-        const uint32_t lit_end = sq[SEQ_WORDS * (nseq - 1) + 3] + sq[SEQ_WORDS * (nseq - 1)];                  // literals consumed by the sequences
-        const uint32_t out_end = sq[SEQ_WORDS * (nseq - 1) + 4] + sq[SEQ_WORDS * (nseq - 1)] + sq[SEQ_WORDS * (nseq - 1) + 1];
-        for (uint32_t i = 0; i <= nseq; ++i) {
-            const uint32_t lp = i < nseq ? sq[SEQ_WORDS * i + 3] : lit_end, opos = i < nseq ? sq[SEQ_WORDS * i + 4] : out_end;
-            const uint32_t len = i < nseq ? sq[SEQ_WORDS * i] : op.regen - lit_end;
-            uint8_t* d = dst + opos;
+        for (uint32_t i = 0; i < nruns; ++i) {
+            const uint32_t lp = run[i].x, len = (i + 1 < nruns ? run[i + 1].x : regen) - lp;
+            uint8_t* d = dst + lp + run[i].y;
             if (op.ltype == 1) for (uint32_t q = tid; q < len; q += NTH) d[q] = (uint8_t)op.lit;
             else { const uint8_t* s = region + op.lit + lp; for (uint32_t q = tid; q < len; q += NTH) d[q] = s[q]; }
         }
-        __syncthreads();
     }
-    // short matches: one thread each; long ones are queued and copied by a whole warp each
-    constexpr uint32_t LONG = 24, QCAP = 128;
-    if (tid == 0) ws->nlong[0] = 0;
-    __syncthreads();
-    for (uint32_t lvl = 0; lvl <= op.max_depth; ++lvl) {
-        const uint32_t par = lvl & 1u;
-        if (tid == 0) ws->nlong[par ^ 1u] = 0;
-        for (uint32_t i = tid; i < nseq; i += NTH) {
-            if (sq[SEQ_WORDS * i + 5] != lvl) continue;
-            const uint32_t ml = sq[SEQ_WORDS * i + 1], of = sq[SEQ_WORDS * i + 2];
-            if (ml > LONG) { const uint32_t k = atomicAdd(&ws->nlong[par], 1u); if (k < QCAP) { ws->longq[k] = i; continue; } }
-            uint8_t* d = dst + sq[SEQ_WORDS * i + 4] + sq[SEQ_WORDS * i];
-            const uint8_t* s = d - of;
-            for (uint32_t q = 0; q < ml; ++q) d[q] = s[q];             // ascending byte order: correct for overlapping (offset < length) matches
-        }
-        __syncthreads();
-        const uint32_t nl = min(ws->nlong[par], QCAP);
-        if (nl) {
-            const uint32_t lane = tid & 31u;
-            for (uint32_t k = tid >> 5; k < nl; k += NTH / 32) {
-                const uint32_t i = ws->longq[k];
-                const uint32_t ml = sq[SEQ_WORDS * i + 1], of = sq[SEQ_WORDS * i + 2];
-                uint8_t* d = dst + sq[SEQ_WORDS * i + 4] + sq[SEQ_WORDS * i];
-                const uint8_t* sp = d - of;
-                if (of >= 32) { for (uint32_t k0 = 0; k0 < ml; k0 += 32) { const uint32_t q = k0 + lane; if (q < ml) d[q] = sp[q]; __syncwarp(); } }
-                else { for (uint32_t q = lane; q < ml; q += 32) d[q] = sp[q % of]; }
+    // Origin words of bytes [q0, q1) of one match. Bytes of the first period (q < offset) read output positions
+    // ms - of + q: located once in the run table (binary search), then walked -- a position is inside a run's literals
+    // or in the matched span behind them. Later bytes of an overlapping match repeat the first period: they point at
+    // their own match (one extra jump round instead of a chain as long as the match).
+    auto emit = [&](uint32_t ms, uint32_t ml, uint32_t of, uint32_t mb, uint32_t q0, uint32_t q1) {
+        const uint32_t qe = min(q1, min(of, ml));
+        if (q0 < qe) {
+            uint32_t x = ms - of + q0;
+            int k = -1;                               // last run whose first output position is <= x (-1: none)
+            if (nruns && x >= run[0].x + run[0].y) {
+                uint32_t lo = 0, hi = nruns;
+                while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; const uint2 r = run[mid]; if (r.x + r.y <= x) lo = mid; else hi = mid; }
+                k = (int)lo;
             }
-            __syncthreads();
+            uint32_t next_lit = k + 1 < (int)nruns ? run[k + 1].x : regen;          // first literal index of the next run
+            uint32_t lit_end = k >= 0 ? next_lit + run[k].y : 0u;                    // end of run k's literals in the output
+            uint32_t next_start = k + 1 < (int)nruns ? next_lit + run[k + 1].y : 0xFFFFFFFFu;   // first output position of the next run
+            for (uint32_t q = q0; q < qe; ++q, ++x) {
+                while (x >= next_start) {
+                    ++k;
+                    next_lit = k + 1 < (int)nruns ? run[k + 1].x : regen;
+                    lit_end = next_lit + run[k].y;
+                    next_start = k + 1 < (int)nruns ? next_lit + run[k + 1].y : 0xFFFFFFFFu;
+                }
+                origin[mb + q] = x < lit_end ? (ORIGIN_LIT | x) : x - next_lit;
+            }
         }
+        uint32_t q = max(q0, of);
+        for (uint32_t r = q % of; q < q1; ++q) { origin[mb + q] = mb + r; if (++r == of) r = 0; }
+    };
+    constexpr uint32_t LONG = 48, QCAP = 128;
+    if (tid == 0) ws->nlong = 0;
+    // my (up to two) sequences, fetched once from the global pool
+    uint32_t m_ms[2] = {0, 0}, m_ml[2] = {0, 0}, m_of[2] = {1, 1}, m_mb[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t i = tid + k * NTH;
+        if (i < nseq) { const uint32_t* e = sq + (size_t)SEQ_WORDS * i; m_ms[k] = e[4] + e[0]; m_ml[k] = e[1]; m_of[k] = e[2]; m_mb[k] = e[5]; }
     }
+    __syncthreads();
+    // ---- round 0: origin of every matched byte ----
+    for (uint32_t i = tid, k = 0; i < nseq; i += NTH, ++k) {
+        uint32_t ms, ml, of, mb;
+        if (k < 2) { ms = m_ms[k & 1]; ml = m_ml[k & 1]; of = m_of[k & 1]; mb = m_mb[k & 1]; }
+        else { const uint32_t* e = sq + (size_t)SEQ_WORDS * i; ms = e[4] + e[0]; ml = e[1]; of = e[2]; mb = e[5]; }
+        if (ml > LONG) {
+            const uint32_t q = atomicAdd(&ws->nlong, 1u);
+            if (q < QCAP) { ws->longq[q] = i; ws->long_ms[q] = ms; ws->long_ml[q] = ml; ws->long_of[q] = of; ws->long_mb[q] = mb; continue; }
+        }
+        emit(ms, ml, of, mb, 0, ml);
+    }
+    __syncthreads();
+    const uint32_t nl = min(ws->nlong, QCAP), lane = tid & 31u;
+    for (uint32_t k = tid >> 5; k < nl; k += NTH / 32) {
+        const uint32_t ms = ws->long_ms[k], ml = ws->long_ml[k], of = ws->long_of[k], mb = ws->long_mb[k];
+        const uint32_t c = (ml + 31) / 32;                                  // a contiguous piece per lane
+        emit(ms, ml, of, mb, min(ml, lane * c), min(ml, (lane + 1) * c));
+    }
+    __syncthreads();
+    // ---- pointer jumping ----
+    for (int round = 0; round < 32; ++round) {
+        bool open = false;
+        for (uint32_t b = tid; b < op.mbytes; b += NTH) {
+            const uint32_t o = origin[b];
+            if (!(o & ORIGIN_LIT)) { const uint32_t o2 = origin[o]; origin[b] = o2; open |= !(o2 & ORIGIN_LIT); }
+        }
+        if (!__syncthreads_or(open)) break;
+    }
+    // ---- every matched byte from its literal ----
+    for (uint32_t i = tid, k = 0; i < nseq; i += NTH, ++k) {
+        uint32_t ms, ml, mb;
+        if (k < 2) { ms = m_ms[k & 1]; ml = m_ml[k & 1]; mb = m_mb[k & 1]; }
+        else { const uint32_t* e = sq + (size_t)SEQ_WORDS * i; ms = e[4] + e[0]; ml = e[1]; mb = e[5]; }
+        if (ml > LONG) { bool queued = false; for (uint32_t q = 0; q < nl; ++q) queued |= ws->longq[q] == i; if (queued) continue; }
+        for (uint32_t q = 0; q < ml; ++q) dst[ms + q] = dst[origin[mb + q] & ~ORIGIN_LIT];
+    }
+    for (uint32_t k = tid >> 5; k < nl; k += NTH / 32) {
+        const uint32_t ms = ws->long_ms[k], ml = ws->long_ml[k], mb = ws->long_mb[k];
+        for (uint32_t q = lane; q < ml; q += 32) dst[ms + q] = dst[origin[mb + q] & ~ORIGIN_LIT];
+    }
+    __syncthreads();
 }
 
 // Decodes chunk c into stream views (ws->view) and ws->status. Must be entered by the whole CTA after a barrier.
@@ -298,20 +356,16 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     {
         const uint32_t* s = (const uint32_t*)&pl->head; uint32_t* d = (uint32_t*)&ws->head;
         for (uint32_t i = tid; i < sizeof(PlanHead) / 4; i += NTH) d[i] = s[i];
-        const uint32_t nhuf = pl->head.nhuf, nseq = pl->head.nseq;
+        const uint32_t nhuf = pl->head.nhuf;
         s = (const uint32_t*)pl->h; d = (uint32_t*)ws->h;
         for (uint32_t i = tid; i < (uint32_t)sizeof(HufPlan) / 4 * nhuf; i += NTH) d[i] = s[i];
-        // sequences: copied to shared memory when few (the usual case), read from the global pool otherwise
-        if (nseq <= PLAN_MAX_SEQ) {
-            uint32_t base = 0;
-            for (uint32_t k = 0; k < pl->head.nsop; ++k) {
-                const uint32_t cnt = pl->head.sop[k].nseq;
-                const uint32_t* g = P.seq_pool + (size_t)SEQ_WORDS * pl->head.sop[k].seq_base;
-                for (uint32_t i = tid; i < SEQ_WORDS * cnt; i += NTH) ws->seq[SEQ_WORDS * base + i] = g[i];
-                if (tid == 0) ws->sq[k] = ws->seq + SEQ_WORDS * base;
-                base += cnt;
-            }
-        } else if (tid < 5 && (uint32_t)tid < pl->head.nsop) ws->sq[tid] = P.seq_pool + (size_t)SEQ_WORDS * pl->head.sop[tid].seq_base;
+        // run tables of the frames with sequences: {first literal index, shift} of every non-empty literal run
+        for (uint32_t k = 0; k < pl->head.nsop; ++k) {
+            const SeqOp op = pl->head.sop[k];
+            const uint32_t* g = P.seq_pool + (size_t)SEQ_WORDS * op.seq_base;
+            uint2* run = (uint2*)(region + op.meta_off);
+            for (uint32_t i = tid; i < op.nruns; i += NTH) run[i] = make_uint2(g[SEQ_WORDS * i + 6], g[SEQ_WORDS * i + 7]);
+        }
     }
     __syncthreads();
     // prefetch the next chunk index while this one is decoded
@@ -329,7 +383,9 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     __syncthreads();
     pc.mark(PH_STAGE);
     if (hd.nst && fast_huffman<NTH>(ws, region, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
-    for (uint32_t i = 0; i < hd.nsop; ++i) fast_exec_sequences<NTH>(ws, hd.sop[i], ws->sq[i], region);
+    for (uint32_t i = 0; i < hd.nsop; ++i) fast_exec_sequences<NTH>(ws, hd.sop[i], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[i].seq_base, region,
+                                                                   // origin words: in the dead bitstream area of the staged chunk when they fit, else global scratch
+                                                                   (size_t)hd.sop[i].mbytes * 4 <= hd.zone_len ? (uint32_t*)(region + hd.zone_off) : P.origin + (size_t)blockIdx.x * P.origin_stride);
     if (tid < 5) { ws->view[tid].p = region + hd.view[tid].off; ws->view[tid].len = hd.view[tid].len; }
     if (tid == 0 && hd.view_status != RNSC_OK) ws->status = hd.view_status;
     __syncthreads();

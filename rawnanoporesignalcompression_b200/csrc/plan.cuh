@@ -36,7 +36,8 @@ struct FramePlan {               // planner-internal description of one frame
     uint32_t lit_dst;            // unused
     uint32_t nstreams, huf;      // Huffman: 1 or 4 streams; index of the HufPlan
     uint32_t nseq, seq_base;     // sequences [seq_base, seq_base + nseq) of the sequence pool
-    uint32_t max_depth, pad;     // longest chain of matches that read each other's output
+    uint32_t max_depth, pad;     // max_depth: unused; pad = number of non-empty literal runs
+    uint32_t hz_off, hz_len;     // chunk offset / size of the Huffman bitstream area (dead once the literals are decoded)
     uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
 };
 struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decoding table
@@ -51,15 +52,21 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
 // ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
 struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pad0, pad1, pad2; };   // sop: index of the frame's SeqOp or ~0
 struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
-struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base, max_depth, pad; };   // LZ sequences of a frame (entries [seq_base, +nseq) of the
-                                                                                   // sequence pool); lit = region offset of raw literals or the RLE byte
+struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base, nruns, meta_off, mbytes, pad; };   // mbytes = matched bytes = fcs - regen   // LZ sequences of a frame (entries [seq_base, +nseq) of the
+                                                                                   // sequence pool); lit = region offset of raw literals or the RLE byte; meta_off = region offset of the run table
+                                                                                   // the kernel copies there: nruns x {first literal index, shift to the final position} (non-empty literal runs only)
 struct ViewPlan { uint32_t off, len; };                                  // stream k of the splitter inverse = region[off .. off+len)
-constexpr int SEQ_WORDS = 6;     // (literal length, match length, offset, literal position, output position, dependency depth)
+// Sequence pool entry i of a frame: words 0-5 describe sequence i (literal length, match length, offset, literal position,
+// output position, matched bytes in front of it); words 6-7 of entry k = the k-th NON-EMPTY literal run (first literal
+// index, shift to its final position = matched bytes in front of it; the tail after the last match included).
+constexpr int SEQ_WORDS = 8;
+constexpr uint32_t ORIGIN_LIT = 0x80000000u;   // origin word of a matched byte: literal flag | output position, or the index of another matched byte
 
 struct PlanHead {                // what the fast kernel copies to shared memory for every chunk
     uint32_t cls, need, phase, stage_bytes;
     uint32_t nhuf, nst, sub, nfill, nsop, nseq;
     int32_t view_status; uint32_t pad;
+    uint32_t zone_off, zone_len;   // region bytes that are dead after the Huffman stage (the largest bitstream area): match resolver scratch
     uint32_t st_first[PLAN_MAX_STREAMS + 1];
     StreamPlan st[PLAN_MAX_STREAMS];
     FillOp fill[5];
@@ -90,18 +97,19 @@ struct PlanScratch {
 };
 static_assert(sizeof(PlanScratch) == 900, "PlanScratch layout");
 
-__device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+__host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+__host__ __device__ inline uint32_t seq_meta_bytes(uint32_t nseq) { return align16((nseq + 1) * 8); }
 
 // Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
 // an FSE description). Returns 0 on success. Single exit (the planner runs one chunk per lane).
 __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, const uint32_t* tll, int ll_log, const uint32_t* tof, int of_log,
-                                     const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out, uint32_t* max_depth)
+                                     const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out, uint32_t* nruns)
 {
     BwdBits b;
     bool bad = bwd_init(b, bs, bs_size) != 0;
     uint32_t sl = 0, so = 0, sm = 0;
     if (!bad) { sl = bwd_read(b, ll_log); so = bwd_read(b, of_log); sm = bwd_read(b, ml_log); }
-    uint32_t rep0 = 1, rep1 = 4, rep2 = 8, op = 0, lp = 0;
+    uint32_t rep0 = 1, rep1 = 4, rep2 = 8, op = 0, lp = 0, nr = 0;
     for (uint32_t i = 0; i < nseq && !bad; ++i) {
         const uint32_t el = tll[sl], eo = tof[so], em = tml[sm];
         const uint32_t llc = el & 0xFF, ofc = eo & 0xFF, mlc = em & 0xFF;
@@ -127,23 +135,15 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
             so = (eo >> 16) + bwd_read(b, (int)((eo >> 8) & 0xFF));
         }
         if (b.overflow || lp + ll > regen || op + ll + ml > fcs || offset > op + ll) { bad = true; break; }
-        out[SEQ_WORDS * i] = ll; out[SEQ_WORDS * i + 1] = ml; out[SEQ_WORDS * i + 2] = offset; out[SEQ_WORDS * i + 3] = lp; out[SEQ_WORDS * i + 4] = op;
+        out[SEQ_WORDS * i] = ll; out[SEQ_WORDS * i + 1] = ml; out[SEQ_WORDS * i + 2] = offset; out[SEQ_WORDS * i + 3] = lp; out[SEQ_WORDS * i + 4] = op; out[SEQ_WORDS * i + 5] = op - lp;
+        if (ll) { out[SEQ_WORDS * nr + 6] = lp; out[SEQ_WORDS * nr + 7] = op - lp; ++nr; }      // compact list of the non-empty literal runs (nr <= i)
         op += ll + ml; lp += ll;
     }
     if (!bad && (b.bitpos != 0 || op + (regen - lp) != fcs)) bad = true;
-    // Dependency depth of every match: 0 if its source lies in literals (or in itself), else 1 + the deepest earlier
-    // match whose output it reads. The kernel executes matches level by level, all matches of a level in parallel.
-    uint32_t maxd = 0;
-    for (uint32_t i = 0; i < nseq && !bad; ++i) {
-        const uint32_t ms = out[SEQ_WORDS * i + 4] + out[SEQ_WORDS * i], ml = out[SEQ_WORDS * i + 1], of = out[SEQ_WORDS * i + 2];
-        const uint32_t a = ms - of, e = min(ms, a + ml);                     // source bytes outside the match itself
-        uint32_t lo = 0, hi = i;                                             // first earlier match whose end is > a (ends increase with the index)
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const uint32_t me = out[SEQ_WORDS * mid + 4] + out[SEQ_WORDS * mid] + out[SEQ_WORDS * mid + 1]; if (me > a) hi = mid; else lo = mid + 1; }
-        uint32_t d = 0;
-        for (uint32_t k = lo; k < i && out[SEQ_WORDS * k + 4] + out[SEQ_WORDS * k] < e; ++k) if (out[SEQ_WORDS * k + 1]) d = max(d, out[SEQ_WORDS * k + 5] + 1);
-        out[SEQ_WORDS * i + 5] = d; maxd = max(maxd, d);
+    if (!bad) {
+        if (regen > lp) { out[SEQ_WORDS * nr + 6] = lp; out[SEQ_WORDS * nr + 7] = op - lp; ++nr; }   // the tail (the allocation has nseq + 1 entries)
+        *nruns = nr;
     }
-    *max_depth = maxd;
     return bad ? 1 : 0;
 }
 
@@ -201,6 +201,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     if (huf && !u) { bad = true; huf = false; }
     if (huf) {
         uint32_t p = lhs + u, left = comp - u;
+        fp.hz_off = boff + p; fp.hz_len = left;
         uint32_t sz[4] = {0, 0, 0, 0};
         if (nstreams == 1) { sz[0] = left; fp.s_beg[0] = boff + p; }
         else if (left < 6) bad = true;
@@ -245,8 +246,8 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     warp_converge<true>();
     // ---- sequences: predefined, RLE or FSE-described tables (repeat mode is invalid in a first block) ----
     if (!bad && nseq) {
-        const uint32_t base = atomicAdd(P.pool_cursor, nseq);                // bump allocation in the sequence pool
-        if (base + nseq > P.pool_cap) bad = true;
+        const uint32_t base = atomicAdd(P.pool_cursor, nseq + 1);            // bump allocation in the sequence pool (+1: the tail run)
+        if (base + nseq + 1 > P.pool_cap) bad = true;
         fp.seq_base = base;
         uint32_t rle[3] = {0, 0, 0};
         const uint32_t* tab[3] = {deftab, deftab, deftab}; int tlog[3] = {0, 0, 0};
@@ -270,7 +271,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
             } else { bad = true; break; }
         }
         if (!bad && p >= size) bad = true;
-        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, P.seq_pool + (size_t)SEQ_WORDS * base, &fp.max_depth)) bad = true;
+        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, P.seq_pool + (size_t)SEQ_WORDS * base, &fp.pad)) bad = true;
         if (!bad) nseq_tot += nseq;
     }
     return bad ? 1 : 0;
@@ -319,7 +320,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         const bool live = st == RNSC_OK && !slow;
         FramePlan fp;
         fp.kind = FK_RAW; fp.fcs = (uint32_t)fcs; fp.data_off = 0; fp.dst_off = 0; fp.ltype = 0; fp.regen = 0; fp.lit_off = 0; fp.lit_dst = 0;
-        fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0; fp.max_depth = 0; fp.pad = 0;
+        fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0; fp.max_depth = 0; fp.pad = 0; fp.hz_off = 0; fp.hz_len = 0;
         for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; }
         bool comp_block = false; uint32_t bsz = 0;
         if (live) {
@@ -351,11 +352,14 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     if (slow) { plan_emit(P, c, CLS_SLOW); return; }
     // ---- Huffman tables live in the region too ----
     for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].tab_off = region; region += align16(2u << pl->h[h].log); }
+    uint32_t meta = region;                                      // run tables of the frames with sequences
+    for (int f = 0; f < nf; ++f) { const FramePlan& q = pl->f[f]; if (q.kind == FK_COMP && q.nseq) region += seq_meta_bytes(q.nseq); }
+    if (slow) { plan_emit(P, c, CLS_SLOW); return; }
     const uint32_t cls = region <= P.region[0] ? CLS_S : (region <= P.region[1] ? CLS_A : (region <= P.region[2] ? CLS_B : CLS_SLOW));
     if (cls == CLS_SLOW) { plan_emit(P, c, CLS_SLOW); return; }
     const uint32_t nth = class_threads(cls);
     // ---- the kernel's program: Huffman streams, fills, sequence ops, views ----
-    uint32_t nst = 0, ttot = 0, nfill = 0, nsop = 0;
+    uint32_t nst = 0, ttot = 0, nfill = 0, nsop = 0, zone_off = 0, zone_len = 0;
     int vst = RNSC_OK;
     const uint32_t kl = key_len(P.codec, n);
     uint32_t tot_fcs = 0;
@@ -369,6 +373,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         else if (fp.kind == FK_COMP && fp.nseq == 0 && fp.ltype == 1) hd->fill[nfill++] = FillOp{fp.dst_off, fp.fcs, fp.lit_off};
         const uint32_t my_sop = (fp.kind == FK_COMP && fp.nseq) ? nsop : 0xFFFFFFFFu;
         if (fp.kind == FK_COMP && fp.ltype == 2) {
+            if (fp.hz_len > zone_len + 16) { const uint32_t z0 = align16(cbase + fp.hz_off); zone_off = z0; zone_len = cbase + fp.hz_off + fp.hz_len - z0; }
             const uint32_t q = (fp.regen + 3) / 4;
             for (uint32_t j = 0; j < fp.nstreams; ++j) {
                 StreamPlan sp;
@@ -381,7 +386,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }
         }
-        if (fp.kind == FK_COMP && fp.nseq) hd->sop[nsop++] = SeqOp{fp.dst_off, fp.ltype, fp.ltype == 0 ? cbase + fp.lit_off : fp.lit_off, fp.regen, fp.nseq, fp.seq_base, fp.max_depth, 0};
+        if (fp.kind == FK_COMP && fp.nseq) { hd->sop[nsop++] = SeqOp{fp.dst_off, fp.ltype, fp.ltype == 0 ? cbase + fp.lit_off : fp.lit_off, fp.regen, fp.nseq, fp.seq_base, fp.pad, meta, fp.fcs - fp.regen, 0}; meta += seq_meta_bytes(fp.nseq); }
         // A.8: stream views = slices of the decompressed buffer(s)
         if (nf == 1) {
             if (fp.fcs < kl) vst = RNSC_ERR_REMAINING;
@@ -402,7 +407,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     for (uint32_t s = 0; s < nst; ++s) { hd->st_first[s] = first; first += (hd->st[s].tbits + sub - 1) / sub; }
     for (uint32_t s = nst; s <= PLAN_MAX_STREAMS; ++s) hd->st_first[s] = first;
     hd->need = region; hd->phase = phase; hd->stage_bytes = stage;
-    hd->nhuf = nhuf; hd->nst = nst; hd->sub = sub; hd->nfill = nfill; hd->nsop = nsop; hd->nseq = nseq_tot; hd->view_status = vst; hd->pad = 0;
+    hd->nhuf = nhuf; hd->nst = nst; hd->sub = sub; hd->nfill = nfill; hd->nsop = nsop; hd->nseq = nseq_tot; hd->view_status = vst; hd->pad = 0; hd->zone_off = zone_off; hd->zone_len = zone_len;
     plan_emit(P, c, cls);
 }
 

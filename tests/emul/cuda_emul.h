@@ -29,6 +29,8 @@
 
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint3e { unsigned x, y, z; };
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 extern uint3e threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
 extern unsigned char* emul_dyn_smem;
