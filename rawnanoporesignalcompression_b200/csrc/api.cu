@@ -131,7 +131,11 @@ struct Lane {
     cudaEvent_t ev_in = nullptr, ev_dec = nullptr, ev_out = nullptr;
     bool used = false;
 };
-constexpr uint64_t kSliceSamples = 48ull << 20;   // ~96 MiB of int16 per slice
+static uint64_t slice_samples()                   // samples per pipeline slice (default 128 MiB of int16); RNSC_SLICE_SAMPLES overrides (tuning)
+{
+    static const uint64_t v = [] { const char* e = getenv("RNSC_SLICE_SAMPLES"); const unsigned long long x = e ? strtoull(e, nullptr, 10) : 0; return x ? (uint64_t)x : (64ull << 20); }();
+    return v;
+}
 
 struct rnsc_ctx {
     int device = 0;
@@ -468,14 +472,14 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
     std::lock_guard<std::mutex> lk(c->mu);
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     for (size_t i = 0; i < nchunks; ++i) if (comp_off[i + 1] < comp_off[i]) return fail(RNSC_ERR_BAD_ARG, "comp_off must be non-decreasing");
-    // The batch is cut into slices of about kSliceSamples samples that flow through two lanes of device staging:
+    // The batch is cut into slices of about slice_samples() samples that flow through two lanes of device staging:
     // H2D of slice i+1, decode of slice i and D2H of slice i-1 overlap (three streams chained by events). Chunk i may
     // live anywhere in `comp`/`samples`; inside a lane the chunks are staged back to back (the kernels accept any
     // byte/sample alignment) with dense offset tables.
     size_t first = 0; int slice = 0; int rc = RNSC_OK;
     while (first < nchunks && rc == RNSC_OK) {
         size_t last = first; uint64_t cb = 0, sb = 0; uint32_t max_n = 0;
-        while (last < nchunks && (last == first || sb + n[last] <= kSliceSamples)) { cb += comp_off[last + 1] - comp_off[last]; sb += n[last]; if (n[last] > max_n) max_n = n[last]; ++last; }
+        while (last < nchunks && (last == first || sb + n[last] <= slice_samples())) { cb += comp_off[last + 1] - comp_off[last]; sb += n[last]; if (n[last] > max_n) max_n = n[last]; ++last; }
         const size_t m = last - first;
         Lane& L = c->lane[slice & 1];
         if (L.used) CUDA_OK(cudaEventSynchronize(L.ev_out));     // the lane's previous slice has left the device; its pinned tables are free

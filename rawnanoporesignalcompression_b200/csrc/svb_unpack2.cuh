@@ -146,6 +146,25 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
                 acc += zz_dec(z);
                 val[j] = acc;
             }
+        } else if ((CODEC == RNSC_VBZ || CODEC == RNSC_C1) && cnt == S) {
+            // full thread: the (16 .. 32) payload bytes go through four 64-bit register windows, one per 4 samples
+            uint32_t used = 0;
+#pragma unroll
+            for (int g = 0; g < S / 4; ++g) {
+                uint32_t wlo, whi;
+                load_bits64(s1, 8 * (p1 + used), wlo, whi);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * g + jj;
+                    const bool k = (kb >> j) & 1u;
+                    const uint32_t z = k ? (wlo & 0xFFFFu) : (wlo & 0xFFu);
+                    const uint32_t sh = k ? 16u : 8u;
+                    wlo = __funnelshift_r(wlo, whi, sh); whi >>= sh;
+                    acc += zz_dec(z);
+                    val[j] = acc;
+                }
+                used += 4 + __popc((kb >> (4 * g)) & 15u);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < S; ++j) {
