@@ -43,7 +43,7 @@ struct FastWs {
     Unpack2Ws<NTH> u2;
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
-    uint32_t nlong, longq[128], long_ms[128], long_ml[128], long_of[128], long_mb[128];   // long matches of the frame being resolved (a warp each)
+    uint32_t nlong, longq[128], long_k[128], long_ms[128], long_ml[128], long_of[128], long_mb[128];   // long matches of the frame being resolved (a warp each)
     View view[5];
     int status; uint32_t next;
     alignas(8) unsigned long long mbar;
@@ -235,107 +235,128 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
     return r;
 }
 
-// Executes the LZ sequences of one frame.
+// Origin words of bytes [q0, q1) of one match (stored at origin[mb + q]; matched-byte indices are offset by `obase`,
+// the frame's first word in the shared origin array). Bytes of the first period (q < offset) read output positions
+// ms - of + q: located once in the run table (binary search), then walked -- a position is inside a run's literals
+// or in the matched span behind them. Later bytes of an overlapping match repeat the first period: they point at
+// their own match (one extra jump round instead of a chain as long as the match).
+__device__ inline void emit_origins(const uint2* run, uint32_t nruns, uint32_t regen, uint32_t* origin, uint32_t obase,
+                                    uint32_t ms, uint32_t ml, uint32_t of, uint32_t mb, uint32_t q0, uint32_t q1)
+{
+    const uint32_t qe = min(q1, min(of, ml));
+    mb += obase;
+    if (q0 < qe) {
+        uint32_t x = ms - of + q0;
+        int k = -1;                               // last run whose first output position is <= x (-1: none)
+        if (nruns && x >= run[0].x + run[0].y) {
+            uint32_t lo = 0, hi = nruns;
+            while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; const uint2 r = run[mid]; if (r.x + r.y <= x) lo = mid; else hi = mid; }
+            k = (int)lo;
+        }
+        uint32_t next_lit = k + 1 < (int)nruns ? run[k + 1].x : regen;          // first literal index of the next run
+        uint32_t lit_end = k >= 0 ? next_lit + run[k].y : 0u;                    // end of run k's literals in the output
+        uint32_t next_start = k + 1 < (int)nruns ? next_lit + run[k + 1].y : 0xFFFFFFFFu;   // first output position of the next run
+        for (uint32_t q = q0; q < qe; ++q, ++x) {
+            while (x >= next_start) {
+                ++k;
+                next_lit = k + 1 < (int)nruns ? run[k + 1].x : regen;
+                lit_end = next_lit + run[k].y;
+                next_start = k + 1 < (int)nruns ? next_lit + run[k + 1].y : 0xFFFFFFFFu;
+            }
+            origin[mb + q] = x < lit_end ? (ORIGIN_LIT | x) : obase + x - next_lit;
+        }
+    }
+    uint32_t q = max(q0, of);
+    for (uint32_t r = q % of; q < q1; ++q) { origin[mb + q] = mb + r; if (++r == of) r = 0; }
+}
+
+// Executes the LZ sequences of ALL frames of the chunk in one pass.
 // Literal runs: Huffman literals were already written in place by fast_huffman; raw / RLE literal runs are copied /
 // filled here. Matches: resolved byte-parallel by POINTER JUMPING instead of in sequence order. Every matched byte gets
-// an origin word (global scratch): the output position of a literal, or the index of the matched byte it copies
-// (classified through the run table: a position is either inside a literal run or in the matched span behind it).
-// Chains (a match copying an earlier match, overlapping run-length matches) halve every round; then every matched
-// byte is read from its literal. One thread per short match, a whole warp per long one.
+// an origin word: the output position of a literal, or the index of the matched byte it copies (classified through the
+// run table). Chains (a match copying an earlier match) halve every round; then every matched byte is read from its
+// literal. One thread per short match, a whole warp per long one. The origin words live in the dead bitstream area
+// of the staged chunk when they fit, else in global scratch.
 template <int NTH>
-__device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const SeqOp& op, const uint32_t* sq, uint8_t* region, uint32_t* origin)
+__device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const PlanHead& hd, const uint32_t* pool, uint8_t* region, uint32_t* gorigin)
 {
     const int tid = threadIdx.x;
-    uint8_t* dst = region + op.dst_off;
-    const uint32_t nseq = op.nseq, nruns = op.nruns, regen = op.regen;
-    const uint2* run = (const uint2*)(region + op.meta_off);
-    if (op.ltype != 2) {
-        for (uint32_t i = 0; i < nruns; ++i) {
-            const uint32_t lp = run[i].x, len = (i + 1 < nruns ? run[i + 1].x : regen) - lp;
+    const uint32_t nsop = hd.nsop;
+    uint32_t sbase[6], obase[6];                       // first sequence / first origin word of every frame
+    sbase[0] = 0; obase[0] = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { const bool on = (uint32_t)k < nsop; sbase[k + 1] = sbase[k] + (on ? hd.sop[k].nseq : 0u); obase[k + 1] = obase[k] + (on ? hd.sop[k].mbytes : 0u); }
+    const uint32_t total_seq = sbase[5], total_mb = obase[5];
+    uint32_t* origin = (size_t)total_mb * 4 <= hd.zone_len ? (uint32_t*)(region + hd.zone_off) : gorigin;
+    for (uint32_t k = 0; k < nsop; ++k) {
+        const SeqOp& op = hd.sop[k];
+        if (op.ltype == 2) continue;
+        const uint2* run = (const uint2*)(region + op.meta_off);
+        uint8_t* dst = region + op.dst_off;
+        for (uint32_t i = 0; i < op.nruns; ++i) {
+            const uint32_t lp = run[i].x, len = (i + 1 < op.nruns ? run[i + 1].x : op.regen) - lp;
             uint8_t* d = dst + lp + run[i].y;
             if (op.ltype == 1) for (uint32_t q = tid; q < len; q += NTH) d[q] = (uint8_t)op.lit;
             else { const uint8_t* s = region + op.lit + lp; for (uint32_t q = tid; q < len; q += NTH) d[q] = s[q]; }
         }
     }
-    // Origin words of bytes [q0, q1) of one match. Bytes of the first period (q < offset) read output positions
-    // ms - of + q: located once in the run table (binary search), then walked -- a position is inside a run's literals
-    // or in the matched span behind them. Later bytes of an overlapping match repeat the first period: they point at
-    // their own match (one extra jump round instead of a chain as long as the match).
-    auto emit = [&](uint32_t ms, uint32_t ml, uint32_t of, uint32_t mb, uint32_t q0, uint32_t q1) {
-        const uint32_t qe = min(q1, min(of, ml));
-        if (q0 < qe) {
-            uint32_t x = ms - of + q0;
-            int k = -1;                               // last run whose first output position is <= x (-1: none)
-            if (nruns && x >= run[0].x + run[0].y) {
-                uint32_t lo = 0, hi = nruns;
-                while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; const uint2 r = run[mid]; if (r.x + r.y <= x) lo = mid; else hi = mid; }
-                k = (int)lo;
-            }
-            uint32_t next_lit = k + 1 < (int)nruns ? run[k + 1].x : regen;          // first literal index of the next run
-            uint32_t lit_end = k >= 0 ? next_lit + run[k].y : 0u;                    // end of run k's literals in the output
-            uint32_t next_start = k + 1 < (int)nruns ? next_lit + run[k + 1].y : 0xFFFFFFFFu;   // first output position of the next run
-            for (uint32_t q = q0; q < qe; ++q, ++x) {
-                while (x >= next_start) {
-                    ++k;
-                    next_lit = k + 1 < (int)nruns ? run[k + 1].x : regen;
-                    lit_end = next_lit + run[k].y;
-                    next_start = k + 1 < (int)nruns ? next_lit + run[k + 1].y : 0xFFFFFFFFu;
-                }
-                origin[mb + q] = x < lit_end ? (ORIGIN_LIT | x) : x - next_lit;
-            }
-        }
-        uint32_t q = max(q0, of);
-        for (uint32_t r = q % of; q < q1; ++q) { origin[mb + q] = mb + r; if (++r == of) r = 0; }
-    };
     constexpr uint32_t LONG = 48, QCAP = 128;
     if (tid == 0) ws->nlong = 0;
-    // my (up to two) sequences, fetched once from the global pool
-    uint32_t m_ms[2] = {0, 0}, m_ml[2] = {0, 0}, m_of[2] = {1, 1}, m_mb[2] = {0, 0};
+    // my (up to two) sequences, fetched once from the global pool: frame, match start, length, offset, matched-byte index
+    uint32_t m_k[2] = {0, 0}, m_ms[2] = {0, 0}, m_ml[2] = {0, 0}, m_of[2] = {1, 1}, m_mb[2] = {0, 0};
+    auto fetch = [&](uint32_t idx, uint32_t& k, uint32_t& ms, uint32_t& ml, uint32_t& of, uint32_t& mb) {
+        k = 0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const uint32_t i = tid + k * NTH;
-        if (i < nseq) { const uint32_t* e = sq + (size_t)SEQ_WORDS * i; m_ms[k] = e[4] + e[0]; m_ml[k] = e[1]; m_of[k] = e[2]; m_mb[k] = e[5]; }
-    }
+        for (int j = 1; j < 5; ++j) if (idx >= sbase[j]) k = j;
+        const uint32_t* e = pool + (size_t)SEQ_WORDS * (hd.sop[k].seq_base + idx - sbase[k]);
+        ms = e[4] + e[0]; ml = e[1]; of = e[2]; mb = e[5];
+    };
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { const uint32_t idx = tid + j * NTH; if (idx < total_seq) fetch(idx, m_k[j], m_ms[j], m_ml[j], m_of[j], m_mb[j]); }
     __syncthreads();
     // ---- round 0: origin of every matched byte ----
-    for (uint32_t i = tid, k = 0; i < nseq; i += NTH, ++k) {
-        uint32_t ms, ml, of, mb;
-        if (k < 2) { ms = m_ms[k & 1]; ml = m_ml[k & 1]; of = m_of[k & 1]; mb = m_mb[k & 1]; }
-        else { const uint32_t* e = sq + (size_t)SEQ_WORDS * i; ms = e[4] + e[0]; ml = e[1]; of = e[2]; mb = e[5]; }
+    for (uint32_t idx = tid, j = 0; idx < total_seq; idx += NTH, ++j) {
+        uint32_t k, ms, ml, of, mb;
+        if (j < 2) { k = m_k[j & 1]; ms = m_ms[j & 1]; ml = m_ml[j & 1]; of = m_of[j & 1]; mb = m_mb[j & 1]; } else fetch(idx, k, ms, ml, of, mb);
         if (ml > LONG) {
             const uint32_t q = atomicAdd(&ws->nlong, 1u);
-            if (q < QCAP) { ws->longq[q] = i; ws->long_ms[q] = ms; ws->long_ml[q] = ml; ws->long_of[q] = of; ws->long_mb[q] = mb; continue; }
+            if (q < QCAP) { ws->longq[q] = idx; ws->long_k[q] = k; ws->long_ms[q] = ms; ws->long_ml[q] = ml; ws->long_of[q] = of; ws->long_mb[q] = mb; continue; }
         }
-        emit(ms, ml, of, mb, 0, ml);
+        const SeqOp& op = hd.sop[k];
+        emit_origins((const uint2*)(region + op.meta_off), op.nruns, op.regen, origin, obase[k], ms, ml, of, mb, 0, ml);
     }
     __syncthreads();
     const uint32_t nl = min(ws->nlong, QCAP), lane = tid & 31u;
-    for (uint32_t k = tid >> 5; k < nl; k += NTH / 32) {
-        const uint32_t ms = ws->long_ms[k], ml = ws->long_ml[k], of = ws->long_of[k], mb = ws->long_mb[k];
+    for (uint32_t w = tid >> 5; w < nl; w += NTH / 32) {
+        const uint32_t k = ws->long_k[w], ms = ws->long_ms[w], ml = ws->long_ml[w], of = ws->long_of[w], mb = ws->long_mb[w];
+        const SeqOp& op = hd.sop[k];
         const uint32_t c = (ml + 31) / 32;                                  // a contiguous piece per lane
-        emit(ms, ml, of, mb, min(ml, lane * c), min(ml, (lane + 1) * c));
+        emit_origins((const uint2*)(region + op.meta_off), op.nruns, op.regen, origin, obase[k], ms, ml, of, mb, min(ml, lane * c), min(ml, (lane + 1) * c));
     }
     __syncthreads();
     // ---- pointer jumping ----
     for (int round = 0; round < 32; ++round) {
         bool open = false;
-        for (uint32_t b = tid; b < op.mbytes; b += NTH) {
+        for (uint32_t b = tid; b < total_mb; b += NTH) {
             const uint32_t o = origin[b];
             if (!(o & ORIGIN_LIT)) { const uint32_t o2 = origin[o]; origin[b] = o2; open |= !(o2 & ORIGIN_LIT); }
         }
         if (!__syncthreads_or(open)) break;
     }
     // ---- every matched byte from its literal ----
-    for (uint32_t i = tid, k = 0; i < nseq; i += NTH, ++k) {
-        uint32_t ms, ml, mb;
-        if (k < 2) { ms = m_ms[k & 1]; ml = m_ml[k & 1]; mb = m_mb[k & 1]; }
-        else { const uint32_t* e = sq + (size_t)SEQ_WORDS * i; ms = e[4] + e[0]; ml = e[1]; mb = e[5]; }
-        if (ml > LONG) { bool queued = false; for (uint32_t q = 0; q < nl; ++q) queued |= ws->longq[q] == i; if (queued) continue; }
-        for (uint32_t q = 0; q < ml; ++q) dst[ms + q] = dst[origin[mb + q] & ~ORIGIN_LIT];
+    for (uint32_t idx = tid, j = 0; idx < total_seq; idx += NTH, ++j) {
+        uint32_t k, ms, ml, of, mb;
+        if (j < 2) { k = m_k[j & 1]; ms = m_ms[j & 1]; ml = m_ml[j & 1]; mb = m_mb[j & 1]; } else fetch(idx, k, ms, ml, of, mb);
+        if (ml > LONG) { bool queued = false; for (uint32_t q = 0; q < nl; ++q) queued |= ws->longq[q] == idx; if (queued) continue; }
+        uint8_t* dst = region + hd.sop[k].dst_off;
+        const uint32_t* o = origin + obase[k] + mb;
+        for (uint32_t q = 0; q < ml; ++q) dst[ms + q] = dst[o[q] & ~ORIGIN_LIT];
     }
-    for (uint32_t k = tid >> 5; k < nl; k += NTH / 32) {
-        const uint32_t ms = ws->long_ms[k], ml = ws->long_ml[k], mb = ws->long_mb[k];
-        for (uint32_t q = lane; q < ml; q += 32) dst[ms + q] = dst[origin[mb + q] & ~ORIGIN_LIT];
+    for (uint32_t w = tid >> 5; w < nl; w += NTH / 32) {
+        const uint32_t k = ws->long_k[w], ms = ws->long_ms[w], ml = ws->long_ml[w], mb = ws->long_mb[w];
+        uint8_t* dst = region + hd.sop[k].dst_off;
+        const uint32_t* o = origin + obase[k] + mb;
+        for (uint32_t q = lane; q < ml; q += 32) dst[ms + q] = dst[o[q] & ~ORIGIN_LIT];
     }
     __syncthreads();
 }
@@ -383,9 +404,7 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     __syncthreads();
     pc.mark(PH_STAGE);
     if (hd.nst && fast_huffman<NTH>(ws, region, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
-    for (uint32_t i = 0; i < hd.nsop; ++i) fast_exec_sequences<NTH>(ws, hd.sop[i], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[i].seq_base, region,
-                                                                   // origin words: in the dead bitstream area of the staged chunk when they fit, else global scratch
-                                                                   (size_t)hd.sop[i].mbytes * 4 <= hd.zone_len ? (uint32_t*)(region + hd.zone_off) : P.origin + (size_t)blockIdx.x * P.origin_stride);
+    if (hd.nsop) fast_exec_sequences<NTH>(ws, hd, P.seq_pool, region, P.origin + (size_t)blockIdx.x * P.origin_stride);
     if (tid < 5) { ws->view[tid].p = region + hd.view[tid].off; ws->view[tid].len = hd.view[tid].len; }
     if (tid == 0 && hd.view_status != RNSC_OK) ws->status = hd.view_status;
     __syncthreads();
