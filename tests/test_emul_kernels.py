@@ -73,3 +73,29 @@ def test_fast_path_routing_and_sequences(ecodec, oracle):
         assert fs + fa + fb + slow == len(chunks)
         if codec != 1:
             assert slow == 0 and fb >= 1 and fs >= 1, (codec, fs, fa, fb, slow)
+
+
+def test_fuzz_corrupt_chunks_never_crash_and_agree_with_rfc_decoder(ecodec, oracle):
+    """Random byte flips anywhere in a chunk (headers, Huffman tree, bitstreams, sequences): the decoder must return a
+    status or the same samples as the oracle's RFC 8878 decoder -- never crash, hang or write out of bounds."""
+    rng = np.random.default_rng(1234)
+    x = recipes.walk(6000, 31, 14.0)
+    flat = x.copy(); flat[1000:1600] = flat[999]
+    for codec, src in ((6, x), (0, x), (6, flat), (0, flat), (1, x)):
+        good = oracle.encode(codec, src)
+        trials = []
+        for _ in range(24):
+            b = bytearray(good)
+            for _k in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(0, len(b)))
+                b[pos] ^= int(rng.integers(1, 256))
+            trials.append(bytes(b))
+        trials.append(good[: len(good) // 2])                       # truncated
+        trials.append(good + b"\x00\x01\x02")                       # trailing garbage
+        outs, st = ecodec.decompress_batch(trials + [good], [src.size] * (len(trials) + 1), codec)
+        assert st[-1] == 0 and (outs[-1] == src).all()              # the intact chunk next to them is untouched
+        for t, o, s in zip(trials, outs, st):
+            ost, oy = oracle.decode_status(codec, t, src.size, own_zstd=True)
+            assert (s != 0) == (ost != 0), (codec, s, ost)
+            if ost == 0:
+                assert (o == oy).all()
