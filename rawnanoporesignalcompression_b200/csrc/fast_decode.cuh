@@ -270,6 +270,40 @@ __device__ inline void emit_origins(const uint2* run, uint32_t nruns, uint32_t r
     for (uint32_t r = q % of; q < q1; ++q) { origin[mb + q] = mb + r; if (++r == of) r = 0; }
 }
 
+// Frames with a handful of sequences (C5: keys, Lhigh): ONE warp executes the frame's matches in sequence order, the
+// lanes copying the bytes of a match together; different frames of the chunk are handled by different warps at once.
+__device__ inline void fast_exec_sequences_ordered(const SeqOp& op, const uint32_t* sq, uint8_t* region)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    uint8_t* dst = region + op.dst_off;
+    const uint32_t nseq = op.nseq;
+    if (op.ltype != 2) {
+        const uint2* run = (const uint2*)(region + op.meta_off);
+        for (uint32_t i = 0; i < op.nruns; ++i) {
+            const uint32_t lp = run[i].x, len = (i + 1 < op.nruns ? run[i + 1].x : op.regen) - lp;
+            uint8_t* d = dst + lp + run[i].y;
+            if (op.ltype == 1) for (uint32_t q = lane; q < len; q += 32) d[q] = (uint8_t)op.lit;
+            else { const uint8_t* s = region + op.lit + lp; for (uint32_t q = lane; q < len; q += 32) d[q] = s[q]; }
+        }
+    }
+    uint32_t m_ms[2] = {0, 0}, m_ml[2] = {0, 0}, m_of[2] = {1, 1};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t i = lane + k * 32;
+        if (i < nseq) { const uint32_t* e = sq + (size_t)SEQ_WORDS * i; m_ms[k] = e[4] + e[0]; m_ml[k] = e[1]; m_of[k] = e[2]; }
+    }
+    __syncwarp();
+    for (uint32_t i = 0; i < nseq; ++i) {
+        const int src = (int)(i & 31u);
+        const uint32_t ms = __shfl_sync(0xffffffffu, i < 32 ? m_ms[0] : m_ms[1], src), ml = __shfl_sync(0xffffffffu, i < 32 ? m_ml[0] : m_ml[1], src);
+        const uint32_t of = __shfl_sync(0xffffffffu, i < 32 ? m_of[0] : m_of[1], src);
+        uint8_t* d = dst + ms; const uint8_t* sp = d - of;
+        if (of >= 32) { for (uint32_t k0 = 0; k0 < ml; k0 += 32) { const uint32_t q = k0 + lane; if (q < ml) d[q] = sp[q]; __syncwarp(); } }
+        else { for (uint32_t q = lane; q < ml; q += 32) d[q] = sp[q % of]; }
+        __syncwarp();
+    }
+}
+
 // Executes the LZ sequences of ALL frames of the chunk in one pass.
 // Literal runs: Huffman literals were already written in place by fast_huffman; raw / RLE literal runs are copied /
 // filled here. Matches: resolved byte-parallel by POINTER JUMPING instead of in sequence order. Every matched byte gets
@@ -404,7 +438,13 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     __syncthreads();
     pc.mark(PH_STAGE);
     if (hd.nst && fast_huffman<NTH>(ws, region, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
-    if (hd.nsop) fast_exec_sequences<NTH>(ws, hd, P.seq_pool, region, P.origin + (size_t)blockIdx.x * P.origin_stride);
+    if (hd.nsop) {
+        if (hd.nseq <= 64) {      // few sequences: one warp per frame, in order
+            const uint32_t w = tid >> 5;
+            if (w < hd.nsop) fast_exec_sequences_ordered(hd.sop[w], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[w].seq_base, region);
+            __syncthreads();
+        } else fast_exec_sequences<NTH>(ws, hd, P.seq_pool, region, P.origin + (size_t)blockIdx.x * P.origin_stride);
+    }
     if (tid < 5) { ws->view[tid].p = region + hd.view[tid].off; ws->view[tid].len = hd.view[tid].len; }
     if (tid == 0 && hd.view_status != RNSC_OK) ws->status = hd.view_status;
     __syncthreads();
