@@ -6,7 +6,7 @@
 // FSE-compressed weights) into a table *recipe*, and decodes the (few) sequences of the frame when their
 // tables are predefined or RLE. The result is a fixed-size ChunkPlan in global memory that the fast decode
 // kernel (fast_decode.cuh) consumes with no serial work left. Anything unusual (multi-block frames,
-// treeless literals, FSE-compressed sequence tables, too many sequences, inconsistent sizes) is not an error
+// treeless literals, more Huffman sections than the plan holds, inconsistent sizes) is not an error
 // here: the chunk is routed to the general CTA-cooperative decoder (zstd_decode.cuh, k_decode_chunks), which
 // owns the exact error semantics. Replaces, with the fast kernel, the reference's ZSTD_getFrameContentSize +
 // ZSTD_decompress calls (signal_compression.cpp:103,117; C5.hpp:494-565,588-655).
@@ -15,7 +15,6 @@
 
 namespace rnsc {
 
-constexpr int PLAN_MAX_SEQ = 256;     // chunks with at most this many sequences get them copied to shared memory
 constexpr int PLAN_MAX_HUF = 3;       // Huffman-coded literal sections per chunk described in the plan
 constexpr int PLAN_MAX_STREAMS = 4 * PLAN_MAX_HUF;
 constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
@@ -33,10 +32,9 @@ struct FramePlan {               // planner-internal description of one frame
     uint32_t dst_off;            // region offset of the decoded output (RLE, COMP unless zero-copy)
     uint32_t ltype, regen;       // literals: 0 raw, 1 RLE, 2 Huffman; count
     uint32_t lit_off;            // raw literals: chunk offset; RLE literals: the byte value
-    uint32_t lit_dst;            // unused
     uint32_t nstreams, huf;      // Huffman: 1 or 4 streams; index of the HufPlan
     uint32_t nseq, seq_base;     // sequences [seq_base, seq_base + nseq) of the sequence pool
-    uint32_t max_depth, pad;     // max_depth: unused; pad = number of non-empty literal runs
+    uint32_t nruns;              // number of non-empty literal runs (the tail after the last match included)
     uint32_t hz_off, hz_len;     // chunk offset / size of the Huffman bitstream area (dead once the literals are decoded)
     uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
 };
@@ -52,9 +50,10 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
 // ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
 struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pad0, pad1, pad2; };   // sop: index of the frame's SeqOp or ~0
 struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
-struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base, nruns, meta_off, mbytes, pad; };   // mbytes = matched bytes = fcs - regen   // LZ sequences of a frame (entries [seq_base, +nseq) of the
-                                                                                   // sequence pool); lit = region offset of raw literals or the RLE byte; meta_off = region offset of the run table
-                                                                                   // the kernel copies there: nruns x {first literal index, shift to the final position} (non-empty literal runs only)
+// LZ sequences of a frame: entries [seq_base, seq_base + nseq] of the sequence pool. lit = region offset of raw literals or
+// the RLE byte; meta_off = region offset of the run table the kernel copies there: nruns x {first literal index, shift to
+// the final position} (non-empty literal runs only); mbytes = matched bytes = fcs - regen.
+struct SeqOp { uint32_t dst_off, ltype, lit, regen, nseq, seq_base, nruns, meta_off, mbytes, pad; };
 struct ViewPlan { uint32_t off, len; };                                  // stream k of the splitter inverse = region[off .. off+len)
 // Sequence pool entry i of a frame: words 0-5 describe sequence i (literal length, match length, offset, literal position,
 // output position, matched bytes in front of it); words 6-7 of entry k = the k-th NON-EMPTY literal run (first literal
@@ -190,7 +189,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     }
     if (!bad && nseq == 0 && regen != fp.fcs) bad = true;
     if (!bad) {
-        fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = 0; fp.max_depth = 0; fp.pad = 0;
+        fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = 0; fp.nruns = 0;
         fp.lit_off = ltype == 0 ? boff + lhs : (ltype == 1 ? ldg8(src + lhs) : 0);
     }
     // ---- Huffman tree description + stream geometry (every lane walks through huf_read_weights) ----
@@ -271,7 +270,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
             } else { bad = true; break; }
         }
         if (!bad && p >= size) bad = true;
-        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, P.seq_pool + (size_t)SEQ_WORDS * base, &fp.pad)) bad = true;
+        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, P.seq_pool + (size_t)SEQ_WORDS * base, &fp.nruns)) bad = true;
         if (!bad) nseq_tot += nseq;
     }
     return bad ? 1 : 0;
@@ -319,8 +318,8 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         }
         const bool live = st == RNSC_OK && !slow;
         FramePlan fp;
-        fp.kind = FK_RAW; fp.fcs = (uint32_t)fcs; fp.data_off = 0; fp.dst_off = 0; fp.ltype = 0; fp.regen = 0; fp.lit_off = 0; fp.lit_dst = 0;
-        fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0; fp.max_depth = 0; fp.pad = 0; fp.hz_off = 0; fp.hz_len = 0;
+        fp.kind = FK_RAW; fp.fcs = (uint32_t)fcs; fp.data_off = 0; fp.dst_off = 0; fp.ltype = 0; fp.regen = 0; fp.lit_off = 0;
+        fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0; fp.nruns = 0; fp.hz_off = 0; fp.hz_len = 0;
         for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; }
         bool comp_block = false; uint32_t bsz = 0;
         if (live) {
@@ -386,7 +385,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }
         }
-        if (fp.kind == FK_COMP && fp.nseq) { hd->sop[nsop++] = SeqOp{fp.dst_off, fp.ltype, fp.ltype == 0 ? cbase + fp.lit_off : fp.lit_off, fp.regen, fp.nseq, fp.seq_base, fp.pad, meta, fp.fcs - fp.regen, 0}; meta += seq_meta_bytes(fp.nseq); }
+        if (fp.kind == FK_COMP && fp.nseq) { hd->sop[nsop++] = SeqOp{fp.dst_off, fp.ltype, fp.ltype == 0 ? cbase + fp.lit_off : fp.lit_off, fp.regen, fp.nseq, fp.seq_base, fp.nruns, meta, fp.fcs - fp.regen, 0}; meta += seq_meta_bytes(fp.nseq); }
         // A.8: stream views = slices of the decompressed buffer(s)
         if (nf == 1) {
             if (fp.fcs < kl) vst = RNSC_ERR_REMAINING;
