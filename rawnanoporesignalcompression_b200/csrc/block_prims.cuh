@@ -16,6 +16,22 @@ __device__ __forceinline__ T warp_inclusive_scan(T v)
     return v;
 }
 
+// 32-bit flavour: shfl.up returns "source lane exists" as a predicate, so a step is a shuffle and a predicated add.
+// All 32 lanes must call it.
+template <>
+__device__ __forceinline__ uint32_t warp_inclusive_scan<uint32_t>(uint32_t v)
+{
+#ifdef RNSC_EMUL
+    const int lane = threadIdx.x & 31;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+#else
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n.reg .pred p;\n.reg .b32 r;\nshfl.sync.up.b32 r|p, %0, %1, 0, 0xffffffff;\n@p add.u32 %0, %0, r;\n}" : "+r"(v) : "r"(d));
+#endif
+    return v;
+}
+
 // Exclusive scan over the NT threads of the CTA. `scratch` holds NWARP+1 elements of T in shared memory.
 // Every thread of the CTA must call it. Returns the exclusive prefix; *total receives the CTA sum.
 // Two __syncthreads(): scratch may be reused right after the call returns for a *different* array only.

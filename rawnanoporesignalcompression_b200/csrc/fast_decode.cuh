@@ -93,7 +93,7 @@ __device__ inline void fast_build_table(uint16_t* tab, const HufPlan* hp, int t,
             if (u < size) {
                 while (hp->cls_start[w + 1] <= u) ++w;
                 const uint32_t sym = hp->sorted[hp->cls_sym[w] + ((u - hp->cls_start[w]) >> (w - 1))];
-                e = ((L + 1 - w) << 8) | sym;
+                e = (sym << 8) | (L + 1 - w);        // low byte: code length, high byte: symbol
             }
             if (k & 1) packed[k >> 1] |= e << 16; else packed[k >> 1] = e;
         }
@@ -110,25 +110,27 @@ __device__ __forceinline__ void bits_ending_at(const uint32_t* w, uint32_t A, ui
     hi = __funnelshift_l(b, a, sh); lo = __funnelshift_l(c, b, sh);
 }
 
-#define RNSC_HUF_STEP(hi, lo, tab, L, nbv, ev)                                   \
-    do { ev = (tab)[(hi) >> (32 - (L))]; nbv = ev >> 8;                          \
-         hi = __funnelshift_l(lo, hi, nbv); lo <<= nbv; } while (0)
+// One symbol: table entry `ev` = symbol << 8 | code length. The funnel shifts take the entry itself as the shift
+// amount (they use its low 5 bits; a code is at most 12 bits), so the serial chain is peek -> load -> shift.
+#define RNSC_HUF_STEP(hi, lo, tab, L, ev)                                        \
+    do { ev = (tab)[(hi) >> (32 - (L))];                                         \
+         hi = __funnelshift_l(lo, hi, ev); lo = __funnelshift_l(0u, lo, ev); } while (0)
 
 // Advances from consumed-bit position p to the first symbol boundary >= lim; counts the symbols decoded.
 __device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, const uint16_t* tab, uint32_t L, uint32_t& p, uint32_t lim, uint32_t& cnt)
 {
-    uint32_t hi, lo, nb, e;
+    uint32_t hi, lo, e;
     while (p + 4 * HUF_LOG_MAX <= lim) {
         bits_ending_at(words, abit - p, hi, lo);
-        uint32_t adv = 0;
+        uint32_t adv = 0;                           // the low byte sums the four code lengths (<= 48)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { RNSC_HUF_STEP(hi, lo, tab, L, nb, e); adv += nb; }
-        p += adv; cnt += 4;
+        for (int k = 0; k < 4; ++k) { RNSC_HUF_STEP(hi, lo, tab, L, e); adv += e; }
+        p += adv & 0xFFu; cnt += 4;
     }
     while (p < lim) {
         bits_ending_at(words, abit - p, hi, lo);
-        RNSC_HUF_STEP(hi, lo, tab, L, nb, e);
-        p += nb; cnt += 1;
+        RNSC_HUF_STEP(hi, lo, tab, L, e);
+        p += e & 0xFFu; cnt += 1;
     }
 }
 
@@ -186,7 +188,7 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
     bool bad = false;
     if (active && (uint32_t)tid + 1 == hd.st_first[j + 1]) bad = (my_end != T) || (off + my_cnt != sp.count);
     if (active && my_cnt && off < sp.count) {
-        uint32_t p = my_start, rem = min(my_cnt, sp.count - off), hi, lo, nb, e;      // clamped: a corrupt stream cannot write outside its output
+        uint32_t p = my_start, rem = min(my_cnt, sp.count - off), hi, lo, e;      // clamped: a corrupt stream cannot write outside its output
         uint32_t li = sp.lit0 + off;                                                   // literal index of my first symbol
         // Literal runs: without sequences the whole frame is one run at shift 0; with sequences run i (the literals in
         // front of match i; run nseq = the tail) starts at literal index run[i].x and lands run[i].y bytes further
@@ -202,15 +204,18 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
         }
         if (li + rem <= run_end) {      // all my literals belong to one run (always, without sequences)
             uint8_t* o = region + sp.out + li + shift;
-            while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --rem; }
+            while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
             while (rem >= 4) {
                 bits_ending_at(words, abit - p, hi, lo);
                 uint32_t word = 0, adv = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { RNSC_HUF_STEP(hi, lo, tab, L, nb, e); adv += nb; word |= (e & 0xFFu) << (8 * q); }
-                *(uint32_t*)o = word; o += 4; p += adv; rem -= 4;
+                for (int q = 0; q < 4; ++q) {
+                    RNSC_HUF_STEP(hi, lo, tab, L, e); adv += e;
+                    word = __byte_perm(word, e, q == 0 ? 0x3215u : (q == 1 ? 0x3250u : (q == 2 ? 0x3510u : 0x5210u)));   // byte q <- symbol
+                }
+                *(uint32_t*)o = word; o += 4; p += adv & 0xFFu; rem -= 4;
             }
-            while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, nb, e); p += nb; *o++ = (uint8_t)e; --rem; }
+            while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
         } else {
             // runs can be a few literals long (the key region of a VBZ frame): one symbol at a time from a buffered
             // 64-bit window, switching the output position whenever a run ends (the next run is fetched ahead)
@@ -219,9 +224,9 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
             int avail = 0;
             while (rem) {
                 if (avail < (int)HUF_LOG_MAX) { bits_ending_at(words, abit - p, hi, lo); avail = 64; }
-                RNSC_HUF_STEP(hi, lo, tab, L, nb, e);
-                p += nb; avail -= (int)nb;
-                *o++ = (uint8_t)e; ++li; --rem;
+                RNSC_HUF_STEP(hi, lo, tab, L, e);
+                p += e & 0xFFu; avail -= (int)(e & 0xFFu);
+                *o++ = (uint8_t)(e >> 8); ++li; --rem;
                 if (li == run_end) {
                     ++seg; o = region + sp.out + li + nxt.y;
                     nxt = seg + 1 < nruns ? run[seg + 1] : make_uint2(sp.regen, 0u);

@@ -6,8 +6,12 @@
 //     OUTPUT: results go from registers to global memory with two 128-bit stores, no shared-memory tile;
 //   * key bits and the thread's payload bytes/nibbles are fetched as aligned 32-bit words and funnel-shifted
 //     into register windows (C4/C5), so the per-sample work is predicates, shifts and adds, no loads;
-//   * stream positions and the delta^-1 prefix sum use one-barrier CTA scans (block_scan_1b).
-// Works on generic pointers: the streams may live in shared memory (fast decoder) or global memory.
+//   * stream positions and the delta^-1 prefix sum use one-barrier CTA scans of ONE 32-bit word each
+//     (block_scan_1b): the unit counts of two streams share a word, and the count of large values of the
+//     NEXT tile rides in the low half of the word whose high half carries the tile's delta sums (mod 2^16);
+//   * the per-sample step of C4/C5 is predicated code without branches (win_step).
+// Works on generic pointers; every stream must be readable up to 8 bytes past its end (the fast decoder's
+// region pads each stream with 16 bytes).
 #pragma once
 #include "block_prims.cuh"
 
@@ -17,25 +21,23 @@ constexpr int U2_SPT = 16;
 
 template <int NTH>
 struct Unpack2Ws {
-    unsigned long long s64[2][NTH / 32];
-    uint32_t s32[2][NTH / 32];
+    uint32_t sa[NTH / 32], sb[NTH / 32];      // warp totals of the two scans of a tile (A: unit counts, B: delta sums | large count)
     int err;
 };
 
-// Exclusive CTA scan with a single barrier: every warp redundantly scans the per-warp totals. `scratch` must
-// alternate between two buffers on consecutive calls.
-template <typename T, int NTH>
-__device__ __forceinline__ T block_scan_1b(T v, T* scratch, T* total)
+// Exclusive CTA scan of a 32-bit word with a single barrier: every warp sums the totals of the warps in front of
+// it with one warp reduction. Two consecutive calls must use different scratch arrays.
+template <int NTH>
+__device__ __forceinline__ uint32_t block_scan_1b(uint32_t v, uint32_t* scratch, uint32_t* total)
 {
     constexpr int NW = NTH / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const T inc = warp_inclusive_scan(v);
+    const uint32_t inc = warp_inclusive_scan(v);
     if (lane == 31) scratch[warp] = inc;
     __syncthreads();
-    const T w = lane < NW ? scratch[lane] : T(0);
-    const T winc = warp_inclusive_scan(w);
-    const T base = __shfl_sync(0xffffffffu, winc - w, warp);
-    *total = __shfl_sync(0xffffffffu, winc, NW - 1);
+    const uint32_t w = lane < NW ? scratch[lane] : 0u;
+    *total = __reduce_add_sync(0xffffffffu, w);
+    const uint32_t base = __reduce_add_sync(0xffffffffu, lane < warp ? w : 0u);
     return base + inc - v;
 }
 
@@ -57,7 +59,48 @@ __device__ __forceinline__ void load_bits64(const uint8_t* p, uint32_t bit, uint
     lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
 }
 
-__device__ __forceinline__ uint32_t zz_dec(uint32_t z) { return (z >> 1) ^ (0u - (z & 1u)); }   // low 16 bits are the delta
+// sum += zigzag^-1(z) in 32-bit arithmetic (the low 16 bits are what counts): z even -> z/2, z odd -> -(z/2) - 1 = z/2 - z
+__device__ __forceinline__ uint32_t zz_dec(uint32_t z) { return (z >> 1) - (z & 1u) * z; }
+
+// One sample of C4/C5: `bit` = 1 << 2j selects sample j in the class masks m1 (nibble), m2 (byte), m3 (two bytes).
+// Takes the sample's unit from the front of its stream window and returns the zigzag value z. Predicated, no branch:
+// the three classes are rare enough per lane and common enough per warp that a branch would always be taken.
+// zq:zq2 hold the thread's next four large values, offsets already added.
+template <int CODEC>
+__device__ __forceinline__ uint32_t win_step(uint32_t bit, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t& sw, uint32_t& mlo, uint32_t& mhi,
+                                             uint32_t& zq, uint32_t& zq2)
+{
+    constexpr uint32_t OS = CODEC == RNSC_C5 ? 1u : 0u, OM = CODEC == RNSC_C5 ? 17u : 0u;
+    uint32_t z;
+#ifdef RNSC_EMUL
+    z = 0;
+    if (m1 & bit) { z = (sw & 15u) + OS; sw >>= 4; }
+    if (m2 & bit) { z = (mlo & 255u) + OM; mlo = __funnelshift_r(mlo, mhi, 8); mhi >>= 8; }
+    if (m3 & bit) { z = zq & 0xFFFFu; zq = __funnelshift_r(zq, zq2, 16); zq2 >>= 16; }
+#else
+    asm("{\n"
+        ".reg .pred ps, pm, pl;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %6, %9;\n setp.ne.u32 ps, t, 0;\n"
+        "and.b32 t, %7, %9;\n setp.ne.u32 pm, t, 0;\n"
+        "and.b32 t, %8, %9;\n setp.ne.u32 pl, t, 0;\n"
+        "mov.u32 %0, 0;\n"
+        "@ps and.b32 %0, %1, 15;\n"
+        "@ps add.u32 %0, %0, %10;\n"
+        "@ps shr.u32 %1, %1, 4;\n"
+        "@pm and.b32 %0, %2, 255;\n"
+        "@pm add.u32 %0, %0, %11;\n"
+        "@pm shf.r.wrap.b32 %2, %2, %3, 8;\n"
+        "@pm shr.u32 %3, %3, 8;\n"
+        "@pl and.b32 %0, %4, 0xffff;\n"
+        "@pl shf.r.wrap.b32 %4, %4, %5, 16;\n"
+        "@pl shr.u32 %5, %5, 16;\n"
+        "}"
+        : "=r"(z), "+r"(sw), "+r"(mlo), "+r"(mhi), "+r"(zq), "+r"(zq2)
+        : "r"(m1), "r"(m2), "r"(m3), "r"(bit), "r"(OS), "r"(OM));
+#endif
+    return z;
+}
 
 // v[0] = keys, v[1..4] = payload streams in wire order. Returns an rnsc_status (same in every thread).
 template <int CODEC, int NTH>
@@ -65,6 +108,7 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
 {
     constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
     constexpr bool WIN = (CODEC == RNSC_C4 || CODEC == RNSC_C5);       // register-window fast path
+    constexpr bool ONE_STREAM = (CODEC == RNSC_VBZ || CODEC == RNSC_C1 || CODEC == RNSC_VBZ0);   // scan word A holds c1 alone
     constexpr int KB = TWO ? 2 : 1;
     constexpr int S = U2_SPT;
     const int tid = threadIdx.x;
@@ -77,19 +121,30 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
     const uint32_t nv = n + ph;
     uint32_t run1 = 0, run2 = 0, run3 = 0, carry = 0;
     bool oob = false;
-    int flip = 0;
+    // key bits of the valid samples of this thread in the tile starting at virtual sample tb, at slot positions jlo..
+    auto load_keys = [&](uint32_t tb) -> uint32_t {
+        const uint32_t v0 = tb + (uint32_t)tid * S;
+        const uint32_t vlo = max(v0, ph), vhi = min(v0 + S, nv);
+        if (vhi <= vlo) return 0u;
+        const uint32_t cnt = vhi - vlo;
+        uint32_t kb = load_bits32(keys, KB * (vlo - ph));
+        if (KB * cnt < 32) kb &= (1u << (KB * cnt)) - 1u;
+        return kb << (KB * (vlo - v0));
+    };
+    auto large_mask = [](uint32_t kb) -> uint32_t { return kb & (kb >> 1) & 0x55555555u; };
     __syncthreads();
-    for (uint32_t tb = 0; tb < nv; tb += NTH * S, flip ^= 1) {
+    uint32_t kb_next = nv ? load_keys(0) : 0u, p3 = 0;
+    if (WIN) {   // positions of the first tile's large values (later tiles: piggybacked on the previous tile's second scan)
+        uint32_t tot;
+        p3 = block_scan_1b<NTH>((uint32_t)__popc(large_mask(kb_next)), ws->sb, &tot);
+        run3 = tot;
+    }
+    for (uint32_t tb = 0; tb < nv; tb += NTH * S) {
         const uint32_t v0 = tb + (uint32_t)tid * S;
         const uint32_t vlo = max(v0, ph), vhi = min(v0 + S, nv);
         const uint32_t cnt = vhi > vlo ? vhi - vlo : 0, jlo = cnt ? vlo - v0 : 0;
-        // ---- key bits of my valid samples, at slot positions jlo.. ----
-        uint32_t kb = 0;
-        if (cnt) {
-            kb = load_bits32(keys, KB * (vlo - ph));
-            if (KB * cnt < 32) kb &= (1u << (KB * cnt)) - 1u;
-            kb <<= KB * jlo;
-        }
+        uint32_t kb = kb_next;
+        kb_next = tb + NTH * S < nv ? load_keys(tb + NTH * S) : 0u;
         // ---- unit counts -> stream positions ----
         uint32_t c1 = 0, c2 = 0, c3 = 0, m1 = 0, m2 = 0, m3 = 0;
         if (TWO) {
@@ -103,11 +158,12 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
             else if (CODEC == RNSC_C2) { c1 = cnt; c2 = nl; }
             else { c2 = nl; c1 = cnt - nl; }
         }
-        unsigned long long tot64;
-        const unsigned long long ex64 = block_scan_1b<unsigned long long, NTH>(
-            (unsigned long long)c1 | ((unsigned long long)c2 << 21) | ((unsigned long long)c3 << 42), ws->s64[flip], &tot64);
-        uint32_t p1 = run1 + (uint32_t)(ex64 & 0x1FFFFF), p2 = run2 + (uint32_t)((ex64 >> 21) & 0x1FFFFF), p3 = run3 + (uint32_t)(ex64 >> 42);
-        run1 += (uint32_t)(tot64 & 0x1FFFFF); run2 += (uint32_t)((tot64 >> 21) & 0x1FFFFF); run3 += (uint32_t)(tot64 >> 42);
+        // one word: a thread adds at most 64 units (VBZ0, alone in the word) or 16 + 16 (two halves), a tile at most 2^16 / 2^14
+        uint32_t totA;
+        const uint32_t exA = block_scan_1b<NTH>(ONE_STREAM ? c1 : (c1 | (c2 << 16)), ws->sa, &totA);
+        uint32_t p1, p2;
+        if (ONE_STREAM) { p1 = run1 + exA; p2 = 0; run1 += totA; }
+        else { p1 = run1 + (exA & 0xFFFFu); p2 = run2 + (exA >> 16); run1 += totA & 0xFFFFu; run2 += totA >> 16; }
         // ---- one bounds check per thread instead of one per load (over-reads stay inside the padded buffers) ----
         bool ok;
         if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) ok = p1 + c1 <= l1;
@@ -115,36 +171,44 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
         else if (CODEC == RNSC_C3) ok = p1 + c1 <= l1 && p2 + c2 <= l2 && p2 + c2 <= l3;
         else if (CODEC == RNSC_VBZ0) ok = p1 + c1 <= 2 * l1;
         else ok = p1 + c1 <= 2 * l1 && p2 + c2 <= l2 && p3 + c3 <= l3 && p3 + c3 <= l4;
-        if (!ok) { oob = true; kb = 0; m1 = m2 = m3 = 0; }
+        if (!ok) { oob = true; kb = 0; m1 = m2 = m3 = 0; c3 = 0; }
         // ---- gather, zigzag^-1, thread-local running sum ----
         uint32_t val[S]; uint32_t acc = 0;
         if (WIN) {
+            constexpr uint32_t OL = CODEC == RNSC_C5 ? 273u : 0u;
             uint32_t sw[2] = {0, 0}, mlo[2] = {0, 0}, mhi[2] = {0, 0};
-            uint32_t zq = 0, lused = 0, lbase = 0;       // the next (up to two) large values of this thread, 16 bits each
-            auto load_large = [&](uint32_t k) -> uint32_t {
-                return k < c3 ? ((((uint32_t)ld8(s4 + p3 + k) << 8) + ld8(s3 + p3 + k) + (CODEC == RNSC_C5 ? 273u : 0u)) & 0xFFFFu) : 0u;
-            };
             if (cnt && ok) {
                 const uint32_t n1a = __popc(m1 & 0xFFFFu), n2a = __popc(m2 & 0xFFFFu);
                 sw[0] = load_bits32(s1, 4 * p1); sw[1] = load_bits32(s1, 4 * (p1 + n1a));
                 load_bits64(s2, 8 * p2, mlo[0], mhi[0]); load_bits64(s2, 8 * (p2 + n2a), mlo[1], mhi[1]);
-                if (m3) zq = load_large(0) | (load_large(1) << 16);       // rare (class >= 273): low and high byte streams
             }
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const int h = j >> 3;
-                const bool isS = (m1 >> (2 * j)) & 1u, isM = (m2 >> (2 * j)) & 1u;
-                uint32_t z = 0;
-                if (isS) z = (sw[h] & 15u) + (CODEC == RNSC_C5 ? 1u : 0u);
-                if (isM) z = (mlo[h] & 255u) + (CODEC == RNSC_C5 ? 17u : 0u);
-                if (isS) sw[h] >>= 4;
-                if (isM) { mlo[h] = __funnelshift_r(mlo[h], mhi[h], 8); mhi[h] >>= 8; }
-                if ((m3 >> (2 * j)) & 1u) {
-                    if (lused == 2) { zq = load_large(lbase + 2) | (load_large(lbase + 3) << 16); lbase += 2; lused = 0; }
-                    z = zq & 0xFFFFu; zq >>= 16; ++lused;
+            if (c3 <= 4) {
+                uint32_t zq = 0, zq2 = 0;                  // the (up to four) large values of this thread, 16 bits each
+                if (m3) {
+                    const uint32_t lo4 = load_bits32(s3, 8 * p3), hi4 = load_bits32(s4, 8 * p3);
+                    const uint32_t a = __byte_perm(lo4, hi4, 0x5140), b = __byte_perm(lo4, hi4, 0x7362);
+                    zq = ((a + OL) & 0xFFFFu) | ((a & 0xFFFF0000u) + (OL << 16));         // uint16 arithmetic (C5.hpp:224-228)
+                    zq2 = ((b + OL) & 0xFFFFu) | ((b & 0xFFFF0000u) + (OL << 16));
                 }
-                acc += zz_dec(z);
-                val[j] = acc;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const int h = j >> 3;
+                    const uint32_t z = win_step<CODEC>(1u << (2 * j), m1, m2, m3, sw[h], mlo[h], mhi[h], zq, zq2);
+                    acc += zz_dec(z);
+                    val[j] = acc;
+                }
+            } else {   // a burst of large values: same arithmetic, byte loads
+                uint32_t k3 = p3;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const int h = j >> 3;
+                    uint32_t z = 0;
+                    if ((m1 >> (2 * j)) & 1u) { z = (sw[h] & 15u) + (CODEC == RNSC_C5 ? 1u : 0u); sw[h] >>= 4; }
+                    if ((m2 >> (2 * j)) & 1u) { z = (mlo[h] & 255u) + (CODEC == RNSC_C5 ? 17u : 0u); mlo[h] = __funnelshift_r(mlo[h], mhi[h], 8); mhi[h] >>= 8; }
+                    if ((m3 >> (2 * j)) & 1u) { z = ((ld8(s4 + k3) << 8) + ld8(s3 + k3) + OL) & 0xFFFFu; ++k3; }
+                    acc += zz_dec(z);
+                    val[j] = acc;
+                }
             }
         } else if ((CODEC == RNSC_VBZ || CODEC == RNSC_C1) && cnt == S) {
             // full thread: the (16 .. 32) payload bytes go through four 64-bit register windows, one per 4 samples
@@ -191,11 +255,13 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
                 val[j] = acc;
             }
         }
-        // ---- delta^-1: CTA scan of the per-thread sums (mod 2^16 arithmetic survives in 32 bits) ----
-        uint32_t tot32;
-        const uint32_t ex32 = block_scan_1b<uint32_t, NTH>(acc, ws->s32[flip], &tot32);
-        const uint32_t base = carry + ex32;
-        carry += tot32;
+        // ---- delta^-1: CTA scan of the per-thread sums (mod 2^16, upper half of the word); the lower half scans the
+        //      large-value counts of the next tile ----
+        uint32_t totB;
+        const uint32_t exB = block_scan_1b<NTH>((acc << 16) | (WIN ? (uint32_t)__popc(large_mask(kb_next)) : 0u), ws->sb, &totB);
+        const uint32_t base = carry + (exB >> 16);
+        carry += totB >> 16;
+        if (WIN) { p3 = run3 + (exB & 0xFFFFu); run3 += totB & 0xFFFFu; }
         if (cnt == S) {
             uint32_t w[S / 2];
 #pragma unroll

@@ -68,6 +68,9 @@ inline unsigned __ballot_sync(unsigned mask, int p) {
 inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
 inline int __all_sync(unsigned mask, int p) { unsigned long long all[32]; unsigned arrived = emul::warp_exchange(mask, p ? 1 : 0, all);
     for (int i = 0; i < 32; ++i) if (((arrived >> i) & 1) && !all[i]) return 0; return 1; }
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    unsigned long long all[32]; unsigned arrived = emul::warp_exchange(mask, v, all); unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if ((arrived >> i) & 1) r += (unsigned)all[i]; return r; }
 inline unsigned __activemask() { return 0xffffffffu; }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
