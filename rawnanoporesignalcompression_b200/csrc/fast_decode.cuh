@@ -112,24 +112,49 @@ __device__ __forceinline__ void bits_ending_at(const uint32_t* w, uint32_t A, ui
 
 // One symbol: table entry `ev` = symbol << 8 | code length. The funnel shifts take the entry itself as the shift
 // amount (they use its low 5 bits; a code is at most 12 bits), so the serial chain is peek -> load -> shift.
-#define RNSC_HUF_STEP(hi, lo, tab, L, ev)                                        \
-    do { ev = (tab)[(hi) >> (32 - (L))];                                         \
+// The integer ALU pipe (shifts, logic, 3-input adds) issues at half rate and is what bounds these loops, so the peek
+// and the address go through the multiplier pipe instead: index = mulhi(window, 2^L), address = index * pitch + base,
+// with the pitch (2 bytes) kept as a run-time value so that it stays a multiply-add.
+struct HufTab {
+    const uint16_t* tab; uint32_t L;
+    uint32_t addr, pow, pitch;
+    __device__ __forceinline__ HufTab(const uint16_t* t, uint32_t log, uint32_t pitch_) : tab(t), L(log), pow(1u << log), pitch(pitch_)
+    {
+#ifdef RNSC_EMUL
+        addr = 0;
+#else
+        addr = (uint32_t)__cvta_generic_to_shared(t);
+#endif
+    }
+    __device__ __forceinline__ uint32_t lookup(uint32_t hi) const
+    {
+#ifdef RNSC_EMUL
+        return tab[hi >> (32 - L)];
+#else
+        uint32_t e;
+        asm("{\n.reg .b32 t;\nmul.hi.u32 t, %1, %2;\nmad.lo.u32 t, t, %3, %4;\nld.shared.u16 %0, [t];\n}" : "=r"(e) : "r"(hi), "r"(pow), "r"(pitch), "r"(addr));
+        return e;
+#endif
+    }
+};
+#define RNSC_HUF_STEP(hi, lo, ht, ev)                                            \
+    do { ev = (ht).lookup(hi);                                                   \
          hi = __funnelshift_l(lo, hi, ev); lo = __funnelshift_l(0u, lo, ev); } while (0)
 
 // Advances from consumed-bit position p to the first symbol boundary >= lim; counts the symbols decoded.
-__device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, const uint16_t* tab, uint32_t L, uint32_t& p, uint32_t lim, uint32_t& cnt)
+__device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, const HufTab& tab, uint32_t& p, uint32_t lim, uint32_t& cnt)
 {
     uint32_t hi, lo, e;
     while (p + 4 * HUF_LOG_MAX <= lim) {
         bits_ending_at(words, abit - p, hi, lo);
         uint32_t adv = 0;                           // the low byte sums the four code lengths (<= 48)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { RNSC_HUF_STEP(hi, lo, tab, L, e); adv += e; }
+        for (int k = 0; k < 4; ++k) { RNSC_HUF_STEP(hi, lo, tab, e); adv += e; }
         p += adv & 0xFFu; cnt += 4;
     }
     while (p < lim) {
         bits_ending_at(words, abit - p, hi, lo);
-        RNSC_HUF_STEP(hi, lo, tab, L, e);
+        RNSC_HUF_STEP(hi, lo, tab, e);
         p += e & 0xFFu; cnt += 1;
     }
 }
@@ -149,15 +174,15 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
     const bool active = (uint32_t)tid < hd.st_first[nst];
     const uint32_t t0 = hd.st_first[j], k = (uint32_t)tid - t0;
     const StreamPlan sp = hd.st[j];
-    const uint32_t T = sp.tbits, abit = sp.abit, L = sp.log;
-    const uint16_t* tab = (const uint16_t*)(region + sp.tab_off);
+    const uint32_t T = sp.tbits, abit = sp.abit;
+    const HufTab tab((const uint16_t*)(region + sp.tab_off), sp.log, sp.pitch);
     const uint32_t s0 = k * sub, lim = min(s0 + sub, T);
     uint32_t my_start = 0, my_end = 0, my_cnt = 0;
     if (active) {
         uint32_t p = s0 > FAST_WARM_BITS ? s0 - FAST_WARM_BITS : 0, dummy = 0;
-        huf_walk(words, abit, tab, L, p, s0, dummy);
+        huf_walk(words, abit, tab, p, s0, dummy);
         my_start = p;
-        huf_walk(words, abit, tab, L, p, lim, my_cnt);
+        huf_walk(words, abit, tab, p, lim, my_cnt);
         my_end = p;
     }
     pc.mark(PH_HUF1);
@@ -174,7 +199,7 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
         if (round >= NTH) return 1;                  // cannot happen for a consistent stream: every round fixes at least one more sub-sequence
         if (bad) {
             uint32_t p = want; my_start = p; my_cnt = 0;
-            if (p < lim) huf_walk(words, abit, tab, L, p, lim, my_cnt);
+            if (p < lim) huf_walk(words, abit, tab, p, lim, my_cnt);
             my_end = p;
         }
     }
@@ -204,18 +229,18 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
         }
         if (li + rem <= run_end) {      // all my literals belong to one run (always, without sequences)
             uint8_t* o = region + sp.out + li + shift;
-            while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
+            while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
             while (rem >= 4) {
                 bits_ending_at(words, abit - p, hi, lo);
                 uint32_t word = 0, adv = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    RNSC_HUF_STEP(hi, lo, tab, L, e); adv += e;
+                    RNSC_HUF_STEP(hi, lo, tab, e); adv += e;
                     word = __byte_perm(word, e, q == 0 ? 0x3215u : (q == 1 ? 0x3250u : (q == 2 ? 0x3510u : 0x5210u)));   // byte q <- symbol
                 }
                 *(uint32_t*)o = word; o += 4; p += adv & 0xFFu; rem -= 4;
             }
-            while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, L, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
+            while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
         } else {
             // runs can be a few literals long (the key region of a VBZ frame): one symbol at a time from a buffered
             // 64-bit window, switching the output position whenever a run ends (the next run is fetched ahead)
@@ -224,7 +249,7 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
             int avail = 0;
             while (rem) {
                 if (avail < (int)HUF_LOG_MAX) { bits_ending_at(words, abit - p, hi, lo); avail = 64; }
-                RNSC_HUF_STEP(hi, lo, tab, L, e);
+                RNSC_HUF_STEP(hi, lo, tab, e);
                 p += e & 0xFFu; avail -= (int)(e & 0xFFu);
                 *o++ = (uint8_t)(e >> 8); ++li; --rem;
                 if (li == run_end) {
@@ -442,12 +467,19 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     mbar_wait(&ws->mbar, parity);
     __syncthreads();
     pc.mark(PH_STAGE);
+    // frames with a few sequences over raw / RLE literals: the last warp (which the planner kept free of Huffman
+    // sub-sequences) executes them now, off the critical path
+    if (hd.early && (tid >> 5) == NTH / 32 - 1)
+        for (uint32_t k = 0; k < hd.nsop; ++k)
+            if ((hd.early >> k) & 1u) fast_exec_sequences_ordered(hd.sop[k], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[k].seq_base, region);
     if (hd.nst && fast_huffman<NTH>(ws, region, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
     if (hd.nsop) {
-        if (hd.nseq <= 64) {      // few sequences: one warp per frame, in order
-            const uint32_t w = tid >> 5;
-            if (w < hd.nsop) fast_exec_sequences_ordered(hd.sop[w], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[w].seq_base, region);
-            __syncthreads();
+        if (hd.nseq <= FAST_ORDERED_MAX) {      // few sequences: one warp per remaining frame, in order
+            const uint32_t late = ((1u << hd.nsop) - 1u) & ~hd.early, w = tid >> 5;
+            if (late) {
+                if ((late >> w) & 1u) fast_exec_sequences_ordered(hd.sop[w], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[w].seq_base, region);
+                __syncthreads();
+            }
         } else fast_exec_sequences<NTH>(ws, hd, P.seq_pool, region, P.origin + (size_t)blockIdx.x * P.origin_stride);
     }
     if (tid < 5) { ws->view[tid].p = region + hd.view[tid].off; ws->view[tid].len = hd.view[tid].len; }

@@ -20,6 +20,7 @@ constexpr int PLAN_MAX_STREAMS = 4 * PLAN_MAX_HUF;
 constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
 constexpr uint32_t REGION_HEAD = 16;  // readable bytes in front of the staged chunk (bit-window over-read)
 constexpr uint32_t PLAN_SUB_MIN = 384;   // minimum Huffman sub-sequence length in bits
+constexpr uint32_t FAST_ORDERED_MAX = 64;   // chunks with at most this many sequences run them in order, one warp per frame
 
 enum : uint32_t { FK_RAW = 0, FK_RLE = 1, FK_COMP = 2 };
 // size classes of the fast kernel (threads per CTA x CTAs per SM): S 256x4, A 512x2, B 1024x1; then the general decoder
@@ -48,7 +49,7 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
 // One Huffman bitstream: payload bits, absolute bit address of the end mark in the region, symbols, region offset of
 // the frame's output, literal index of its first symbol, its table; and, when LZ sequences follow, where they are in
 // ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
-struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pad0, pad1, pad2; };   // sop: index of the frame's SeqOp or ~0
+struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pitch, pad1, pad2; };   // sop: index of the frame's SeqOp or ~0; pitch: bytes per table entry
 struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
 // LZ sequences of a frame: entries [seq_base, seq_base + nseq] of the sequence pool. lit = region offset of raw literals or
 // the RLE byte; meta_off = region offset of the run table the kernel copies there: nruns x {first literal index, shift to
@@ -64,7 +65,8 @@ constexpr uint32_t ORIGIN_LIT = 0x80000000u;   // origin word of a matched byte:
 struct PlanHead {                // what the fast kernel copies to shared memory for every chunk
     uint32_t cls, need, phase, stage_bytes;
     uint32_t nhuf, nst, sub, nfill, nsop, nseq;
-    int32_t view_status; uint32_t pad;
+    int32_t view_status;
+    uint32_t early;                // bit k: the sequences of sop[k] (raw / RLE literals) are executed by the CTA's last warp while the others decode Huffman streams
     uint32_t zone_off, zone_len;   // region bytes that are dead after the Huffman stage (the largest bitstream area): match resolver scratch
     uint32_t st_first[PLAN_MAX_STREAMS + 1];
     StreamPlan st[PLAN_MAX_STREAMS];
@@ -380,7 +382,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 sp.count = fp.nstreams == 1 ? fp.regen : (j < 3 ? q : fp.regen - 3 * q);
                 sp.out = fp.dst_off; sp.lit0 = fp.nstreams == 1 ? 0 : j * q;
                 sp.tab_off = pl->h[fp.huf].tab_off; sp.log = pl->h[fp.huf].log;
-                sp.sop = my_sop; sp.regen = fp.regen; sp.pad0 = sp.pad1 = sp.pad2 = 0;
+                sp.sop = my_sop; sp.regen = fp.regen; sp.pitch = 2; sp.pad1 = sp.pad2 = 0;
                 if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }
@@ -400,13 +402,17 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     for (int f = nf; f < 5 && nf > 1; ++f) hd->view[f] = ViewPlan{cbase, 0};
     if (n == 0 && tot_fcs) vst = RNSC_ERR_REMAINING;
     if (slow) { plan_emit(P, c, CLS_SLOW); return; }
-    uint32_t sub = nst ? (ttot + (nth - nst) - 1) / (nth - nst) : PLAN_SUB_MIN;
+    // Frames whose sequences do not wait for Huffman literals (C5: Lhigh) get the last warp to themselves during the Huffman stage
+    uint32_t early = 0;
+    if (nst && nseq_tot <= FAST_ORDERED_MAX) for (uint32_t k = 0; k < nsop; ++k) if (hd->sop[k].ltype != 2) early |= 1u << k;
+    const uint32_t nth_h = early ? nth - 32 : nth;
+    uint32_t sub = nst ? (ttot + (nth_h - nst) - 1) / (nth_h - nst) : PLAN_SUB_MIN;
     if (sub < PLAN_SUB_MIN) sub = PLAN_SUB_MIN;
     uint32_t first = 0;
     for (uint32_t s = 0; s < nst; ++s) { hd->st_first[s] = first; first += (hd->st[s].tbits + sub - 1) / sub; }
     for (uint32_t s = nst; s <= PLAN_MAX_STREAMS; ++s) hd->st_first[s] = first;
     hd->need = region; hd->phase = phase; hd->stage_bytes = stage;
-    hd->nhuf = nhuf; hd->nst = nst; hd->sub = sub; hd->nfill = nfill; hd->nsop = nsop; hd->nseq = nseq_tot; hd->view_status = vst; hd->pad = 0; hd->zone_off = zone_off; hd->zone_len = zone_len;
+    hd->nhuf = nhuf; hd->nst = nst; hd->sub = sub; hd->nfill = nfill; hd->nsop = nsop; hd->nseq = nseq_tot; hd->view_status = vst; hd->early = early; hd->zone_off = zone_off; hd->zone_len = zone_len;
     plan_emit(P, c, cls);
 }
 
