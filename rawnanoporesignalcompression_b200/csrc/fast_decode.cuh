@@ -44,7 +44,6 @@ struct FastWs {
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
     uint32_t nlong, longq[128], long_k[128], long_ms[128], long_ml[128], long_of[128], long_mb[128];   // long matches of the frame being resolved (a warp each)
-    View view[5];
     int status; uint32_t next;
     alignas(8) unsigned long long mbar;
 };
@@ -425,7 +424,7 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const PlanHead& hd, 
     __syncthreads();
 }
 
-// Decodes chunk c into stream views (ws->view) and ws->status. Must be entered by the whole CTA after a barrier.
+// Decodes chunk c: the stream views are ws->head.view (offsets into the region), the result ws->status. Must be entered by the whole CTA after a barrier.
 template <int NTH>
 __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, uint32_t c, uint32_t parity, PhaseClock& pc)
 {
@@ -482,7 +481,6 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
             }
         } else fast_exec_sequences<NTH>(ws, hd, P.seq_pool, region, P.origin + (size_t)blockIdx.x * P.origin_stride);
     }
-    if (tid < 5) { ws->view[tid].p = region + hd.view[tid].off; ws->view[tid].len = hd.view[tid].len; }
     if (tid == 0 && hd.view_status != RNSC_OK) ws->status = hd.view_status;
     __syncthreads();
     pc.mark(PH_SEQ);

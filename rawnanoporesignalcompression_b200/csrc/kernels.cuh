@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NT, 2) k_decode_chunks(DecodeParams p)
 
 // ---------------------------------------------------------------------------------------------------
 // Fast whole-chunk decode of planned chunks (plan.cuh, fast_decode.cuh). Persistent CTAs pull chunk indices of
-// one size class from the planner's list. The dynamic shared memory is [FastWs | region]; the region holds the
+// one size class from the planner's list. The dynamic shared memory is [FastWs | key-byte table (C4/C5) | region]; the region holds the
 // staged compressed chunk and every decoded stream.
 // ---------------------------------------------------------------------------------------------------
 template <int NTH>
@@ -147,9 +147,11 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
 {
     RNSC_DYN_SMEM(smem);
     FastWs<NTH>* ws = (FastWs<NTH>*)smem;
-    uint8_t* region = smem + ((sizeof(FastWs<NTH>) + 15) & ~(size_t)15);
+    KeyLut* lut = (KeyLut*)(smem + ((sizeof(FastWs<NTH>) + 15) & ~(size_t)15));
+    uint8_t* region = (uint8_t*)lut + unpack2_lut_bytes(P.codec);
     const int tid = threadIdx.x;
     if (tid == 0) { mbar_init(&ws->mbar, 1); const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
+    unpack2_init<NTH>(P.codec, lut);
     __syncthreads();
     uint32_t parity = 0;
     PhaseClock pc; pc.start(P.prof);
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
         parity ^= 1u;
         const uint32_t n = P.n[c];
         if (ws->status == RNSC_OK && n > 0) {
-            const int r = unpack2_any<NTH>(P.codec, ws->view, n, P.samples + P.sample_off[c], &ws->u2);
+            const int r = unpack2_any<NTH>(P.codec, region, lut, ws->head.view, n, P.samples + P.sample_off[c], &ws->u2);
             if (r && tid == 0) ws->status = r;
         }
         __syncthreads();

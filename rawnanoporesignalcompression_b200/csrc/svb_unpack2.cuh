@@ -9,15 +9,37 @@
 //   * stream positions and the delta^-1 prefix sum use one-barrier CTA scans of ONE 32-bit word each
 //     (block_scan_1b): the unit counts of two streams share a word, and the count of large values of the
 //     NEXT tile rides in the low half of the word whose high half carries the tile's delta sums (mod 2^16);
-//   * the per-sample step of C4/C5 is predicated code without branches (win_step).
+//   * C4/C5 go four samples at a time: a 256-entry table indexed by the key byte gives the byte-permute selectors that
+//     pull the samples' units out of the stream windows; zigzag^-1 runs on two 16-bit lanes per register.
 // Works on generic pointers; every stream must be readable up to 8 bytes past its end (the fast decoder's
 // region pads each stream with 16 bytes).
 #pragma once
 #include "block_prims.cuh"
+#include "plan.cuh"
 
 namespace rnsc {
 
 constexpr int U2_SPT = 16;
+
+// C4/C5: what one key byte (four 2-bit codes) says about its four samples. x = byte-permute selectors that pull the
+// samples' units out of the next four nibbles (low half) / bytes (high half) of the stream windows, a zero byte for
+// samples of another class; y = bits to drop from the nibble window | bits to drop from the byte window << 8;
+// z, w = the class offsets (C5: 1 / 17 / 0) of samples 0,1 and 2,3 as 16-bit lanes.
+struct alignas(16) KeyLut { uint32_t x, y, z, w; };
+
+template <int CODEC>
+__device__ inline KeyLut make_key_lut(uint32_t kbyte)
+{
+    uint32_t selS = 0, selM = 0, nS = 0, nM = 0, off[4];
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t c = (kbyte >> (2 * j)) & 3u;
+        selS |= (c == 1 ? nS : 4u) << (4 * j);
+        selM |= (c == 2 ? nM : 4u) << (4 * j);
+        off[j] = CODEC == RNSC_C5 ? (c == 1 ? 1u : (c == 2 ? 17u : 0u)) : 0u;
+        nS += c == 1; nM += c == 2;
+    }
+    return KeyLut{selS | (selM << 16), (4 * nS) | ((8 * nM) << 8), off[0] | (off[1] << 16), off[2] | (off[3] << 16)};
+}
 
 template <int NTH>
 struct Unpack2Ws {
@@ -41,19 +63,29 @@ __device__ __forceinline__ uint32_t block_scan_1b(uint32_t v, uint32_t* scratch,
     return base + inc - v;
 }
 
-__device__ __forceinline__ uint32_t ldw(uintptr_t a) { return *(const uint32_t*)a; }
+// Shared-memory byte addresses as plain integers: the streams live in the caller's shared-memory region, and a load
+// through a generic pointer would take the slower generic path.
+#ifdef RNSC_EMUL
+typedef uintptr_t saddr_t;
+__device__ __forceinline__ saddr_t to_saddr(const void* p) { return (uintptr_t)p; }
+__device__ __forceinline__ uint32_t ldw(saddr_t a) { return *(const uint32_t*)a; }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t to_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t ldw(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+#endif
 
-// 32 bits starting at bit `bit` of the byte stream p (any alignment). Reads the two aligned words that cover
-// them: up to 7 bytes past the last byte needed, never below the aligned word holding the first.
-__device__ __forceinline__ uint32_t load_bits32(const uint8_t* p, uint32_t bit)
+// 32 bits starting at bit `bit` of the byte stream at shared address p (any alignment). Reads the two aligned words
+// that cover them: up to 7 bytes past the last byte needed, never below the aligned word holding the first.
+__device__ __forceinline__ uint32_t load_bits32(saddr_t p, uint32_t bit)
 {
-    const uintptr_t a = (uintptr_t)p + (bit >> 3), al = a & ~(uintptr_t)3;
+    const saddr_t a = p + (bit >> 3), al = a & ~(saddr_t)3;
     const uint32_t sh = ((uint32_t)(a & 3) << 3) + (bit & 7);
     return __funnelshift_r(ldw(al), ldw(al + 4), sh);
 }
-__device__ __forceinline__ void load_bits64(const uint8_t* p, uint32_t bit, uint32_t& lo, uint32_t& hi)
+__device__ __forceinline__ void load_bits64(saddr_t p, uint32_t bit, uint32_t& lo, uint32_t& hi)
 {
-    const uintptr_t a = (uintptr_t)p + (bit >> 3), al = a & ~(uintptr_t)3;
+    const saddr_t a = p + (bit >> 3), al = a & ~(saddr_t)3;
     const uint32_t sh = ((uint32_t)(a & 3) << 3) + (bit & 7);
     const uint32_t w0 = ldw(al), w1 = ldw(al + 4), w2 = ldw(al + 8);
     lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
@@ -62,49 +94,11 @@ __device__ __forceinline__ void load_bits64(const uint8_t* p, uint32_t bit, uint
 // sum += zigzag^-1(z) in 32-bit arithmetic (the low 16 bits are what counts): z even -> z/2, z odd -> -(z/2) - 1 = z/2 - z
 __device__ __forceinline__ uint32_t zz_dec(uint32_t z) { return (z >> 1) - (z & 1u) * z; }
 
-// One sample of C4/C5: `bit` = 1 << 2j selects sample j in the class masks m1 (nibble), m2 (byte), m3 (two bytes).
-// Takes the sample's unit from the front of its stream window and returns the zigzag value z. Predicated, no branch:
-// the three classes are rare enough per lane and common enough per warp that a branch would always be taken.
-// zq:zq2 hold the thread's next four large values, offsets already added.
-template <int CODEC>
-__device__ __forceinline__ uint32_t win_step(uint32_t bit, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t& sw, uint32_t& mlo, uint32_t& mhi,
-                                             uint32_t& zq, uint32_t& zq2)
-{
-    constexpr uint32_t OS = CODEC == RNSC_C5 ? 1u : 0u, OM = CODEC == RNSC_C5 ? 17u : 0u;
-    uint32_t z;
-#ifdef RNSC_EMUL
-    z = 0;
-    if (m1 & bit) { z = (sw & 15u) + OS; sw >>= 4; }
-    if (m2 & bit) { z = (mlo & 255u) + OM; mlo = __funnelshift_r(mlo, mhi, 8); mhi >>= 8; }
-    if (m3 & bit) { z = zq & 0xFFFFu; zq = __funnelshift_r(zq, zq2, 16); zq2 >>= 16; }
-#else
-    asm("{\n"
-        ".reg .pred ps, pm, pl;\n"
-        ".reg .b32 t;\n"
-        "and.b32 t, %6, %9;\n setp.ne.u32 ps, t, 0;\n"
-        "and.b32 t, %7, %9;\n setp.ne.u32 pm, t, 0;\n"
-        "and.b32 t, %8, %9;\n setp.ne.u32 pl, t, 0;\n"
-        "mov.u32 %0, 0;\n"
-        "@ps and.b32 %0, %1, 15;\n"
-        "@ps add.u32 %0, %0, %10;\n"
-        "@ps shr.u32 %1, %1, 4;\n"
-        "@pm and.b32 %0, %2, 255;\n"
-        "@pm add.u32 %0, %0, %11;\n"
-        "@pm shf.r.wrap.b32 %2, %2, %3, 8;\n"
-        "@pm shr.u32 %3, %3, 8;\n"
-        "@pl and.b32 %0, %4, 0xffff;\n"
-        "@pl shf.r.wrap.b32 %4, %4, %5, 16;\n"
-        "@pl shr.u32 %5, %5, 16;\n"
-        "}"
-        : "=r"(z), "+r"(sw), "+r"(mlo), "+r"(mhi), "+r"(zq), "+r"(zq2)
-        : "r"(m1), "r"(m2), "r"(m3), "r"(bit), "r"(OS), "r"(OM));
-#endif
-    return z;
-}
-
-// v[0] = keys, v[1..4] = payload streams in wire order. Returns an rnsc_status (same in every thread).
+// Stream k = base[v[k].off .. + v[k].len): v[0] = keys, v[1..4] = payload streams in wire order. `base` is the
+// caller's shared-memory region (passed as base + offsets and inlined so that the loads compile to shared-space loads,
+// not generic ones). Returns an rnsc_status (same in every thread).
 template <int CODEC, int NTH>
-__device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
+__device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lut, const ViewPlan* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
 {
     constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
     constexpr bool WIN = (CODEC == RNSC_C4 || CODEC == RNSC_C5);       // register-window fast path
@@ -113,8 +107,8 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
     constexpr int S = U2_SPT;
     const int tid = threadIdx.x;
     if (tid == 0) ws->err = 0;
-    const uint8_t* keys = v[0].p;
-    const uint8_t *s1 = v[1].p, *s2 = v[2].p, *s3 = v[3].p, *s4 = v[4].p;
+    const uint8_t *s1 = base + v[1].off, *s2 = base + v[2].off, *s3 = base + v[3].off, *s4 = base + v[4].off;
+    const saddr_t a0 = to_saddr(base + v[0].off), a1 = to_saddr(s1), a2 = to_saddr(s2), a3 = to_saddr(s3), a4 = to_saddr(s4);
     const uint32_t l1 = v[1].len, l2 = v[2].len, l3 = v[3].len, l4 = v[4].len;
     const uint32_t ph = (uint32_t)(((uintptr_t)out >> 1) & 7);        // samples past a 16-byte boundary
     int16_t* outa = out - ph;                                          // 16-byte aligned; virtual sample vi <-> outa[vi]
@@ -127,7 +121,7 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
         const uint32_t vlo = max(v0, ph), vhi = min(v0 + S, nv);
         if (vhi <= vlo) return 0u;
         const uint32_t cnt = vhi - vlo;
-        uint32_t kb = load_bits32(keys, KB * (vlo - ph));
+        uint32_t kb = load_bits32(a0, KB * (vlo - ph));
         if (KB * cnt < 32) kb &= (1u << (KB * cnt)) - 1u;
         return kb << (KB * (vlo - v0));
     };
@@ -179,23 +173,45 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
             uint32_t sw[2] = {0, 0}, mlo[2] = {0, 0}, mhi[2] = {0, 0};
             if (cnt && ok) {
                 const uint32_t n1a = __popc(m1 & 0xFFFFu), n2a = __popc(m2 & 0xFFFFu);
-                sw[0] = load_bits32(s1, 4 * p1); sw[1] = load_bits32(s1, 4 * (p1 + n1a));
-                load_bits64(s2, 8 * p2, mlo[0], mhi[0]); load_bits64(s2, 8 * (p2 + n2a), mlo[1], mhi[1]);
+                sw[0] = load_bits32(a1, 4 * p1); sw[1] = load_bits32(a1, 4 * (p1 + n1a));
+                load_bits64(a2, 8 * p2, mlo[0], mhi[0]); load_bits64(a2, 8 * (p2 + n2a), mlo[1], mhi[1]);
             }
             if (c3 <= 4) {
-                uint32_t zq = 0, zq2 = 0;                  // the (up to four) large values of this thread, 16 bits each
-                if (m3) {
-                    const uint32_t lo4 = load_bits32(s3, 8 * p3), hi4 = load_bits32(s4, 8 * p3);
+                // four samples at a time: the key byte's table entry pulls their units out of the windows with two byte
+                // permutes; zigzag^-1 runs on two 16-bit lanes per register
+                uint32_t zp[S / 2];
+#pragma unroll
+                for (int g = 0; g < S / 4; ++g) {
+                    const int h = g >> 1;
+                    const KeyLut e = lut[__byte_perm(kb, 0u, 0x4440u | (uint32_t)g)];
+                    uint32_t x = sw[h] & 0xFFFFu;                                  // next four nibbles -> four bytes
+                    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu;
+                    const uint32_t zb = __byte_perm(x, 0u, e.x) | __byte_perm(mlo[h], 0u, e.x >> 16);
+                    sw[h] = __funnelshift_r(sw[h], 0u, e.y);                       // low 5 bits of e.y: 4 x nibbles used (<= 16)
+                    const uint32_t shm = e.y >> 8;                                 // 8 x bytes used (<= 32)
+                    mlo[h] = __funnelshift_rc(mlo[h], mhi[h], shm); mhi[h] = __funnelshift_rc(mhi[h], 0u, shm);
+                    zp[2 * g] = __byte_perm(zb, 0u, 0x4140u) + e.z;
+                    zp[2 * g + 1] = __byte_perm(zb, 0u, 0x4342u) + e.w;
+                }
+                if (m3) {   // the thread's (up to four) large values: bytes p3.. of the low and high byte streams, patched into their lanes
+                    const uint32_t lo4 = load_bits32(a3, 8 * p3), hi4 = load_bits32(a4, 8 * p3);
                     const uint32_t a = __byte_perm(lo4, hi4, 0x5140), b = __byte_perm(lo4, hi4, 0x7362);
-                    zq = ((a + OL) & 0xFFFFu) | ((a & 0xFFFF0000u) + (OL << 16));         // uint16 arithmetic (C5.hpp:224-228)
-                    zq2 = ((b + OL) & 0xFFFFu) | ((b & 0xFFFF0000u) + (OL << 16));
+                    uint32_t zq = ((a + OL) & 0xFFFFu) | ((a & 0xFFFF0000u) + (OL << 16));         // uint16 arithmetic (C5.hpp:224-228)
+                    uint32_t zq2 = ((b + OL) & 0xFFFFu) | ((b & 0xFFFF0000u) + (OL << 16));
+                    for (uint32_t mm = m3; mm; mm &= mm - 1u) {
+                        const uint32_t j2 = (uint32_t)__ffs((int)mm) - 1u;         // 2 x sample index
+                        const uint32_t pv = (zq & 0xFFFFu) << ((j2 & 2u) << 3), r = j2 >> 2;
+                        zq = __funnelshift_r(zq, zq2, 16); zq2 >>= 16;
+#pragma unroll
+                        for (int q = 0; q < S / 2; ++q) if (r == (uint32_t)q) zp[q] |= pv;
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    const int h = j >> 3;
-                    const uint32_t z = win_step<CODEC>(1u << (2 * j), m1, m2, m3, sw[h], mlo[h], mhi[h], zq, zq2);
-                    acc += zz_dec(z);
-                    val[j] = acc;
+                for (int q = 0; q < S / 2; ++q) {
+                    const uint32_t z = zp[q];
+                    const uint32_t d = ((z >> 1) & 0x7FFF7FFFu) ^ ((z & 0x00010001u) * 0xFFFFu);   // zigzag^-1 of both lanes
+                    acc += d; val[2 * q] = acc;                                    // bits above 16 are don't-care from here on
+                    acc += d >> 16; val[2 * q + 1] = acc;
                 }
             } else {   // a burst of large values: same arithmetic, byte loads
                 uint32_t k3 = p3;
@@ -216,7 +232,7 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
 #pragma unroll
             for (int g = 0; g < S / 4; ++g) {
                 uint32_t wlo, whi;
-                load_bits64(s1, 8 * (p1 + used), wlo, whi);
+                load_bits64(a1, 8 * (p1 + used), wlo, whi);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = 4 * g + jj;
@@ -286,17 +302,28 @@ __device__ int svb_unpack2(const View* v, uint32_t n, int16_t* out, Unpack2Ws<NT
     return ws->err;
 }
 
+// Shared memory the key-byte table of a codec needs in front of the region (only C4 and C5 have one).
+__host__ __device__ inline uint32_t unpack2_lut_bytes(int codec) { return (codec == RNSC_C4 || codec == RNSC_C5) ? 256u * (uint32_t)sizeof(KeyLut) : 0u; }
+
+// Once per CTA, before the first svb_unpack2; followed by a barrier at the caller. `lut` = unpack2_lut_bytes(codec) bytes.
 template <int NTH>
-__device__ inline int unpack2_any(int codec, const View* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
+__device__ inline void unpack2_init(int codec, KeyLut* lut)
+{
+    if (codec != RNSC_C4 && codec != RNSC_C5) return;
+    for (uint32_t i = threadIdx.x; i < 256; i += NTH) lut[i] = codec == RNSC_C5 ? make_key_lut<RNSC_C5>(i) : make_key_lut<RNSC_C4>(i);
+}
+
+template <int NTH>
+__device__ __forceinline__ int unpack2_any(int codec, const uint8_t* base, const KeyLut* lut, const ViewPlan* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
 {
     switch (codec) {
-    case RNSC_VBZ: return svb_unpack2<RNSC_VBZ, NTH>(v, n, out, ws);
-    case RNSC_VBZ0: return svb_unpack2<RNSC_VBZ0, NTH>(v, n, out, ws);
-    case RNSC_C1: return svb_unpack2<RNSC_C1, NTH>(v, n, out, ws);
-    case RNSC_C2: return svb_unpack2<RNSC_C2, NTH>(v, n, out, ws);
-    case RNSC_C3: return svb_unpack2<RNSC_C3, NTH>(v, n, out, ws);
-    case RNSC_C4: return svb_unpack2<RNSC_C4, NTH>(v, n, out, ws);
-    default: return svb_unpack2<RNSC_C5, NTH>(v, n, out, ws);
+    case RNSC_VBZ: return svb_unpack2<RNSC_VBZ, NTH>(base, lut, v, n, out, ws);
+    case RNSC_VBZ0: return svb_unpack2<RNSC_VBZ0, NTH>(base, lut, v, n, out, ws);
+    case RNSC_C1: return svb_unpack2<RNSC_C1, NTH>(base, lut, v, n, out, ws);
+    case RNSC_C2: return svb_unpack2<RNSC_C2, NTH>(base, lut, v, n, out, ws);
+    case RNSC_C3: return svb_unpack2<RNSC_C3, NTH>(base, lut, v, n, out, ws);
+    case RNSC_C4: return svb_unpack2<RNSC_C4, NTH>(base, lut, v, n, out, ws);
+    default: return svb_unpack2<RNSC_C5, NTH>(base, lut, v, n, out, ws);
     }
 }
 

@@ -80,6 +80,7 @@ inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) if (v >> i & 1) r |= 1u << (31 - i); return r; }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { unsigned long long v = ((unsigned long long)hi << 32) | lo; return (unsigned)(v >> (s & 31)); }
+inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned s) { unsigned long long v = ((unsigned long long)hi << 32) | lo; return (unsigned)(v >> (s > 32 ? 32 : s)); }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { unsigned long long v = ((unsigned long long)hi << 32) | lo; return (unsigned)((v << (s & 31)) >> 32); }
 inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) { unsigned long long v = ((unsigned long long)b << 32) | a; unsigned r = 0;
     for (int i = 0; i < 4; ++i) { unsigned sel = (s >> (4 * i)) & 7; r |= (unsigned)((v >> (8 * sel)) & 0xff) << (8 * i); } return r; }
