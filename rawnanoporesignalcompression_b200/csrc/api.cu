@@ -193,7 +193,7 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     // streams and fill SMs as class B CTAs retire. Join before returning to the caller's stream.
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
-    fp.plans = (const ChunkPlan*)c->d_plans.p; fp.seq_pool = (const uint32_t*)c->d_seqpool.p;
+    fp.plans = (const ChunkPlan*)c->d_plans.p; fp.seq_pool = (const uint32_t*)c->d_seqpool.p; fp.nchunks = (uint32_t)nchunks;
     // match resolver scratch: one origin word per matched byte, a matched byte count is below the class's region size
     size_t origin_words[3], origin_base[3], origin_total = 0;
     for (int k = 0; k < 3; ++k) { origin_words[k] = kFastSmem[k]; origin_base[k] = origin_total; origin_total += origin_words[k] * (size_t)c->sm_count * (4 >> k); }

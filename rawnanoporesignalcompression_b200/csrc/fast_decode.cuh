@@ -22,7 +22,7 @@ constexpr uint32_t FAST_NONE = 0xFFFFFFFFu;
 struct FastParams {
     const uint8_t* comp; const uint64_t* comp_off; const uint32_t* n; const uint64_t* sample_off;
     int16_t* samples; int32_t* status; int codec;
-    const ChunkPlan* plans; const uint32_t* list; const uint32_t* count; uint32_t* counter;
+    const ChunkPlan* plans; const uint32_t* list; const uint32_t* count; uint32_t* counter; uint32_t nchunks;
     const uint32_t* seq_pool;    // the planner's sequence pool (SEQ_WORDS words per entry)
     uint32_t* origin; unsigned long long origin_stride;   // per-CTA global scratch (words) of the match resolver
     unsigned long long* prof;    // optional (rnsc_set_profiling): 8 phase cycle counters of this size class, summed over CTAs
@@ -40,6 +40,8 @@ template <int NTH>
 struct FastWs {
     uint32_t sub_end[NTH], sub_inc[NTH];       // end position of each sub-sequence; in-warp inclusive scan of the symbol counts
     uint32_t warp_tot[NTH / 32];
+    uint32_t skip_on;                          // this chunk's Huffman tables have skip tables
+    uint32_t stash_tag;                        // chunk whose plan words wait in the stash (sub_end/sub_inc, idle between two Huffman stages)
     Unpack2Ws<NTH> u2;
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
@@ -101,6 +103,46 @@ __device__ inline void fast_build_table(uint16_t* tab, const HufPlan* hp, int t,
     }
 }
 
+// Skip table of a finished decoding table: entry u = sum of the code lengths | number << 6 of the whole symbols (one
+// or two) that the L-bit peek u determines. A second symbol counts only if its code ends inside the peek: then the
+// bits behind the peek cannot change it. Built in two steps so that no step has a bank-conflicting access pattern
+// of any size: (1) aux: for every code length l in use and every value r of the L - l bits behind such a code, the
+// length of the symbol that r starts with, if it fits (0 otherwise) -- 2^(L-l) entries at offset A - 2^(L-l+1),
+// A = 2^(L-lmin+1); (2) skip[u] from table[u] and aux, four entries per thread and store.
+__device__ __forceinline__ uint32_t huf_min_len(const HufPlan* hp)
+{
+    uint32_t w = hp->log;
+    while (w > 1 && hp->cls_start[w] >= hp->cls_start[w + 1]) --w;      // heaviest weight class in use
+    return hp->log + 1 - w;
+}
+__device__ __forceinline__ uint32_t skip_aux_bytes(uint32_t L, uint32_t lmin) { return 2u << (L - lmin); }
+__device__ __forceinline__ void fast_build_aux(uint8_t* aux, const uint16_t* tab, uint32_t L, uint32_t lmin, int t, int nthr)
+{
+    const uint32_t A = skip_aux_bytes(L, lmin);
+    for (uint32_t idx = (uint32_t)t; idx + 1 < A; idx += (uint32_t)nthr) {
+        const uint32_t k = 31u - (uint32_t)__clz((int)(A - idx - 1u));   // bits behind the first code
+        const uint32_t l = L - k, r = idx - (A - (2u << k));
+        const uint32_t len = tab[r << l] & 0xFFu;
+        aux[idx] = (uint8_t)(len <= k ? len : 0u);
+    }
+}
+__device__ __forceinline__ void fast_build_skip(uint8_t* skip, const uint8_t* aux, const uint16_t* tab, uint32_t L, uint32_t lmin, int t, int nthr)
+{
+    const uint32_t size = 1u << L, A = skip_aux_bytes(L, lmin);
+    for (uint32_t u0 = (uint32_t)t * 4; u0 < size; u0 += (uint32_t)nthr * 4) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t u = (u0 + q) & (size - 1u);
+            const uint32_t l1 = tab[u] & 0xFFu, k = L - l1;
+            const uint32_t a = aux[A - (2u << k) + (u & ((1u << k) - 1u))];
+            w |= ((l1 + a) | (a ? 0x80u : 0x40u)) << (8 * q);
+        }
+        if (size >= 4) *(uint32_t*)(skip + u0) = w;
+        else for (uint32_t q = 0; q < size; ++q) skip[q] = (uint8_t)(w >> (8 * q));
+    }
+}
+
 // 64 bits of a backward bitstream ending (exclusive) at absolute bit address A of the word array w, left aligned.
 __device__ __forceinline__ void bits_ending_at(const uint32_t* w, uint32_t A, uint32_t& hi, uint32_t& lo)
 {
@@ -115,14 +157,25 @@ __device__ __forceinline__ void bits_ending_at(const uint32_t* w, uint32_t A, ui
 // and the address go through the multiplier pipe instead: index = mulhi(window, 2^L), address = index * pitch + base,
 // with the pitch (2 bytes) kept as a run-time value so that it stays a multiply-add.
 struct HufTab {
-    const uint16_t* tab; uint32_t L;
-    uint32_t addr, pow, pitch;
-    __device__ __forceinline__ HufTab(const uint16_t* t, uint32_t log, uint32_t pitch_) : tab(t), L(log), pow(1u << log), pitch(pitch_)
+    const uint16_t* tab; const uint8_t* skip; uint32_t L;
+    uint32_t addr, saddr, pow, pitch;
+    __device__ __forceinline__ HufTab(const uint16_t* t, const uint8_t* sk, uint32_t log, uint32_t pitch_) : tab(t), skip(sk), L(log), pow(1u << log), pitch(pitch_)
     {
 #ifdef RNSC_EMUL
-        addr = 0;
+        addr = 0; saddr = 0;
 #else
-        addr = (uint32_t)__cvta_generic_to_shared(t);
+        addr = (uint32_t)__cvta_generic_to_shared(t); saddr = (uint32_t)__cvta_generic_to_shared(sk);
+#endif
+    }
+    // skip table: the same peek -> code length sum | symbol count << 6 of the (one or two) whole symbols inside the peek
+    __device__ __forceinline__ uint32_t lookup_skip(uint32_t hi) const
+    {
+#ifdef RNSC_EMUL
+        return skip[hi >> (32 - L)];
+#else
+        uint32_t e;
+        asm("{\n.reg .b32 t;\nmul.hi.u32 t, %1, %2;\nadd.u32 t, t, %3;\nld.shared.u8 %0, [t];\n}" : "=r"(e) : "r"(hi), "r"(pow), "r"(saddr));
+        return e;
 #endif
     }
     __device__ __forceinline__ uint32_t lookup(uint32_t hi) const
@@ -140,16 +193,27 @@ struct HufTab {
     do { ev = (ht).lookup(hi);                                                   \
          hi = __funnelshift_l(lo, hi, ev); lo = __funnelshift_l(0u, lo, ev); } while (0)
 
-// Advances from consumed-bit position p to the first symbol boundary >= lim; counts the symbols decoded.
+// Advances from consumed-bit position p to the first symbol boundary >= lim; counts the symbols decoded. Nothing is
+// written, so while the limit is far the walk strides over up to two symbols per table access (the skip table).
 __device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, const HufTab& tab, uint32_t& p, uint32_t lim, uint32_t& cnt)
 {
     uint32_t hi, lo, e;
-    while (p + 4 * HUF_LOG_MAX <= lim) {
-        bits_ending_at(words, abit - p, hi, lo);
-        uint32_t adv = 0;                           // the low byte sums the four code lengths (<= 48)
+    if (tab.skip) {
+        while (p + 4 * HUF_LOG_MAX <= lim) {
+            bits_ending_at(words, abit - p, hi, lo);
+            uint32_t sum = 0;                       // bits 0-5: the four length sums (<= 48); above: the symbol counts
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { RNSC_HUF_STEP(hi, lo, tab, e); adv += e; }
-        p += adv & 0xFFu; cnt += 4;
+            for (int k = 0; k < 4; ++k) { e = tab.lookup_skip(hi); hi = __funnelshift_l(lo, hi, e); lo = __funnelshift_l(0u, lo, e); sum += e; }
+            p += sum & 63u; cnt += sum >> 6;
+        }
+    } else {
+        while (p + 4 * HUF_LOG_MAX <= lim) {
+            bits_ending_at(words, abit - p, hi, lo);
+            uint32_t adv = 0;                       // the low byte sums the four code lengths (<= 48)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { RNSC_HUF_STEP(hi, lo, tab, e); adv += e; }
+            p += adv & 0xFFu; cnt += 4;
+        }
     }
     while (p < lim) {
         bits_ending_at(words, abit - p, hi, lo);
@@ -158,10 +222,22 @@ __device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, c
     }
 }
 
+// Plan prefetch: the words the next chunk's start needs (plan head, Huffman table recipes, offset of its compressed
+// bytes) are fetched from global memory during this chunk's Huffman stage and parked in the sub-sequence arrays, so
+// that a chunk does not begin with a chain of dependent global loads.
+constexpr uint32_t ST_HEAD_W = sizeof(PlanHead) / 4, ST_HUF_W = PLAN_MAX_HUF * sizeof(HufPlan) / 4, ST_WORDS = ST_HEAD_W + ST_HUF_W + 2;
+static_assert(ST_WORDS <= 2 * 256, "the stash must fit the smallest CTA's sub-sequence arrays");
+__device__ __forceinline__ uint32_t stash_fetch(const FastParams& P, uint32_t c, uint32_t idx)
+{
+    if (idx < ST_HEAD_W) return ((const uint32_t*)&P.plans[c].head)[idx];
+    if (idx < ST_HEAD_W + ST_HUF_W) return ((const uint32_t*)P.plans[c].h)[idx - ST_HEAD_W];
+    return ((const uint32_t*)(P.comp_off + c))[idx - ST_HEAD_W - ST_HUF_W];
+}
+
 // Decodes every Huffman stream of the chunk (ws->head.st[]) from the staged chunk into the region. Three barriers
 // in the common case. Returns 0 on success (same value in all threads).
 template <int NTH>
-__device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock& pc)
+__device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, PhaseClock& pc)
 {
     constexpr int NW = NTH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -174,7 +250,7 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
     const uint32_t t0 = hd.st_first[j], k = (uint32_t)tid - t0;
     const StreamPlan sp = hd.st[j];
     const uint32_t T = sp.tbits, abit = sp.abit;
-    const HufTab tab((const uint16_t*)(region + sp.tab_off), sp.log, sp.pitch);
+    const HufTab tab((const uint16_t*)(region + sp.tab_off), ws->skip_on ? region + sp.skip_off : nullptr, sp.log, sp.pitch);
     const uint32_t s0 = k * sub, lim = min(s0 + sub, T);
     uint32_t my_start = 0, my_end = 0, my_cnt = 0;
     if (active) {
@@ -185,6 +261,12 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
         my_end = p;
     }
     pc.mark(PH_HUF1);
+    // next chunk's plan words: requested now, parked after the second pass
+    constexpr int PF = (ST_WORDS + NTH - 1) / NTH;
+    uint32_t pf[PF];
+    const uint32_t nx = ws->next;
+#pragma unroll
+    for (int q = 0; q < PF; ++q) { const uint32_t idx = (uint32_t)tid + (uint32_t)q * NTH; pf[q] = (nx != FAST_NONE && idx < ST_WORDS) ? stash_fetch(P, nx, idx) : 0u; }
     uint32_t inc;
     for (int round = 0;; ++round) {
         inc = warp_inclusive_scan(active ? my_cnt : 0u);
@@ -260,6 +342,11 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, PhaseClock&
         }
     }
     const int r = __syncthreads_or(bad);
+    if (nx != FAST_NONE) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) { const uint32_t idx = (uint32_t)tid + (uint32_t)q * NTH; if (idx < ST_WORDS) ws->sub_end[idx] = pf[q]; }   // sub_end and sub_inc are contiguous
+        if (tid == 0) ws->stash_tag = nx;
+    }
     pc.mark(PH_HUF2);
     return r;
 }
@@ -431,21 +518,25 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     const int tid = threadIdx.x;
     const ChunkPlan* pl = P.plans + c;
     // ---- stage the compressed chunk (async) while the plan is copied and the tables are built ----
+    const bool parked = ws->stash_tag == c;          // the previous chunk's Huffman stage fetched this chunk's plan
+    const uint32_t* stash = ws->sub_end;
+    const PlanHead* hsrc = parked ? (const PlanHead*)stash : &pl->head;
     if (tid == 0) {
-        const uint8_t* gsrc = P.comp + P.comp_off[c];
+        const unsigned long long coff = parked ? ((unsigned long long)stash[ST_WORDS - 1] << 32 | stash[ST_WORDS - 2]) : P.comp_off[c];
+        const uint8_t* gsrc = P.comp + coff;
         const uint32_t phase = (uint32_t)((uintptr_t)gsrc & 15u);
         ws->status = RNSC_OK;
-        bulk_load(region + REGION_HEAD, gsrc - phase, pl->head.stage_bytes, &ws->mbar);
+        bulk_load(region + REGION_HEAD, gsrc - phase, hsrc->stage_bytes, &ws->mbar);
     }
     {
-        const uint32_t* s = (const uint32_t*)&pl->head; uint32_t* d = (uint32_t*)&ws->head;
+        const uint32_t* s = (const uint32_t*)hsrc; uint32_t* d = (uint32_t*)&ws->head;
         for (uint32_t i = tid; i < sizeof(PlanHead) / 4; i += NTH) d[i] = s[i];
-        const uint32_t nhuf = pl->head.nhuf;
-        s = (const uint32_t*)pl->h; d = (uint32_t*)ws->h;
+        const uint32_t nhuf = hsrc->nhuf;
+        s = parked ? stash + ST_HEAD_W : (const uint32_t*)pl->h; d = (uint32_t*)ws->h;
         for (uint32_t i = tid; i < (uint32_t)sizeof(HufPlan) / 4 * nhuf; i += NTH) d[i] = s[i];
         // run tables of the frames with sequences: {first literal index, shift} of every non-empty literal run
-        for (uint32_t k = 0; k < pl->head.nsop; ++k) {
-            const SeqOp op = pl->head.sop[k];
+        for (uint32_t k = 0; k < hsrc->nsop; ++k) {
+            const SeqOp op = hsrc->sop[k];
             const uint32_t* g = P.seq_pool + (size_t)SEQ_WORDS * op.seq_base;
             uint2* run = (uint2*)(region + op.meta_off);
             for (uint32_t i = tid; i < op.nruns; i += NTH) run[i] = make_uint2(g[SEQ_WORDS * i + 6], g[SEQ_WORDS * i + 7]);
@@ -460,6 +551,22 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
         if (nhuf) {
             const int per = NTH / (int)nhuf, t = tid / per;
             if (t < (int)nhuf) fast_build_table((uint16_t*)(region + ws->h[t].tab_off), &ws->h[t], tid - t * per, per);
+            // skip tables (all tables of a chunk have room for one, or none has); the scratch of the build lives in the
+            // sub-sequence arrays, which the Huffman stage only uses later
+            bool skip_on = ws->h[0].skip_off != 0;
+            const uint32_t aux_cap = ((uint32_t)sizeof(ws->sub_end) + (uint32_t)sizeof(ws->sub_inc)) / nhuf & ~15u;
+            for (uint32_t h = 0; h < nhuf; ++h) if (skip_aux_bytes(ws->h[h].log, huf_min_len(&ws->h[h])) > aux_cap) skip_on = false;
+            if (tid == 0) ws->skip_on = skip_on;
+            if (skip_on) {
+                uint8_t* aux = (uint8_t*)ws->sub_end + (size_t)aux_cap * (t < (int)nhuf ? t : 0);
+                const HufPlan* hp = &ws->h[t < (int)nhuf ? t : 0];
+                const uint16_t* tb = (const uint16_t*)(region + hp->tab_off);
+                const uint32_t lmin = huf_min_len(hp);
+                __syncthreads();
+                if (t < (int)nhuf) fast_build_aux(aux, tb, hp->log, lmin, tid - t * per, per);
+                __syncthreads();
+                if (t < (int)nhuf) fast_build_skip(region + hp->skip_off, aux, tb, hp->log, lmin, tid - t * per, per);
+            }
         }
     }
     for (uint32_t i = 0; i < hd.nfill; ++i) { uint8_t* d = region + hd.fill[i].dst_off; for (uint32_t q = tid; q < hd.fill[i].len; q += NTH) d[q] = (uint8_t)hd.fill[i].value; }
@@ -471,7 +578,7 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     if (hd.early && (tid >> 5) == NTH / 32 - 1)
         for (uint32_t k = 0; k < hd.nsop; ++k)
             if ((hd.early >> k) & 1u) fast_exec_sequences_ordered(hd.sop[k], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[k].seq_base, region);
-    if (hd.nst && fast_huffman<NTH>(ws, region, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
+    if (hd.nst && fast_huffman<NTH>(ws, region, P, pc)) { if (tid == 0) ws->status = RNSC_ERR_ZSTD_DECODE; __syncthreads(); return; }
     if (hd.nsop) {
         if (hd.nseq <= FAST_ORDERED_MAX) {      // few sequences: one warp per remaining frame, in order
             const uint32_t late = ((1u << hd.nsop) - 1u) & ~hd.early, w = tid >> 5;

@@ -42,6 +42,7 @@ struct FramePlan {               // planner-internal description of one frame
 struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decoding table
     uint32_t log;                // table log (max code length), <= 12
     uint32_t tab_off;            // region offset of the table (2^log entries of 2 bytes)
+    uint32_t skip_off;           // region offset of its skip table (2^log bytes), 0 = none (it would push the chunk into a bigger size class)
     uint16_t cls_start[14];      // first table entry of weight class w (1..log); cls_start[log+1] = 2^log
     uint16_t cls_sym[14];        // index into sorted[] of the first symbol of class w
     uint8_t sorted[256];         // symbols of weight > 0 ordered by (weight, symbol)
@@ -49,7 +50,7 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
 // One Huffman bitstream: payload bits, absolute bit address of the end mark in the region, symbols, region offset of
 // the frame's output, literal index of its first symbol, its table; and, when LZ sequences follow, where they are in
 // ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
-struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pitch, pad1, pad2; };   // sop: index of the frame's SeqOp or ~0; pitch: bytes per table entry
+struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pitch, skip_off, pad2; };   // sop: index of the frame's SeqOp or ~0; pitch: bytes per table entry
 struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
 // LZ sequences of a frame: entries [seq_base, seq_base + nseq] of the sequence pool. lit = region offset of raw literals or
 // the RLE byte; meta_off = region offset of the run table the kernel copies there: nruns x {first literal index, shift to
@@ -99,6 +100,8 @@ struct PlanScratch {
 static_assert(sizeof(PlanScratch) == 900, "PlanScratch layout");
 
 __host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+__host__ __device__ inline uint32_t huf_tab_bytes(uint32_t log) { return align16(2u << log); }
+__host__ __device__ inline uint32_t huf_skip_bytes(uint32_t log) { return align16(1u << log); }
 __host__ __device__ inline uint32_t seq_meta_bytes(uint32_t nseq) { return align16((nseq + 1) * 8); }
 
 // Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
@@ -352,12 +355,17 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     if (st != RNSC_OK) { P.status[c] = st; plan_emit(P, c, CLS_DONE); return; }
     if (slow) { plan_emit(P, c, CLS_SLOW); return; }
     // ---- Huffman tables live in the region too ----
-    for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].tab_off = region; region += align16(2u << pl->h[h].log); }
+    for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].tab_off = region; pl->h[h].skip_off = 0; region += huf_tab_bytes(pl->h[h].log); }
     uint32_t meta = region;                                      // run tables of the frames with sequences
     for (int f = 0; f < nf; ++f) { const FramePlan& q = pl->f[f]; if (q.kind == FK_COMP && q.nseq) region += seq_meta_bytes(q.nseq); }
     if (slow) { plan_emit(P, c, CLS_SLOW); return; }
     const uint32_t cls = region <= P.region[0] ? CLS_S : (region <= P.region[1] ? CLS_A : (region <= P.region[2] ? CLS_B : CLS_SLOW));
     if (cls == CLS_SLOW) { plan_emit(P, c, CLS_SLOW); return; }
+    {   // skip tables (pass 1 strides over several symbols per access) go behind everything else, if the class has room for them
+        uint32_t r2 = region;
+        for (uint32_t h = 0; h < nhuf; ++h) r2 += huf_skip_bytes(pl->h[h].log);
+        if (r2 <= P.region[cls]) for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].skip_off = region; region += huf_skip_bytes(pl->h[h].log); }
+    }
     const uint32_t nth = class_threads(cls);
     // ---- the kernel's program: Huffman streams, fills, sequence ops, views ----
     uint32_t nst = 0, ttot = 0, nfill = 0, nsop = 0, zone_off = 0, zone_len = 0;
@@ -381,8 +389,8 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 sp.tbits = fp.s_tbits[j]; sp.abit = 8 * (cbase + fp.s_beg[j]) + fp.s_tbits[j];
                 sp.count = fp.nstreams == 1 ? fp.regen : (j < 3 ? q : fp.regen - 3 * q);
                 sp.out = fp.dst_off; sp.lit0 = fp.nstreams == 1 ? 0 : j * q;
-                sp.tab_off = pl->h[fp.huf].tab_off; sp.log = pl->h[fp.huf].log;
-                sp.sop = my_sop; sp.regen = fp.regen; sp.pitch = 2; sp.pad1 = sp.pad2 = 0;
+                sp.tab_off = pl->h[fp.huf].tab_off; sp.skip_off = pl->h[fp.huf].skip_off; sp.log = pl->h[fp.huf].log;
+                sp.sop = my_sop; sp.regen = fp.regen; sp.pitch = 2; sp.pad2 = 0;
                 if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }

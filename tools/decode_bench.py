@@ -25,9 +25,11 @@ if '--phases' in sys.argv:
     for cls,ph in cd.phase_cycles().items():
         k=max(1,ph['chunks']); print(cls, ph['chunks']//3, {a:int(b/k) for a,b in ph.items() if a!='chunks'})
     cd.set_profiling(False)
-e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(3): step()
-e1.record(); torch.cuda.synchronize()
-ms=e0.elapsed_time(e1)/3
-print(f"codec {codec}: {2e-6*sig.numel()/ms:.1f} GB/s, {ms:.3f} ms, routing {cd.decode_class_counts()}, bits/sample {8*coff[-1]/sig.numel():.3f}")
+N=20
+ev=[torch.cuda.Event(enable_timing=True) for _ in range(N+1)]
+ev[0].record()
+for i in range(N): step(); ev[i+1].record()
+torch.cuda.synchronize()
+ts=sorted(ev[i].elapsed_time(ev[i+1]) for i in range(N))
+ms=ts[N//2]
+print(f"codec {codec}: {2e-6*sig.numel()/ms:.1f} GB/s median ({2e-6*sig.numel()/ts[0]:.1f} best), {ms:.3f} ms, routing {cd.decode_class_counts()}, bits/sample {8*coff[-1]/sig.numel():.3f}")
