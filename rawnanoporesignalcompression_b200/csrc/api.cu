@@ -150,7 +150,8 @@ struct rnsc_ctx {
     Lane lane[2];
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
-    cudaEvent_t ev_plan = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t hi = nullptr;                             // high priority: the general decoder must get its SMs before the persistent CTAs fill them (see launch_decode)
+    cudaEvent_t ev_plan = nullptr, ev_hi = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
     PinBuf h_a, h_b;
 };
 
@@ -200,22 +201,29 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     if (c->d_origin.reserve(origin_total * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(origin scratch) failed");
     auto set_class = [&](uint32_t cls) { fp.list = (const uint32_t*)c->d_lists.p + (size_t)cls * nchunks; fp.count = cnt + cls; fp.counter = cnt + 8 + cls;
                                          fp.origin = (uint32_t*)c->d_origin.p + origin_base[cls]; fp.origin_stride = origin_words[cls];
-                                         fp.prof = c->profiling ? (unsigned long long*)c->d_prof.p + 8 * cls : nullptr; };
+                                         fp.prof = c->profiling ? (unsigned long long*)c->d_prof.p + 8 * cls : nullptr;
+                                         fp.span = c->profiling ? (unsigned long long*)c->d_prof.p + 24 + 3 * 1024 * cls : nullptr; };
     CUDA_OK(cudaEventRecord(c->ev_plan, st));
-    for (int k = 0; k < 3; ++k) CUDA_OK(cudaStreamWaitEvent(c->side[k], c->ev_plan, 0));
+    for (int k = 0; k < 2; ++k) CUDA_OK(cudaStreamWaitEvent(c->side[k], c->ev_plan, 0));
+    CUDA_OK(cudaStreamWaitEvent(c->hi, c->ev_plan, 0));
+    // The general decoder goes FIRST and on the high-priority stream: it usually has a handful of chunks, but every SM is
+    // about to be filled with persistent CTAs of the fast kernel that stay until their lists run dry -- launched behind
+    // them it would start when everything else is over and add its whole run time to the call.
+    DecodeParams p;
+    p.comp = d_comp; p.comp_off = d_comp_off; p.n = d_n; p.sample_off = d_sample_off; p.samples = d_samples; p.status = d_status;
+    p.nchunks = (uint32_t)nchunks; p.codec = codec; p.scratch = (uint8_t*)c->d_scratch.p; p.scratch_stride = stride;
+    p.counter = cnt + 8 + CLS_SLOW; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
+    p.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_SLOW * nchunks; p.count = cnt + CLS_SLOW;
+    RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, c->hi, p);
+    CUDA_OK(cudaEventRecord(c->ev_hi, c->hi));
     set_class(CLS_B);
     RNSC_LAUNCH(k_decode_fast<1024>, (int)std::min<size_t>((size_t)c->sm_count, nchunks), 1024, kFastSmem[2], st, fp);
     set_class(CLS_A);
     RNSC_LAUNCH(k_decode_fast<512>, (int)std::min<size_t>((size_t)c->sm_count * 2, nchunks), 512, kFastSmem[1], c->side[0], fp);
     set_class(CLS_S);
     RNSC_LAUNCH(k_decode_fast<256>, (int)std::min<size_t>((size_t)c->sm_count * 4, nchunks), 256, kFastSmem[0], c->side[1], fp);
-    DecodeParams p;
-    p.comp = d_comp; p.comp_off = d_comp_off; p.n = d_n; p.sample_off = d_sample_off; p.samples = d_samples; p.status = d_status;
-    p.nchunks = (uint32_t)nchunks; p.codec = codec; p.scratch = (uint8_t*)c->d_scratch.p; p.scratch_stride = stride;
-    p.counter = cnt + 8 + CLS_SLOW; p.arena_bytes = (uint32_t)decode_arena_bytes(); p.spill_bytes = (uint32_t)spill;
-    p.list = (const uint32_t*)c->d_lists.p + (size_t)CLS_SLOW * nchunks; p.count = cnt + CLS_SLOW;
-    RNSC_LAUNCH(k_decode_chunks, grid, NT, kDecodeSmem, c->side[2], p);
-    for (int k = 0; k < 3; ++k) { CUDA_OK(cudaEventRecord(c->ev_side[k], c->side[k])); CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[k], 0)); }
+    for (int k = 0; k < 2; ++k) { CUDA_OK(cudaEventRecord(c->ev_side[k], c->side[k])); CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[k], 0)); }
+    CUDA_OK(cudaStreamWaitEvent(st, c->ev_hi, 0));
     c->launches += 5;
     CUDA_OK(cudaGetLastError());
     return RNSC_OK;
@@ -285,6 +293,11 @@ rnsc_ctx* rnsc_create(int device)
     if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
     bool ok = cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < 3 && ok; ++k) ok = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&c->ev_side[k], cudaEventDisableTiming) == cudaSuccess;
+    {
+        int least = 0, greatest = 0;
+        ok = ok && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess
+                && cudaStreamCreateWithPriority(&c->hi, cudaStreamNonBlocking, greatest) == cudaSuccess && cudaEventCreateWithFlags(&c->ev_hi, cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) ok = cudaEventCreateWithFlags(&c->lane[k].ev_in, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->lane[k].ev_dec, cudaEventDisableTiming) == cudaSuccess &&
                                            cudaEventCreateWithFlags(&c->lane[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
@@ -297,6 +310,12 @@ rnsc_ctx* rnsc_create(int device)
     if (e1 == cudaSuccess) e1 = e3;
     e3 = cudaFuncSetAttribute(k_decode_fast<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[0]);
     if (e1 == cudaSuccess) e1 = e3;
+    // one shared-memory carveout for every decode kernel: kernels that ask for different L1/shared splits cannot share an SM,
+    // and an SM has to drain before it switches
+    for (const void* f : {(const void*)k_decode_fast<1024>, (const void*)k_decode_fast<512>, (const void*)k_decode_fast<256>, (const void*)k_decode_chunks, (const void*)k_plan_chunks}) {
+        e3 = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e1 == cudaSuccess) e1 = e3;
+    }
     if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return nullptr; }
     uint32_t deftab[160];
     host_default_tables(deftab);
@@ -315,6 +334,7 @@ void rnsc_destroy(rnsc_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin}) b->release();
     c->h_a.release(); c->h_b.release();
+    if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); } if (c->ev_hi) cudaEventDestroy(c->ev_hi);
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);
     for (int k = 0; k < 2; ++k) {
@@ -368,11 +388,12 @@ int rnsc_set_profiling(rnsc_ctx* c, int on)
 {
     if (!c) return fail(RNSC_ERR_BAD_ARG, "rnsc_set_profiling: bad argument");
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
-    if (on) { if (c->d_prof.reserve(24 * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(prof) failed"); CUDA_OK(cudaMemset(c->d_prof.p, 0, 24 * 8)); }
+    if (on) { if (c->d_prof.reserve(24 * 8 + 3 * 3 * 1024 * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(prof) failed"); CUDA_OK(cudaMemset(c->d_prof.p, 0, 24 * 8 + 3 * 3 * 1024 * 8)); }
     c->profiling = on != 0;
     return RNSC_OK;
 }
 
+int rnsc_debug_spans(rnsc_ctx* c, unsigned long long* out) { cudaDeviceSynchronize(); return cudaMemcpy(out, (unsigned long long*)c->d_prof.p + 24, 3 * 3 * 1024 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1; }
 int rnsc_get_phase_cycles(rnsc_ctx* c, uint64_t out[24])
 {
     if (!c || !out) return fail(RNSC_ERR_BAD_ARG, "rnsc_get_phase_cycles: bad argument");

@@ -25,6 +25,7 @@ struct FastParams {
     const ChunkPlan* plans; const uint32_t* list; const uint32_t* count; uint32_t* counter; uint32_t nchunks;
     const uint32_t* seq_pool;    // the planner's sequence pool (SEQ_WORDS words per entry)
     uint32_t* origin; unsigned long long origin_stride;   // per-CTA global scratch (words) of the match resolver
+    unsigned long long* span;    // debug
     unsigned long long* prof;    // optional (rnsc_set_profiling): 8 phase cycle counters of this size class, summed over CTAs
 };
 
@@ -47,6 +48,7 @@ struct FastWs {
     HufPlan h[PLAN_MAX_HUF];
     uint32_t nlong, longq[128], long_k[128], long_ms[128], long_ml[128], long_of[128], long_mb[128];   // long matches of the frame being resolved (a warp each)
     int status; uint32_t next;
+    uint32_t n; unsigned long long sample_off;   // the chunk's sample count and offset in the output
     alignas(8) unsigned long long mbar;
 };
 
@@ -225,13 +227,16 @@ __device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, c
 // Plan prefetch: the words the next chunk's start needs (plan head, Huffman table recipes, offset of its compressed
 // bytes) are fetched from global memory during this chunk's Huffman stage and parked in the sub-sequence arrays, so
 // that a chunk does not begin with a chain of dependent global loads.
-constexpr uint32_t ST_HEAD_W = sizeof(PlanHead) / 4, ST_HUF_W = PLAN_MAX_HUF * sizeof(HufPlan) / 4, ST_WORDS = ST_HEAD_W + ST_HUF_W + 2;
+constexpr uint32_t ST_HEAD_W = sizeof(PlanHead) / 4, ST_HUF_W = PLAN_MAX_HUF * sizeof(HufPlan) / 4;
+constexpr uint32_t ST_COFF = ST_HEAD_W + ST_HUF_W, ST_SOFF = ST_COFF + 2, ST_N = ST_SOFF + 2, ST_WORDS = ST_N + 1;   // + compressed offset, sample offset, sample count
 static_assert(ST_WORDS <= 2 * 256, "the stash must fit the smallest CTA's sub-sequence arrays");
 __device__ __forceinline__ uint32_t stash_fetch(const FastParams& P, uint32_t c, uint32_t idx)
 {
     if (idx < ST_HEAD_W) return ((const uint32_t*)&P.plans[c].head)[idx];
     if (idx < ST_HEAD_W + ST_HUF_W) return ((const uint32_t*)P.plans[c].h)[idx - ST_HEAD_W];
-    return ((const uint32_t*)(P.comp_off + c))[idx - ST_HEAD_W - ST_HUF_W];
+    if (idx < ST_SOFF) return ((const uint32_t*)(P.comp_off + c))[idx - ST_COFF];
+    if (idx < ST_N) return ((const uint32_t*)(P.sample_off + c))[idx - ST_SOFF];
+    return P.n[c];
 }
 
 // Decodes every Huffman stream of the chunk (ws->head.st[]) from the staged chunk into the region. Three barriers
@@ -522,11 +527,15 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     const uint32_t* stash = ws->sub_end;
     const PlanHead* hsrc = parked ? (const PlanHead*)stash : &pl->head;
     if (tid == 0) {
-        const unsigned long long coff = parked ? ((unsigned long long)stash[ST_WORDS - 1] << 32 | stash[ST_WORDS - 2]) : P.comp_off[c];
+        const unsigned long long coff = parked ? ((unsigned long long)stash[ST_COFF + 1] << 32 | stash[ST_COFF]) : P.comp_off[c];
         const uint8_t* gsrc = P.comp + coff;
         const uint32_t phase = (uint32_t)((uintptr_t)gsrc & 15u);
         ws->status = RNSC_OK;
         bulk_load(region + REGION_HEAD, gsrc - phase, hsrc->stage_bytes, &ws->mbar);
+    }
+    if (tid == 32) {      // where the samples go and how many (read by the splitter inverse)
+        ws->n = parked ? stash[ST_N] : P.n[c];
+        ws->sample_off = parked ? ((unsigned long long)stash[ST_SOFF + 1] << 32 | stash[ST_SOFF]) : P.sample_off[c];
     }
     {
         const uint32_t* s = (const uint32_t*)hsrc; uint32_t* d = (uint32_t*)&ws->head;

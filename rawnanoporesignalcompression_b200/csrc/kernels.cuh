@@ -155,14 +155,16 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
     __syncthreads();
     uint32_t parity = 0;
     PhaseClock pc; pc.start(P.prof);
+    unsigned long long gt0 = 0; if (P.prof && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+    uint32_t nch = 0;
     for (;;) {
         const uint32_t c = ws->next;            // thread 0 replaces it (prefetch) only after the first barrier of the chunk
         if (c == FAST_NONE) break;
-        fast_decode_chunk<NTH>(ws, region, P, c, parity, pc);
+        fast_decode_chunk<NTH>(ws, region, P, c, parity, pc); ++nch;
         parity ^= 1u;
-        const uint32_t n = P.n[c];
+        const uint32_t n = ws->n;
         if (ws->status == RNSC_OK && n > 0) {
-            const int r = unpack2_any<NTH>(P.codec, region, lut, ws->head.view, n, P.samples + P.sample_off[c], &ws->u2);
+            const int r = unpack2_any<NTH>(P.codec, region, lut, ws->head.view, n, P.samples + ws->sample_off, &ws->u2);
             if (r && tid == 0) ws->status = r;
         }
         __syncthreads();
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
         __syncthreads();                        // the region and ws->status are reused by the next chunk
         pc.mark(PH_OTHER);
     }
+    if (P.prof && tid == 0) { unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1)); unsigned long long* sp = P.span + 3 * (size_t)blockIdx.x; sp[0] = gt0; sp[1] = gt1; sp[2] = nch; }
 }
 
 // ---------------------------------------------------------------------------------------------------

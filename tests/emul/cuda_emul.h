@@ -118,6 +118,8 @@ inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return 0; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (cudaStream_t)1; return 0; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest) { *least = 0; *greatest = -1; return 0; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)1; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
@@ -129,7 +131,8 @@ inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emul"; }
 struct cudaDeviceProp { int multiProcessorCount = 4; size_t sharedMemPerBlockOptin = 227 * 1024; char name[64] = "emul"; };
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return 0; }
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize, cudaFuncAttributePreferredSharedMemoryCarveout };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 
 #define RNSC_LAUNCH(kernel, grid, block, smem, stream, ...) \

@@ -32,4 +32,5 @@ for i in range(N): step(); ev[i+1].record()
 torch.cuda.synchronize()
 ts=sorted(ev[i].elapsed_time(ev[i+1]) for i in range(N))
 ms=ts[N//2]
+if '--steps' in sys.argv: print('step ms:', ' '.join(f'{ev[i].elapsed_time(ev[i+1]):.2f}' for i in range(N)))
 print(f"codec {codec}: {2e-6*sig.numel()/ms:.1f} GB/s median ({2e-6*sig.numel()/ts[0]:.1f} best), {ms:.3f} ms, routing {cd.decode_class_counts()}, bits/sample {8*coff[-1]/sig.numel():.3f}")
