@@ -128,6 +128,11 @@ int rnsc_decode_class_counts(rnsc_ctx* ctx, uint32_t out[4], void* stream);
  * inverse, bookkeeping, chunks). rnsc_get_phase_cycles synchronises the device and returns the running totals. */
 int rnsc_set_profiling(rnsc_ctx* ctx, int on);
 int rnsc_get_phase_cycles(rnsc_ctx* ctx, uint64_t out[24]);
+/* Same switch: every CTA of the fast decode kernels also records {start ns, end ns (%globaltimer), chunks decoded}.
+ * out = 3 classes (S, A, B) x 1024 CTAs x 3 words of the last decode; unused slots are zero. Shows how the kernels of a
+ * call share the SMs over time (tools/span_probe.py). */
+#define RNSC_SPAN_WORDS (3 * 1024 * 3)
+int rnsc_get_cta_spans(rnsc_ctx* ctx, uint64_t out[RNSC_SPAN_WORDS]);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t rnsc_launch_count(const rnsc_ctx* ctx);
 

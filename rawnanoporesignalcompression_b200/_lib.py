@@ -26,7 +26,7 @@ EXPORTS = [
     "rnsc_set_host_threads", "rnsc_max_compressed_size", "rnsc_max_stream_bytes", "rnsc_stream_count",
     "rnsc_compress_chunk", "rnsc_decompress_chunk", "rnsc_compress_batch", "rnsc_decompress_batch",
     "rnsc_dev_decode", "rnsc_dev_svb_encode", "rnsc_dev_svb_decode", "rnsc_dev_rc_encode", "rnsc_dev_rc_decode",
-    "rnsc_dev_exclusive_scan_u32", "rnsc_launch_count", "rnsc_decode_class_counts", "rnsc_set_profiling", "rnsc_get_phase_cycles",
+    "rnsc_dev_exclusive_scan_u32", "rnsc_launch_count", "rnsc_decode_class_counts", "rnsc_set_profiling", "rnsc_get_phase_cycles", "rnsc_get_cta_spans",
     "rnsc_pod5_vbz_compressed_signal_max_size", "rnsc_pod5_vbz_compress_signal", "rnsc_pod5_pinanoraw_compress_signal",
     "rnsc_pod5_vbz_decompress_signal", "rnsc_pod5_pinanoraw_decompress_signal", "rnsc_set_pgnano_variant",
     "rnsc_get_pgnano_variant",
@@ -72,6 +72,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "rnsc_decode_class_counts": (i32, [vp, vp, vp]),
         "rnsc_set_profiling": (i32, [vp, i32]),
         "rnsc_get_phase_cycles": (i32, [vp, vp]),
+        "rnsc_get_cta_spans": (i32, [vp, vp]),
         "rnsc_pod5_vbz_compressed_signal_max_size": (sz, [sz]),
         "rnsc_pod5_vbz_compress_signal": (i32, [vp, sz, vp, C.POINTER(sz)]),
         "rnsc_pod5_pinanoraw_compress_signal": (i32, [vp, sz, vp, C.POINTER(sz)]),

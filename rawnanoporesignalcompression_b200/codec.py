@@ -89,6 +89,12 @@ class Codec:
     def set_profiling(self, on: bool):
         self._check(self.lib.rnsc_set_profiling(self.ctx, int(bool(on))))
 
+    def cta_spans(self):
+        """(3, 1024, 3) uint64: per size class (S, A, B) and CTA {start ns, end ns, chunks} of the last decode (profiling on)."""
+        out = np.zeros(3 * 1024 * 3, dtype=np.uint64)
+        self._check(self.lib.rnsc_get_cta_spans(self.ctx, out.ctypes.data))
+        return out.reshape(3, 1024, 3)
+
     def phase_cycles(self):
         """{class: {phase: cycles}} accumulated by the fast decode kernels since set_profiling(True)."""
         out = (C.c_uint64 * 24)()

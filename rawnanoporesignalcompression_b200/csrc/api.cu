@@ -388,12 +388,11 @@ int rnsc_set_profiling(rnsc_ctx* c, int on)
 {
     if (!c) return fail(RNSC_ERR_BAD_ARG, "rnsc_set_profiling: bad argument");
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
-    if (on) { if (c->d_prof.reserve(24 * 8 + 3 * 3 * 1024 * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(prof) failed"); CUDA_OK(cudaMemset(c->d_prof.p, 0, 24 * 8 + 3 * 3 * 1024 * 8)); }
+    if (on) { if (c->d_prof.reserve((24 + RNSC_SPAN_WORDS) * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(prof) failed"); CUDA_OK(cudaMemset(c->d_prof.p, 0, (24 + RNSC_SPAN_WORDS) * 8)); }
     c->profiling = on != 0;
     return RNSC_OK;
 }
 
-int rnsc_debug_spans(rnsc_ctx* c, unsigned long long* out) { cudaDeviceSynchronize(); return cudaMemcpy(out, (unsigned long long*)c->d_prof.p + 24, 3 * 3 * 1024 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1; }
 int rnsc_get_phase_cycles(rnsc_ctx* c, uint64_t out[24])
 {
     if (!c || !out) return fail(RNSC_ERR_BAD_ARG, "rnsc_get_phase_cycles: bad argument");
@@ -402,6 +401,17 @@ int rnsc_get_phase_cycles(rnsc_ctx* c, uint64_t out[24])
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(out, c->d_prof.p, 24 * 8, cudaMemcpyDeviceToHost));
+    return RNSC_OK;
+}
+
+int rnsc_get_cta_spans(rnsc_ctx* c, uint64_t out[RNSC_SPAN_WORDS])
+{
+    if (!c || !out) return fail(RNSC_ERR_BAD_ARG, "rnsc_get_cta_spans: bad argument");
+    memset(out, 0, RNSC_SPAN_WORDS * 8);
+    if (!c->d_prof.p) return RNSC_OK;
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(out, (const uint64_t*)c->d_prof.p + 24, RNSC_SPAN_WORDS * 8, cudaMemcpyDeviceToHost));
     return RNSC_OK;
 }
 

@@ -25,9 +25,18 @@ struct FastParams {
     const ChunkPlan* plans; const uint32_t* list; const uint32_t* count; uint32_t* counter; uint32_t nchunks;
     const uint32_t* seq_pool;    // the planner's sequence pool (SEQ_WORDS words per entry)
     uint32_t* origin; unsigned long long origin_stride;   // per-CTA global scratch (words) of the match resolver
-    unsigned long long* span;    // debug
+    unsigned long long* span;    // optional (same switch): per CTA {start, end in ns, chunks decoded}
     unsigned long long* prof;    // optional (rnsc_set_profiling): 8 phase cycle counters of this size class, summed over CTAs
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+#ifdef RNSC_EMUL
+    return 0;
+#else
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+#endif
+}
 
 // Phase timing for tuning: thread 0 of every CTA adds the cycles since the previous mark to prof[phase].
 enum { PH_STAGE = 0, PH_HUF1 = 1, PH_HUFSCAN = 2, PH_HUF2 = 3, PH_SEQ = 4, PH_UNPACK = 5, PH_OTHER = 6, PH_CHUNKS = 7 };

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
     __syncthreads();
     uint32_t parity = 0;
     PhaseClock pc; pc.start(P.prof);
-    unsigned long long gt0 = 0; if (P.prof && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+    const unsigned long long gt0 = (P.span && tid == 0) ? global_ns() : 0ull;      // profiling: this CTA's life span and chunk count
     uint32_t nch = 0;
     for (;;) {
         const uint32_t c = ws->next;            // thread 0 replaces it (prefetch) only after the first barrier of the chunk
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
         __syncthreads();                        // the region and ws->status are reused by the next chunk
         pc.mark(PH_OTHER);
     }
-    if (P.prof && tid == 0) { unsigned long long gt1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1)); unsigned long long* sp = P.span + 3 * (size_t)blockIdx.x; sp[0] = gt0; sp[1] = gt1; sp[2] = nch; }
+    if (P.span && tid == 0 && blockIdx.x < 1024) { unsigned long long* sp = P.span + 3 * (size_t)blockIdx.x; sp[0] = gt0; sp[1] = global_ns(); sp[2] = nch; }
 }
 
 // ---------------------------------------------------------------------------------------------------

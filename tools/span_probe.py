@@ -17,13 +17,10 @@ def step(): cd.dev_decode(codec,d_comp,d_coff,d_n,d_off,int(n.max()),out,stt)
 for _ in range(5): step()
 torch.cuda.synchronize()
 cd.set_profiling(True)
-f=cd.lib.rnsc_debug_spans; f.argtypes=[ctypes.c_void_p, ctypes.c_void_p]; f.restype=ctypes.c_int
-buf=np.zeros(3*1024*3,dtype=np.uint64)
 for it in range(6):
     e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
     e0.record(); step(); e1.record(); torch.cuda.synchronize()
-    f(cd.ctx, buf.ctypes.data)
-    b=buf.reshape(3,1024,3)
+    b=cd.cta_spans()
     t0=min(int(b[k,:,0][b[k,:,2]>0].min()) for k in range(3) if (b[k,:,2]>0).any())
     line=f'step {e0.elapsed_time(e1):.2f} ms:'
     for k,name in ((2,'B'),(1,'A'),(0,'S')):
