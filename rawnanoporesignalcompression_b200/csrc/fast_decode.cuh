@@ -90,24 +90,40 @@ __device__ inline void mbar_wait(unsigned long long*, uint32_t) {}
 #endif
 
 // ---- Huffman table from its recipe: each thread fills 8 consecutive entries with one 16-byte store --------
-// `nthr` threads (t = 0 .. nthr-1) build this table.
-__device__ inline void fast_build_table(uint16_t* tab, const HufPlan* hp, int t, int nthr)
+// `nthr` threads (t = 0 .. nthr-1) build this table. The weight class of an entry is found by counting class starts
+// <= the entry in registers (the starts are 14 halfwords, fetched as 7 broadcast words); a group of 8 entries that
+// lies in one class of code length <= L - 3 is one symbol (runs are 2^(w-1) >= 8 entries long and aligned).
+__device__ __forceinline__ void fast_build_table(uint16_t* tab, const HufPlan* hp, int t, int nthr)
 {
     const uint32_t L = hp->log, size = 1u << L;
-    for (uint32_t u0 = (uint32_t)t * 8; u0 < size; u0 += (uint32_t)nthr * 8) {
-        uint32_t w = 1;
-        while (hp->cls_start[w + 1] <= u0) ++w;
-        uint32_t packed[4];
+    uint32_t cs[7];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t u = u0 + k;
-            uint32_t e = 0;
-            if (u < size) {
-                while (hp->cls_start[w + 1] <= u) ++w;
-                const uint32_t sym = hp->sorted[hp->cls_sym[w] + ((u - hp->cls_start[w]) >> (w - 1))];
-                e = (sym << 8) | (L + 1 - w);        // low byte: code length, high byte: symbol
+    for (int k = 0; k < 7; ++k) cs[k] = ((const uint32_t*)hp->cls_start)[k];      // (start[2k], start[2k+1])
+    auto cls_of = [&](uint32_t u) -> uint32_t {       // largest w with cls_start[w] <= u (classes above L start at 2^L > u)
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { w += (cs[k] >> 16) <= u; if (k) w += (cs[k] & 0xFFFFu) <= u; }
+        return w;
+    };
+    for (uint32_t u0 = (uint32_t)t * 8; u0 < size; u0 += (uint32_t)nthr * 8) {
+        uint32_t packed[4];
+        const uint32_t w0 = cls_of(u0), w7 = cls_of(u0 + 7);
+        if (w0 == w7 && w0 >= 4) {
+            const uint32_t sym = hp->sorted[hp->cls_sym[w0] + ((u0 - hp->cls_start[w0]) >> (w0 - 1))];
+            const uint32_t e = (sym << 8) | (L + 1 - w0);        // low byte: code length, high byte: symbol
+            packed[0] = packed[1] = packed[2] = packed[3] = e | (e << 16);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t u = u0 + k;
+                uint32_t e = 0;
+                if (u < size) {
+                    const uint32_t w = cls_of(u);
+                    const uint32_t sym = hp->sorted[hp->cls_sym[w] + ((u - hp->cls_start[w]) >> (w - 1))];
+                    e = (sym << 8) | (L + 1 - w);
+                }
+                if (k & 1) packed[k >> 1] |= e << 16; else packed[k >> 1] = e;
             }
-            if (k & 1) packed[k >> 1] |= e << 16; else packed[k >> 1] = e;
         }
         if (size >= 8) *(V16*)(tab + u0) = V16{packed[0], packed[1], packed[2], packed[3]};
         else for (uint32_t k = 0; k < size; ++k) tab[k] = (uint16_t)(packed[k >> 1] >> (16 * (k & 1)));
@@ -120,12 +136,6 @@ __device__ inline void fast_build_table(uint16_t* tab, const HufPlan* hp, int t,
 // of any size: (1) aux: for every code length l in use and every value r of the L - l bits behind such a code, the
 // length of the symbol that r starts with, if it fits (0 otherwise) -- 2^(L-l) entries at offset A - 2^(L-l+1),
 // A = 2^(L-lmin+1); (2) skip[u] from table[u] and aux, four entries per thread and store.
-__device__ __forceinline__ uint32_t huf_min_len(const HufPlan* hp)
-{
-    uint32_t w = hp->log;
-    while (w > 1 && hp->cls_start[w] >= hp->cls_start[w + 1]) --w;      // heaviest weight class in use
-    return hp->log + 1 - w;
-}
 __device__ __forceinline__ uint32_t skip_aux_bytes(uint32_t L, uint32_t lmin) { return 2u << (L - lmin); }
 __device__ __forceinline__ void fast_build_aux(uint8_t* aux, const uint16_t* tab, uint32_t L, uint32_t lmin, int t, int nthr)
 {
@@ -275,12 +285,6 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
         my_end = p;
     }
     pc.mark(PH_HUF1);
-    // next chunk's plan words: requested now, parked after the second pass
-    constexpr int PF = (ST_WORDS + NTH - 1) / NTH;
-    uint32_t pf[PF];
-    const uint32_t nx = ws->next;
-#pragma unroll
-    for (int q = 0; q < PF; ++q) { const uint32_t idx = (uint32_t)tid + (uint32_t)q * NTH; pf[q] = (nx != FAST_NONE && idx < ST_WORDS) ? stash_fetch(P, nx, idx) : 0u; }
     uint32_t inc;
     for (int round = 0;; ++round) {
         inc = warp_inclusive_scan(active ? my_cnt : 0u);
@@ -298,6 +302,12 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
             my_end = p;
         }
     }
+    // next chunk's plan words: requested now (ws->next was written before the barriers above), parked after the second pass
+    constexpr int PF = (ST_WORDS + NTH - 1) / NTH;
+    uint32_t pf[PF];
+    const uint32_t nx = ws->next;
+#pragma unroll
+    for (int q = 0; q < PF; ++q) { const uint32_t idx = (uint32_t)tid + (uint32_t)q * NTH; pf[q] = (nx != FAST_NONE && idx < ST_WORDS) ? stash_fetch(P, nx, idx) : 0u; }
     // output offset inside my stream = CTA exclusive scan of the counts minus the scan value at the stream's first thread
     const uint32_t wt = lane < NW ? ws->warp_tot[lane] : 0u;
     const uint32_t wex = warp_inclusive_scan(wt) - wt;                        // lane w: symbols before warp w
@@ -526,6 +536,16 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const PlanHead& hd, 
 }
 
 // Decodes chunk c: the stream views are ws->head.view (offsets into the region), the result ws->status. Must be entered by the whole CTA after a barrier.
+__device__ __forceinline__ void copy_run_tables(const PlanHead* hd, const uint32_t* pool, uint8_t* region, uint32_t first, uint32_t step)
+{
+    for (uint32_t k = 0; k < hd->nsop; ++k) {
+        const SeqOp op = hd->sop[k];
+        const uint32_t* g = pool + (size_t)SEQ_WORDS * op.seq_base;
+        uint2* run = (uint2*)(region + op.meta_off);
+        for (uint32_t i = first; i < op.nruns; i += step) run[i] = make_uint2(g[SEQ_WORDS * i + 6], g[SEQ_WORDS * i + 7]);
+    }
+}
+
 template <int NTH>
 __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, uint32_t c, uint32_t parity, PhaseClock& pc)
 {
@@ -552,17 +572,18 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
         const uint32_t nhuf = hsrc->nhuf;
         s = parked ? stash + ST_HEAD_W : (const uint32_t*)pl->h; d = (uint32_t*)ws->h;
         for (uint32_t i = tid; i < (uint32_t)sizeof(HufPlan) / 4 * nhuf; i += NTH) d[i] = s[i];
-        // run tables of the frames with sequences: {first literal index, shift} of every non-empty literal run
-        for (uint32_t k = 0; k < hsrc->nsop; ++k) {
-            const SeqOp op = hsrc->sop[k];
-            const uint32_t* g = P.seq_pool + (size_t)SEQ_WORDS * op.seq_base;
-            uint2* run = (uint2*)(region + op.meta_off);
-            for (uint32_t i = tid; i < op.nruns; i += NTH) run[i] = make_uint2(g[SEQ_WORDS * i + 6], g[SEQ_WORDS * i + 7]);
-        }
+        // run tables of the frames with sequences: {first literal index, shift} of every non-empty literal run. They are
+        // first read in the second Huffman pass: with few sequences the one-CTA-per-SM class leaves the (global memory
+        // latency of the) copy to its spare last warp, below
+        if (!(NTH == 1024 && hsrc->nseq <= FAST_ORDERED_MAX)) copy_run_tables(hsrc, P.seq_pool, region, tid, NTH);
     }
     __syncthreads();
     // prefetch the next chunk index while this one is decoded
-    if (tid == 0) { const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
+    // Three dependent global round trips. With four or two CTAs per SM thread 0 takes them here and the other CTAs cover
+    // the stall; the one-CTA-per-SM class gives them to its last warp, which the planner keeps free of Huffman sub-sequences
+    // (see below), so that nobody waits for them.
+    constexpr bool CHAIN_LATE = NTH == 1024;
+    if (!CHAIN_LATE && tid == 0) { const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
     const PlanHead& hd = ws->head;
     {   // all tables at once: the CTA's threads are split evenly over them
         const uint32_t nhuf = hd.nhuf;
@@ -573,13 +594,13 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
             // sub-sequence arrays, which the Huffman stage only uses later
             bool skip_on = ws->h[0].skip_off != 0;
             const uint32_t aux_cap = ((uint32_t)sizeof(ws->sub_end) + (uint32_t)sizeof(ws->sub_inc)) / nhuf & ~15u;
-            for (uint32_t h = 0; h < nhuf; ++h) if (skip_aux_bytes(ws->h[h].log, huf_min_len(&ws->h[h])) > aux_cap) skip_on = false;
+            for (uint32_t h = 0; h < nhuf; ++h) if (skip_aux_bytes(ws->h[h].log, ws->h[h].lmin) > aux_cap) skip_on = false;
             if (tid == 0) ws->skip_on = skip_on;
             if (skip_on) {
                 uint8_t* aux = (uint8_t*)ws->sub_end + (size_t)aux_cap * (t < (int)nhuf ? t : 0);
                 const HufPlan* hp = &ws->h[t < (int)nhuf ? t : 0];
                 const uint16_t* tb = (const uint16_t*)(region + hp->tab_off);
-                const uint32_t lmin = huf_min_len(hp);
+                const uint32_t lmin = hp->lmin;
                 __syncthreads();
                 if (t < (int)nhuf) fast_build_aux(aux, tb, hp->log, lmin, tid - t * per, per);
                 __syncthreads();
@@ -591,6 +612,10 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     mbar_wait(&ws->mbar, parity);
     __syncthreads();
     pc.mark(PH_STAGE);
+    if (CHAIN_LATE && tid >= NTH - 32) {
+        if (hd.nseq <= FAST_ORDERED_MAX) { copy_run_tables(&hd, P.seq_pool, region, (uint32_t)tid & 31u, 32u); __syncwarp(); }
+        if (tid == NTH - 32) { const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
+    }
     // frames with a few sequences over raw / RLE literals: the last warp (which the planner kept free of Huffman
     // sub-sequences) executes them now, off the critical path
     if (hd.early && (tid >> 5) == NTH / 32 - 1)
@@ -601,6 +626,7 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
         if (hd.nseq <= FAST_ORDERED_MAX) {      // few sequences: one warp per remaining frame, in order
             const uint32_t late = ((1u << hd.nsop) - 1u) & ~hd.early, w = tid >> 5;
             if (late) {
+                if (CHAIN_LATE && !hd.nst) __syncthreads();      // the run tables were copied by the last warp just above
                 if ((late >> w) & 1u) fast_exec_sequences_ordered(hd.sop[w], P.seq_pool + (size_t)SEQ_WORDS * hd.sop[w].seq_base, region);
                 __syncthreads();
             }

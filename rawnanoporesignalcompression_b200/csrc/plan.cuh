@@ -43,6 +43,7 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
     uint32_t log;                // table log (max code length), <= 12
     uint32_t tab_off;            // region offset of the table (2^log entries of 2 bytes)
     uint32_t skip_off;           // region offset of its skip table (2^log bytes), 0 = none (it would push the chunk into a bigger size class)
+    uint32_t lmin;               // shortest code length in use
     uint16_t cls_start[14];      // first table entry of weight class w (1..log); cls_start[log+1] = 2^log
     uint16_t cls_sym[14];        // index into sorted[] of the first symbol of class w
     uint8_t sorted[256];         // symbols of weight > 0 ordered by (weight, symbol)
@@ -234,6 +235,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
         for (int k = 1; k <= maxBits; ++k) {
             hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s;
             const uint32_t cnt = sc->rank_cnt[k];
+            if (cnt) hp->lmin = (uint32_t)(maxBits + 1 - k);
             sc->rank_cnt[k] = s;                     // running insert position of class k
             e += cnt << (k - 1); s += cnt;
         }
@@ -413,7 +415,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     // Frames whose sequences do not wait for Huffman literals (C5: Lhigh) get the last warp to themselves during the Huffman stage
     uint32_t early = 0;
     if (nst && nseq_tot <= FAST_ORDERED_MAX) for (uint32_t k = 0; k < nsop; ++k) if (hd->sop[k].ltype != 2) early |= 1u << k;
-    const uint32_t nth_h = early ? nth - 32 : nth;
+    const uint32_t nth_h = (early || cls == CLS_B) ? nth - 32 : nth;      // class B: the last warp also fetches the CTA's next chunk index meanwhile
     uint32_t sub = nst ? (ttot + (nth_h - nst) - 1) / (nth_h - nst) : PLAN_SUB_MIN;
     if (sub < PLAN_SUB_MIN) sub = PLAN_SUB_MIN;
     uint32_t first = 0;
