@@ -93,12 +93,14 @@ struct PlanParams {
     uint32_t* seq_pool; uint32_t pool_cap; uint32_t* pool_cursor;   // bump-allocated sequence storage (SEQ_WORDS words per entry)
 };
 
-// Per planner thread scratch in shared memory. 225 words: an odd stride, so the same field of the 32 threads
-// of a warp falls into 32 different banks.
+// Per planner thread scratch in shared memory. 161 words: an odd stride, so the same field of the 32 threads of a
+// warp falls into 32 different banks. The FSE build temporaries (norm, next16) are dead before the first weight is
+// written, so they share the weights' bytes: a smaller scratch = more planner CTAs per SM.
 struct PlanScratch {
-    uint8_t weights[256]; uint32_t fse_w[64]; int16_t norm[64]; uint16_t next16[64]; uint32_t rank_start[16]; uint32_t rank_cnt[16]; int huf_log;
+    union { uint8_t weights[256]; struct { int16_t norm[64]; uint16_t next16[64]; }; };
+    uint32_t fse_w[64]; uint32_t rank_start[16]; uint32_t rank_cnt[16]; int huf_log;
 };
-static_assert(sizeof(PlanScratch) == 900, "PlanScratch layout");
+static_assert(sizeof(PlanScratch) == 644, "PlanScratch layout");
 
 __host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 __host__ __device__ inline uint32_t huf_tab_bytes(uint32_t log) { return align16(2u << log); }
