@@ -130,23 +130,35 @@ __device__ inline void fse_build(uint32_t* t, const int16_t* norm, int nsym, int
     }
 }
 
-// MSB-first backward reader over global bytes (FSE streams; serial use only)
-struct BwdBits { const uint8_t* start; int bitpos; int overflow; };
+// MSB-first backward reader over global bytes (FSE streams; serial use only). The two aligned words that cover the
+// current position stay in registers: a read is a compare, a funnel shift and a mask, and one word is fetched when the
+// position crosses a word boundary (every 32 bits) instead of two per read.
+struct BwdBits { const uint8_t* start; int bitpos; int overflow; uintptr_t wa; uint32_t w0, w1; };
 __device__ inline int bwd_init(BwdBits& b, const uint8_t* p, uint32_t size)
 {
     if (size == 0) return -1;
     uint32_t last = ldg8(p + size - 1);
     if (last == 0) return -1;
-    b.start = p; b.overflow = 0;
+    b.start = p; b.overflow = 0; b.wa = 0; b.w0 = b.w1 = 0;
     b.bitpos = (int)size * 8 - (8 - highbit32(last));
     return 0;
+}
+__device__ __forceinline__ uint32_t bwd_bits32(BwdBits& b, uint32_t bit)      // gbits32(b.start, bit) through the cached words
+{
+    const uintptr_t a = (uintptr_t)b.start + (bit >> 3), al = a & ~(uintptr_t)3;
+    if (al != b.wa) {
+        if (al + 4 == b.wa) { b.w1 = b.w0; b.w0 = ldg32((const uint32_t*)al); }
+        else { b.w0 = ldg32((const uint32_t*)al); b.w1 = ldg32((const uint32_t*)(al + 4)); }
+        b.wa = al;
+    }
+    return __funnelshift_r(b.w0, b.w1, ((uint32_t)(a & 3) << 3) + (bit & 7));
 }
 __device__ inline uint32_t bwd_read(BwdBits& b, int n)
 {
     if (n == 0) return 0;
     const int lo = b.bitpos - n;
     b.bitpos = lo;
-    if (lo >= 0) return gbits32(b.start, (uint32_t)lo) & (0xFFFFFFFFu >> (32 - n));     // n <= 31
+    if (lo >= 0) return bwd_bits32(b, (uint32_t)lo) & (0xFFFFFFFFu >> (32 - n));     // n <= 31
     b.overflow = 1;                                           // bits below the start of the stream read as zero
     const int avail = n + lo;
     if (avail <= 0) return 0;
