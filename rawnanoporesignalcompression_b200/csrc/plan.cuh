@@ -231,6 +231,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     warp_converge<true>();
     // table recipe: weight classes in ascending weight (= descending code length), symbols in natural order
     HufPlan* hp = &pl->h[huf ? nhuf : 0];
+    unsigned long long p_lo = 0, p_hi = 0;           // running insert position of every class, 8-bit fields (weights 0-7, 8-15)
     if (huf) {
         const int maxBits = sc->huf_log;
         uint32_t e = 0, s = 0;                       // huf_read_weights left the per-weight symbol counts in rank_cnt
@@ -238,7 +239,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
             hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s;
             const uint32_t cnt = sc->rank_cnt[k];
             if (cnt) hp->lmin = (uint32_t)(maxBits + 1 - k);
-            sc->rank_cnt[k] = s;                     // running insert position of class k
+            if (k & 8) p_hi |= (unsigned long long)(s & 0xFFu) << ((k & 7) * 8); else p_lo |= (unsigned long long)(s & 0xFFu) << ((k & 7) * 8);
             e += cnt << (k - 1); s += cnt;
         }
         hp->cls_start[0] = 0; hp->cls_sym[0] = 0;
@@ -248,7 +249,17 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     warp_converge<true>();
     {
         const int lim = huf ? nw : 0;
-        for (int i = 0; i < lim; ++i) { const uint32_t w = sc->weights[i]; if (w) hp->sorted[sc->rank_cnt[w]++] = (uint8_t)i; }
+        // a position is at most 255 when it is used; the increment past the last symbol of the heaviest class may carry
+        // into the (unused) field above it
+        for (int i = 0; i < lim; ++i) {
+            const uint32_t w = sc->weights[i];
+            if (w) {
+                const uint32_t sh = (w & 7u) * 8u;
+                const uint32_t pos = (uint32_t)(((w & 8u) ? p_hi : p_lo) >> sh) & 0xFFu;
+                hp->sorted[pos] = (uint8_t)i;
+                if (w & 8u) p_hi += 1ull << sh; else p_lo += 1ull << sh;
+            }
+        }
     }
     if (huf) fp.huf = nhuf++;
     warp_converge<true>();

@@ -214,14 +214,21 @@ __device__ inline uint32_t huf_read_weights(WS* ws, const uint8_t* src, uint32_t
         }
     }
     warp_converge<SYNC>();
-    // ---- one pass: validity, total weight and the per-weight symbol counts (kept in ws->rank_cnt: a local array
-    //      with a data-dependent index would be expanded into a compare/select chain per symbol) ----
+    // ---- one pass: validity, total weight and the per-weight symbol counts. The counters are 8-bit fields of two
+    //      64-bit registers (at most 255 weights are listed): no memory read-modify-write chain, and no local array
+    //      (a data-dependent index would be expanded into a compare/select chain per symbol). Left in ws->rank_cnt. ----
     uint32_t* cnt = ws->rank_cnt;
     uint32_t total = 0;
     if (ok) {
-        for (int k = 0; k < 16; ++k) cnt[k] = 0;
+        unsigned long long c_lo = 0, c_hi = 0;              // weights 0-7, 8-15
         bool big = false;
-        for (int i = 0; i < nw; ++i) { uint32_t wi = w[i]; if (wi > HUF_LOG_MAX) { big = true; wi = 0; } total += (1u << wi) >> 1; cnt[wi]++; }
+        for (int i = 0; i < nw; ++i) {
+            uint32_t wi = w[i]; if (wi > HUF_LOG_MAX) { big = true; wi = 0; }
+            total += (1u << wi) >> 1;
+            const unsigned long long one = 1ull << ((wi & 7u) * 8u);
+            if (wi & 8u) c_hi += one; else c_lo += one;
+        }
+        for (int k = 0; k < 8; ++k) { cnt[k] = (uint32_t)(c_lo >> (8 * k)) & 0xFFu; cnt[8 + k] = (uint32_t)(c_hi >> (8 * k)) & 0xFFu; }
         if (big || total == 0) ok = false;
     }
     int maxBits = 0;
