@@ -6,9 +6,9 @@
 //     OUTPUT: results go from registers to global memory with two 128-bit stores, no shared-memory tile;
 //   * key bits and the thread's payload bytes/nibbles are fetched as aligned 32-bit words and funnel-shifted
 //     into register windows (C4/C5), so the per-sample work is predicates, shifts and adds, no loads;
-//   * stream positions and the delta^-1 prefix sum use one-barrier CTA scans of ONE 32-bit word each
-//     (block_scan_1b): the unit counts of two streams share a word, and the count of large values of the
-//     NEXT tile rides in the low half of the word whose high half carries the tile's delta sums (mod 2^16);
+//   * stream positions and the delta^-1 prefix sum are two 32-bit CTA scans behind ONE barrier per tile: the unit
+//     counts of two streams of the NEXT tile share a word, and the count of large values of the next tile rides in
+//     the low half of the word whose high half carries this tile's delta sums (mod 2^16);
 //   * C4/C5 go four samples at a time: a 256-entry table indexed by the key byte gives the byte-permute selectors that
 //     pull the samples' units out of the stream windows; zigzag^-1 runs on two 16-bit lanes per register.
 // Works on generic pointers; every stream must be readable up to 8 bytes past its end (the fast decoder's
@@ -43,25 +43,9 @@ __device__ inline KeyLut make_key_lut(uint32_t kbyte)
 
 template <int NTH>
 struct Unpack2Ws {
-    uint32_t sa[NTH / 32], sb[NTH / 32];      // warp totals of the two scans of a tile (A: unit counts, B: delta sums | large count)
+    uint32_t sa[2][NTH / 32], sb[2][NTH / 32];   // warp totals of the two scans of a tile (A: unit counts, B: delta sums | large count), double-buffered
     int err;
 };
-
-// Exclusive CTA scan of a 32-bit word with a single barrier: every warp sums the totals of the warps in front of
-// it with one warp reduction. Two consecutive calls must use different scratch arrays.
-template <int NTH>
-__device__ __forceinline__ uint32_t block_scan_1b(uint32_t v, uint32_t* scratch, uint32_t* total)
-{
-    constexpr int NW = NTH / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t inc = warp_inclusive_scan(v);
-    if (lane == 31) scratch[warp] = inc;
-    __syncthreads();
-    const uint32_t w = lane < NW ? scratch[lane] : 0u;
-    *total = __reduce_add_sync(0xffffffffu, w);
-    const uint32_t base = __reduce_add_sync(0xffffffffu, lane < warp ? w : 0u);
-    return base + inc - v;
-}
 
 // Shared-memory byte addresses as plain integers: the streams live in the caller's shared-memory region, and a load
 // through a generic pointer would take the slower generic path.
@@ -125,22 +109,15 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
         if (KB * cnt < 32) kb &= (1u << (KB * cnt)) - 1u;
         return kb << (KB * (vlo - v0));
     };
-    auto large_mask = [](uint32_t kb) -> uint32_t { return kb & (kb >> 1) & 0x55555555u; };
-    __syncthreads();
-    uint32_t kb_next = nv ? load_keys(0) : 0u, p3 = 0;
-    if (WIN) {   // positions of the first tile's large values (later tiles: piggybacked on the previous tile's second scan)
-        uint32_t tot;
-        p3 = block_scan_1b<NTH>((uint32_t)__popc(large_mask(kb_next)), ws->sb, &tot);
-        run3 = tot;
-    }
-    for (uint32_t tb = 0; tb < nv; tb += NTH * S) {
+    // valid samples of this thread in the tile starting at tb
+    auto tile_cnt = [&](uint32_t tb) -> uint32_t {
         const uint32_t v0 = tb + (uint32_t)tid * S;
         const uint32_t vlo = max(v0, ph), vhi = min(v0 + S, nv);
-        const uint32_t cnt = vhi > vlo ? vhi - vlo : 0, jlo = cnt ? vlo - v0 : 0;
-        uint32_t kb = kb_next;
-        kb_next = tb + NTH * S < nv ? load_keys(tb + NTH * S) : 0u;
-        // ---- unit counts -> stream positions ----
-        uint32_t c1 = 0, c2 = 0, c3 = 0, m1 = 0, m2 = 0, m3 = 0;
+        return vhi > vlo ? vhi - vlo : 0u;
+    };
+    // class masks and unit counts of a tile from its key bits; wordA = what the positions scan adds up (see below)
+    auto classify = [&](uint32_t kb, uint32_t cnt, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t& m1, uint32_t& m2, uint32_t& m3) -> uint32_t {
+        c1 = c2 = c3 = m1 = m2 = m3 = 0;
         if (TWO) {
             const uint32_t lo = kb & 0x55555555u, hi = (kb >> 1) & 0x55555555u;
             m1 = lo & ~hi; m2 = hi & ~lo; m3 = lo & hi;
@@ -153,8 +130,42 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
             else { c2 = nl; c1 = cnt - nl; }
         }
         // one word: a thread adds at most 64 units (VBZ0, alone in the word) or 16 + 16 (two halves), a tile at most 2^16 / 2^14
-        uint32_t totA;
-        const uint32_t exA = block_scan_1b<NTH>(ONE_STREAM ? c1 : (c1 | (c2 << 16)), ws->sa, &totA);
+        return ONE_STREAM ? c1 : (c1 | (c2 << 16));
+    };
+    // ONE barrier per tile: after a tile is decoded, word B = (the thread's delta sum << 16) | large values of the NEXT
+    // tile and word A = the unit counts of the NEXT tile are scanned together. The warp totals alternate between two
+    // buffers (a warp may be a tile ahead of the slowest reader of the previous totals, never two).
+    auto scan2 = [&](uint32_t a, uint32_t b, int flip, uint32_t& exA, uint32_t& totA, uint32_t& exB, uint32_t& totB) {
+        constexpr int NW = NTH / 32;
+        const int lane = tid & 31, warp = tid >> 5;
+        const uint32_t ia = warp_inclusive_scan(a), ib = warp_inclusive_scan(b);
+        if (lane == 31) { ws->sa[flip][warp] = ia; ws->sb[flip][warp] = ib; }
+        __syncthreads();
+        const uint32_t wa = lane < NW ? ws->sa[flip][lane] : 0u, wb = lane < NW ? ws->sb[flip][lane] : 0u;
+        totA = __reduce_add_sync(0xffffffffu, wa); totB = __reduce_add_sync(0xffffffffu, wb);
+        exA = __reduce_add_sync(0xffffffffu, lane < warp ? wa : 0u) + ia - a;
+        exB = __reduce_add_sync(0xffffffffu, lane < warp ? wb : 0u) + ib - b;
+    };
+    __syncthreads();
+    uint32_t kb_next = nv ? load_keys(0) : 0u, p3 = 0;
+    uint32_t c1, c2, c3, m1, m2, m3, exA, totA;
+    int flip = 0;
+    {   // positions of the first tile
+        uint32_t exB, totB;
+        const uint32_t wordA = classify(kb_next, tile_cnt(0), c1, c2, c3, m1, m2, m3);
+        scan2(wordA, c3, flip, exA, totA, exB, totB);
+        p3 = exB; run3 = totB;
+    }
+    for (uint32_t tb = 0; tb < nv; tb += NTH * S) {
+        flip ^= 1;
+        const uint32_t v0 = tb + (uint32_t)tid * S;
+        const uint32_t vlo = max(v0, ph), vhi = min(v0 + S, nv);
+        const uint32_t cnt = vhi > vlo ? vhi - vlo : 0, jlo = cnt ? vlo - v0 : 0;
+        uint32_t kb = kb_next;
+        const bool more = tb + NTH * S < nv;
+        kb_next = more ? load_keys(tb + NTH * S) : 0u;
+        classify(kb, cnt, c1, c2, c3, m1, m2, m3);
+        // ---- stream positions from the scan made at the end of the previous tile ----
         uint32_t p1, p2;
         if (ONE_STREAM) { p1 = run1 + exA; p2 = 0; run1 += totA; }
         else { p1 = run1 + (exA & 0xFFFFu); p2 = run2 + (exA >> 16); run1 += totA & 0xFFFFu; run2 += totA >> 16; }
@@ -271,10 +282,14 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
                 val[j] = acc;
             }
         }
-        // ---- delta^-1: CTA scan of the per-thread sums (mod 2^16, upper half of the word); the lower half scans the
-        //      large-value counts of the next tile ----
-        uint32_t totB;
-        const uint32_t exB = block_scan_1b<NTH>((acc << 16) | (WIN ? (uint32_t)__popc(large_mask(kb_next)) : 0u), ws->sb, &totB);
+        // ---- delta^-1: CTA scan of the per-thread sums (mod 2^16, upper half of word B); its lower half and word A scan
+        //      the large-value and unit counts of the next tile ----
+        uint32_t exB, totB;
+        {
+            uint32_t n1, n2, n3, q1, q2, q3;
+            const uint32_t wordA = classify(kb_next, more ? tile_cnt(tb + NTH * S) : 0u, n1, n2, n3, q1, q2, q3);
+            scan2(wordA, (acc << 16) | n3, flip, exA, totA, exB, totB);
+        }
         const uint32_t base = carry + (exB >> 16);
         carry += totB >> 16;
         if (WIN) { p3 = run3 + (exB & 0xFFFFu); run3 += totB & 0xFFFFu; }
