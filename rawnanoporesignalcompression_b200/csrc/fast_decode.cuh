@@ -172,6 +172,26 @@ __device__ __forceinline__ void bits_ending_at(const uint32_t* w, uint32_t A, ui
     hi = __funnelshift_l(b, a, sh); lo = __funnelshift_l(c, b, sh);
 }
 
+// Rolling variant for a monotonic walk (second pass): four consecutive words stay in registers; when the position moves
+// down across a word boundary the window slides and ONE new word is fetched, one slide ahead of its first use. Between
+// two get() calls A must not grow and must not drop by more than 64 bits. Reads down to word (A - 1) / 32 - 3.
+struct BitWin {
+    const uint32_t* w; uint32_t wi, a, b, c, d;
+    __device__ __forceinline__ void init(const uint32_t* words, uint32_t A)
+    {
+        w = words; wi = (A - 1) >> 5;
+        a = w[wi]; b = w[wi - 1]; c = w[wi - 2]; d = w[wi - 3];
+    }
+    __device__ __forceinline__ void get(uint32_t A, uint32_t& hi, uint32_t& lo)
+    {
+        const uint32_t nwi = (A - 1) >> 5;
+        if (nwi < wi) { a = b; b = c; c = d; --wi; d = w[wi - 3]; }
+        if (nwi < wi) { a = b; b = c; c = d; --wi; d = w[wi - 3]; }
+        const uint32_t sh = (32u - (A & 31u)) & 31u;
+        hi = __funnelshift_l(b, a, sh); lo = __funnelshift_l(c, b, sh);
+    }
+};
+
 // One symbol: table entry `ev` = symbol << 8 | code length. The funnel shifts take the entry itself as the shift
 // amount (they use its low 5 bits; a code is at most 12 bits), so the serial chain is peek -> load -> shift.
 // The integer ALU pipe (shifts, logic, 3-input adds) issues at half rate and is what bounds these loops, so the peek
@@ -335,8 +355,9 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
         if (li + rem <= run_end) {      // all my literals belong to one run (always, without sequences)
             uint8_t* o = region + sp.out + li + shift;
             while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
+            BitWin bw; bw.init(words, abit - p);
             while (rem >= 4) {
-                bits_ending_at(words, abit - p, hi, lo);
+                bw.get(abit - p, hi, lo);
                 uint32_t word = 0, adv = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
