@@ -459,7 +459,9 @@ __device__ inline void fast_exec_sequences_ordered(const SeqOp& op, const uint32
         const uint32_t ms = __shfl_sync(0xffffffffu, i < 32 ? m_ms[0] : m_ms[1], src), ml = __shfl_sync(0xffffffffu, i < 32 ? m_ml[0] : m_ml[1], src);
         const uint32_t of = __shfl_sync(0xffffffffu, i < 32 ? m_of[0] : m_of[1], src);
         uint8_t* d = dst + ms; const uint8_t* sp = d - of;
-        if (of >= 32) { for (uint32_t k0 = 0; k0 < ml; k0 += 32) { const uint32_t q = k0 + lane; if (q < ml) d[q] = sp[q]; __syncwarp(); } }
+        if (of >= ml) { for (uint32_t q = lane; q < ml; q += 32) d[q] = sp[q]; }                      // no overlap
+        else if (of == 1) { const uint8_t v = sp[0]; for (uint32_t q = lane; q < ml; q += 32) d[q] = v; }   // a run of one byte
+        else if (of >= 32) { for (uint32_t k0 = 0; k0 < ml; k0 += 32) { const uint32_t q = k0 + lane; if (q < ml) d[q] = sp[q]; __syncwarp(); } }
         else { for (uint32_t q = lane; q < ml; q += 32) d[q] = sp[q % of]; }
         __syncwarp();
     }
@@ -635,8 +637,10 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     pc.mark(PH_STAGE);
     if (CHAIN_LATE && tid >= NTH - 32) {
         if (hd.nseq <= FAST_ORDERED_MAX) { copy_run_tables(&hd, P.seq_pool, region, (uint32_t)tid & 31u, 32u); __syncwarp(); }
-        if (tid == NTH - 32) { const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
     }
+    // (the round trips for the next chunk index go to the warp in front of it: the planner's rounding of the sub-sequence
+    // length leaves the last warps with Huffman sub-sequences mostly idle)
+    if (CHAIN_LATE && tid == NTH - 64) { const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
     // frames with a few sequences over raw / RLE literals: the last warp (which the planner kept free of Huffman
     // sub-sequences) executes them now, off the critical path
     if (hd.early && (tid >> 5) == NTH / 32 - 1)
