@@ -431,7 +431,8 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     const uint32_t nth_h = (early || cls == CLS_B) ? nth - 32 : nth;      // class B: the last warp also fetches the CTA's next chunk index meanwhile
     uint32_t sub = nst ? (ttot + (nth_h - nst) - 1) / (nth_h - nst) : PLAN_SUB_MIN;
     if (sub < PLAN_SUB_MIN) sub = PLAN_SUB_MIN;
-    sub = ((sub + 31u) >> 5 | 1u) << 5;          // an odd number of 32-bit words: the lanes of a warp start in 32 different banks of the staged bitstream
+    if (cls == CLS_B) sub = ((sub + 31u) >> 5 | 1u) << 5;   // an odd number of 32-bit words: the lanes of a warp start in 32 different banks of the staged
+                                                            // bitstream (worth its rounding loss only where one CTA has the SM to itself)
     uint32_t first = 0;
     for (uint32_t s = 0; s < nst; ++s) { hd->st_first[s] = first; first += (hd->st[s].tbits + sub - 1) / sub; }
     for (uint32_t s = nst; s <= PLAN_MAX_STREAMS; ++s) hd->st_first[s] = first;
