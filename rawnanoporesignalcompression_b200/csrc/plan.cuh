@@ -19,7 +19,7 @@ constexpr int PLAN_MAX_HUF = 3;       // Huffman-coded literal sections per chun
 constexpr int PLAN_MAX_STREAMS = 4 * PLAN_MAX_HUF;
 constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
 constexpr uint32_t REGION_HEAD = 16;  // readable bytes in front of the staged chunk (bit-window over-read)
-constexpr uint32_t PLAN_SUB_MIN = 384;   // minimum Huffman sub-sequence length in bits
+constexpr uint32_t PLAN_SUB_MIN = 192;   // minimum Huffman sub-sequence length in bits
 constexpr uint32_t FAST_ORDERED_MAX = 64;   // chunks with at most this many sequences run them in order, one warp per frame
 
 enum : uint32_t { FK_RAW = 0, FK_RLE = 1, FK_COMP = 2 };
