@@ -16,7 +16,7 @@
 
 namespace rnsc {
 
-constexpr uint32_t FAST_WARM_BITS = 128;   // speculative warm-up before a sub-sequence
+constexpr uint32_t FAST_WARM_BITS = 256;   // speculative warm-up before a sub-sequence
 constexpr uint32_t FAST_NONE = 0xFFFFFFFFu;
 
 struct FastParams {
