@@ -303,7 +303,7 @@ rnsc_ctx* rnsc_create(int device)
                                            cudaEventCreateWithFlags(&c->lane[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_svb_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SvbWs) + 16 + SVB_STAGE_BYTES));
+    cudaError_t e2 = cudaSuccess;
     cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[2]);
     if (e1 == cudaSuccess) e1 = e3;
     e3 = cudaFuncSetAttribute(k_decode_fast<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[1]);
@@ -433,8 +433,13 @@ int rnsc_dev_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const 
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     if (c->d_sizes.reserve(5 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(sizes) failed");
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->sm_count * 8, nchunks));
-    if (nchunks) { RNSC_LAUNCH(k_svb_sizes, grid, NT, 0, st, codec, d_samples, d_sample_off, d_n, (uint32_t)nchunks, (uint32_t*)c->d_sizes.p); c->launches += 1; }
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)1 << 20, nchunks));   // one CTA per chunk: the hardware scheduler balances the sizes
+    if (nchunks) {
+#define RNSC_SIZES2(C) case C: RNSC_LAUNCH(k_svb_sizes2<C>, grid, P2_NT, 0, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, (uint32_t*)c->d_sizes.p); break
+        switch (codec) { RNSC_SIZES2(RNSC_VBZ); RNSC_SIZES2(RNSC_VBZ0); RNSC_SIZES2(RNSC_C1); RNSC_SIZES2(RNSC_C2); RNSC_SIZES2(RNSC_C3); RNSC_SIZES2(RNSC_C4); default: RNSC_SIZES2(RNSC_C5); }
+#undef RNSC_SIZES2
+        c->launches += 1;
+    }
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_sizes.p, (unsigned long long)(5 * nchunks), (unsigned long long*)d_stream_off);
     c->launches += 1;
     uint64_t total = 0;
@@ -442,8 +447,9 @@ int rnsc_dev_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const 
     CUDA_OK(cudaStreamSynchronize(st));
     if (total > streams_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "stream buffer too small: need %llu bytes, have %zu", (unsigned long long)total, streams_cap);
     if (nchunks) {
-        const size_t smem = ((sizeof(SvbWs) + 15) & ~(size_t)15) + SVB_STAGE_BYTES;
-        RNSC_LAUNCH(k_svb_pack, grid, NT, smem, st, codec, d_samples, d_sample_off, d_n, (uint32_t)nchunks, d_streams, (const uint64_t*)d_stream_off);
+#define RNSC_PACK2(C) case C: RNSC_LAUNCH(k_svb_pack2<C>, grid, P2_NT, (size_t)P2_STAGE_BYTES, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, d_streams, (const uint64_t*)d_stream_off); break
+        switch (codec) { RNSC_PACK2(RNSC_VBZ); RNSC_PACK2(RNSC_VBZ0); RNSC_PACK2(RNSC_C1); RNSC_PACK2(RNSC_C2); RNSC_PACK2(RNSC_C3); RNSC_PACK2(RNSC_C4); default: RNSC_PACK2(RNSC_C5); }
+#undef RNSC_PACK2
         c->launches += 1;
     }
     CUDA_OK(cudaGetLastError());

@@ -2,6 +2,7 @@
 #pragma once
 #include "zstd_decode.cuh"
 #include "svb_codec.cuh"
+#include "svb_pack2.cuh"
 #include "rc_codec.cuh"
 #include "plan.cuh"
 #include "fast_decode.cuh"
@@ -243,19 +244,48 @@ __global__ void __launch_bounds__(NT, 2) k_svb_pack(int codec, const int16_t* sa
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Device prefix scan that assigns output offsets: out[0] = 0, out[i+1] = out[i] + in[i].
-// One CTA walks the array tile by tile (count is ~5 x chunks: a few 100k at most).
+// Second-generation splitter kernels (svb_pack2.cuh): one CTA of P2_NT threads per chunk
 // ---------------------------------------------------------------------------------------------------
+template <int CODEC>
+__global__ void __launch_bounds__(P2_NT, 4) k_svb_sizes2(const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, uint32_t nchunks, uint32_t* sizes)
+{
+    __shared__ Pack2Ws<P2_NT> ws;
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x)
+        svb_sizes2<CODEC, P2_NT>(samples + sample_off[c], n[c], sizes + 5 * (size_t)c, &ws);
+}
+
+template <int CODEC>
+__global__ void __launch_bounds__(P2_NT, 4) k_svb_pack2(const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, uint32_t nchunks,
+                                                        uint8_t* streams, const uint64_t* stream_off)
+{
+    RNSC_DYN_SMEM(stage);
+    __shared__ Pack2Ws<P2_NT> ws;
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        if (threadIdx.x < 5) ws.dst[threadIdx.x] = streams + stream_off[5 * (size_t)c + threadIdx.x];
+        __syncthreads();
+        svb_pack2<CODEC, P2_NT>(samples + sample_off[c], n[c], ws.dst, &ws, stage);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device prefix scan that assigns output offsets: out[0] = 0, out[i+1] = out[i] + in[i].
+// One CTA walks the array, SCAN_ITEMS consecutive entries per thread per step (count is ~5 x chunks: a few 100k).
+// ---------------------------------------------------------------------------------------------------
+constexpr int SCAN_ITEMS = 16;
 __global__ void __launch_bounds__(NT, 1) k_exclusive_scan_u32(const uint32_t* in, unsigned long long count, unsigned long long* out)
 {
     __shared__ unsigned long long scratch[2][NWARP + 1];
     unsigned long long run = 0; int flip = 0;
-    for (unsigned long long base = 0; base < count; base += NT, flip ^= 1) {
-        const unsigned long long i = base + threadIdx.x;
-        const unsigned long long v = i < count ? in[i] : 0;
+    for (unsigned long long base = 0; base < count; base += (unsigned long long)NT * SCAN_ITEMS, flip ^= 1) {
+        const unsigned long long i0 = base + (unsigned long long)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = i0 + k < count ? in[i0 + k] : 0u; sum += v[k]; }
         unsigned long long tot;
-        const unsigned long long ex = block_exclusive_scan<unsigned long long>(v, scratch[flip], &tot);
-        if (i < count) out[i] = run + ex;
+        unsigned long long ex = run + block_exclusive_scan<unsigned long long>(sum, scratch[flip], &tot);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) { if (i0 + k < count) out[i0 + k] = ex; ex += v[k]; }
         run += tot;
     }
     if (threadIdx.x == 0) out[count] = run;

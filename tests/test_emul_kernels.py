@@ -99,3 +99,25 @@ def test_fuzz_corrupt_chunks_never_crash_and_agree_with_rfc_decoder(ecodec, orac
             assert (s != 0) == (ost != 0), (codec, s, ost)
             if ost == 0:
                 assert (o == oy).all()
+
+
+@pytest.mark.parametrize("codec", range(7))
+def test_splitter_encode_ragged_alignments(ecodec, oracle, codec):
+    """Second-generation splitter encode (svb_pack2.cuh): chunks back to back at every 16-byte phase, lengths around the
+    16-sample thread granule and the 4096-sample tile, class mixes from all-zero deltas to bursts of large values."""
+    lens = [1, 7, 8, 15, 16, 17, 33, 4095, 4096, 4097, 3, 12289, 2, 5000, 9, 8193]
+    chunks = []
+    for k, n in enumerate(lens):
+        kind = k % 4
+        if kind == 0: x = recipes.walk(n, 100 + k, 12.0)
+        elif kind == 1: x = recipes.extremes(n, 200 + k)
+        elif kind == 2: x = np.full(n, -7, np.int16)
+        else: x = recipes.walk(n, 300 + k, 3.0)
+        chunks.append(x)
+    comp, st = ecodec.compress_batch(chunks, codec)
+    want = [oracle.encode_status(codec, c) for c in chunks]
+    for got, s, (ws, wb), c in zip(comp, st, want, chunks):
+        if ws:
+            assert s != 0
+        else:
+            assert s == 0 and got == wb, (codec, len(c))

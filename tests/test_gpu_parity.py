@@ -139,7 +139,7 @@ def test_device_resident_api(gpu_codec, oracle):
         torch.cuda.synchronize()
         soff = d_soff.cpu().numpy()
         st_host = d_streams.cpu().numpy()
-        for i in (0, 1, nch - 1):
+        for i in range(nch):
             want = oracle.streams(codec, host[off[i] : off[i] + n[i]])
             got = [st_host[soff[5 * i + k] : soff[5 * i + k + 1]].tobytes() for k in range(5)]
             assert got == want, (NAMES[codec], i)
