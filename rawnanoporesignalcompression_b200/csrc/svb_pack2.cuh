@@ -16,6 +16,7 @@
 #pragma once
 #include "block_prims.cuh"
 #include "svb_codec.cuh"
+#include "svb_unpack2.cuh"
 
 namespace rnsc {
 
@@ -192,6 +193,23 @@ __device__ __forceinline__ void flush_nibbles(uint8_t* g, const uint8_t* st, uin
     }
 }
 
+// C4/C5: one sample's unit into the staging areas without a branch. t = the sample's two key bits in place, one = the
+// value of code 1 at that place; q1/q2/q3/q4 = running shared-memory addresses in the nibble, byte, low and high areas.
+__device__ __forceinline__ void scatter_c45(uint32_t t, uint32_t one, uint32_t v, saddr_t& q1, saddr_t& q2, saddr_t& q3, saddr_t& q4)
+{
+#ifdef RNSC_EMUL
+    if (t == one) { *(uint8_t*)q1 = (uint8_t)v; ++q1; }
+    else if (t == 2 * one) { *(uint8_t*)q2 = (uint8_t)v; ++q2; }
+    else if (t == 3 * one) { *(uint8_t*)q3 = (uint8_t)v; *(uint8_t*)q4 = (uint8_t)(v >> 8); ++q3; ++q4; }
+#else
+    asm volatile("{\n.reg .pred c1, c2, c3, c12;\n.reg .b32 a, h;\n"
+                 "setp.eq.u32 c1, %4, %5;\nsetp.eq.u32 c2, %4, %6;\nsetp.eq.u32 c3, %4, %7;\nor.pred c12, c1, c2;\n"
+                 "selp.b32 a, %0, %1, c1;\n@c12 st.shared.u8 [a], %8;\n@c1 add.u32 %0, %0, 1;\n@c2 add.u32 %1, %1, 1;\n"
+                 "@c3 shr.u32 h, %8, 8;\n@c3 st.shared.u8 [%2], %8;\n@c3 st.shared.u8 [%3], h;\n@c3 add.u32 %2, %2, 1;\n@c3 add.u32 %3, %3, 1;\n}"
+                 : "+r"(q1), "+r"(q2), "+r"(q3), "+r"(q4) : "r"(t), "r"(one), "r"(2u * one), "r"(3u * one), "r"(v) : "memory");
+#endif
+}
+
 // ---- pass 2: write the streams of a chunk at dst[0..4] (global; stream k gets exactly the size pass 1 reported) ------
 // `stage` = P2_STAGE_BYTES of shared memory, 16-byte aligned.
 template <int CODEC, int NTH>
@@ -268,6 +286,7 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
             }
         }
         // ---- scatter the units into the staging areas ----
+        saddr_t q1 = to_saddr(st1) + p1, q2 = to_saddr(st2) + p2, q3 = to_saddr(st3) + ph3 + p3, q4 = to_saddr(st4) + ph4 + p3;   // C4/C5
 #pragma unroll
         for (int j = 0; j < P2_SPT; ++j) {
             const uint32_t vv = v[j];
@@ -280,9 +299,7 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
             } else {
                 const uint32_t code = (kb >> (2 * j)) & 3u;           // samples past the end have code 0
                 if (CODEC == RNSC_VBZ0) { const uint32_t nn = nib_units(code); for (uint32_t q = 0; q < nn; ++q) st1[p1++] = (uint8_t)((vv >> (4 * q)) & 15u); }
-                else if (code == 1) st1[p1++] = (uint8_t)(vv & 15u);
-                else if (code == 2) st2[p2++] = (uint8_t)vv;
-                else if (code == 3) { st3[ph3 + p3] = (uint8_t)vv; st4[ph4 + p3] = (uint8_t)(vv >> 8); p3++; }
+                else scatter_c45(kb & (3u << (2 * j)), 1u << (2 * j), vv, q1, q2, q3, q4);
             }
         }
         __syncthreads();
