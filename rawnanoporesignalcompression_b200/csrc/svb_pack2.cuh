@@ -77,28 +77,66 @@ __device__ __forceinline__ void load16(const int16_t* in, uint32_t n, uint32_t i
     }
 }
 
+// zigzag of the 16-bit delta between two samples (zero-extended int16 bit patterns): svb16/encode_scalar.hpp:11-14,41-43
+__device__ __forceinline__ uint32_t delta_zigzag(uint32_t cur, uint32_t prev)
+{
+    const int32_t d = (int32_t)(int16_t)(uint16_t)(cur - prev);
+    return (uint32_t)((d << 1) ^ (d >> 31));                      // in [0, 65535]: no mask needed on a sign-extended delta
+}
+
+// One sample's class into the key bits (one = 1 << j or 1 << 2j) and, for VBZ0/C5 with WANT_V, the class offset out of zz.
+// Three compares, then predicated adds only: the key field receives +1 per threshold passed (C5.hpp:73-127, C4.hpp:69-121).
+template <int CODEC, bool WANT_V>
+__device__ __forceinline__ void classify_one(uint32_t& zz, uint32_t& kb, uint32_t one)
+{
+    constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
+#ifdef RNSC_EMUL
+    if (!TWO) { if (zz >= 256u) kb += one; }
+    else if (CODEC == RNSC_C4) kb += one * ((zz != 0u) + (zz >= 16u) + (zz >= 256u));
+    else { const uint32_t a = zz != 0u, b = zz > 16u, c = zz > 272u; kb += one * (a + b + c); if (WANT_V) zz -= a + 16u * b + 256u * c; }
+#else
+    if (!TWO) asm("{\n.reg .pred c;\nsetp.gt.u32 c, %1, 255;\n@c add.u32 %0, %0, %2;\n}" : "+r"(kb) : "r"(zz), "r"(one));
+    else if (CODEC == RNSC_C4)
+        asm("{\n.reg .pred a, b, c;\nsetp.ne.u32 a, %1, 0;\nsetp.gt.u32 b, %1, 15;\nsetp.gt.u32 c, %1, 255;\n"
+            "@a add.u32 %0, %0, %2;\n@b add.u32 %0, %0, %2;\n@c add.u32 %0, %0, %2;\n}" : "+r"(kb) : "r"(zz), "r"(one));
+    else if (!WANT_V)
+        asm("{\n.reg .pred a, b, c;\nsetp.ne.u32 a, %1, 0;\nsetp.gt.u32 b, %1, 16;\nsetp.gt.u32 c, %1, 272;\n"
+            "@a add.u32 %0, %0, %2;\n@b add.u32 %0, %0, %2;\n@c add.u32 %0, %0, %2;\n}" : "+r"(kb) : "r"(zz), "r"(one));
+    else
+        asm("{\n.reg .pred a, b, c;\nsetp.ne.u32 a, %1, 0;\nsetp.gt.u32 b, %1, 16;\nsetp.gt.u32 c, %1, 272;\n"
+            "@a add.u32 %0, %0, %2;\n@b add.u32 %0, %0, %2;\n@c add.u32 %0, %0, %2;\n"
+            "@a sub.u32 %1, %1, 1;\n@b sub.u32 %1, %1, 16;\n@c sub.u32 %1, %1, 256;\n}" : "+r"(kb), "+r"(zz) : "r"(one));
+#endif
+}
+
+// Pass 1: thresholds passed by one sample, counted straight into na/nb/nc (no key bits needed).
+template <int CODEC>
+__device__ __forceinline__ void count_one(uint32_t zz, uint32_t& na, uint32_t& nb, uint32_t& nc)
+{
+    constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
+    constexpr uint32_t TB = CODEC == RNSC_C4 ? 15u : 16u, TC = CODEC == RNSC_C4 ? 255u : 272u;
+#ifdef RNSC_EMUL
+    if (!TWO) nc += zz > 255u;
+    else { na += zz != 0u; nb += zz > TB; nc += zz > TC; }
+#else
+    if (!TWO) asm("{\n.reg .pred c;\nsetp.gt.u32 c, %1, 255;\n@c add.u32 %0, %0, 1;\n}" : "+r"(nc) : "r"(zz));
+    else asm("{\n.reg .pred a, b, c;\nsetp.ne.u32 a, %3, 0;\nsetp.gt.u32 b, %3, %4;\nsetp.gt.u32 c, %3, %5;\n"
+             "@a add.u32 %0, %0, 1;\n@b add.u32 %1, %1, 1;\n@c add.u32 %2, %2, 1;\n}" : "+r"(na), "+r"(nb), "+r"(nc) : "r"(zz), "n"(TB), "n"(TC));
+#endif
+}
+
 // delta + zigzag + classify of the thread's 16 samples. Returns the key bits (1 or 2 per sample, sample j at bit j or
 // 2j); v[j] = the payload value of sample j (class offset removed for VBZ0/C5).
-template <int CODEC, bool WANT_V>
+template <int CODEC>
 __device__ __forceinline__ uint32_t classify16(const uint32_t s[P2_SPT], uint32_t prev, uint32_t v[P2_SPT])
 {
     constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
     uint32_t kb = 0;
 #pragma unroll
     for (int j = 0; j < P2_SPT; ++j) {
-        const uint32_t zz = zigzag_enc16((s[j] - prev) & 0xFFFFu); prev = s[j];
-        if (!TWO) {
-            kb |= (zz >= 256u ? 1u : 0u) << j;
-            if (WANT_V) v[j] = zz;
-        } else if (CODEC == RNSC_C4) {
-            const uint32_t code = (zz != 0u) + (zz >= 16u) + (zz >= 256u);
-            kb |= code << (2 * j);
-            if (WANT_V) v[j] = zz;
-        } else {   // VBZ0 / C5: classes 0 | 1..16 | 17..272 | 273.. with the class offset removed
-            const uint32_t a = zz != 0u, b = zz > 16u, c = zz > 272u;
-            kb |= (a + b + c) << (2 * j);
-            if (WANT_V) v[j] = zz - (a + 16u * b + 256u * c);
-        }
+        uint32_t zz = delta_zigzag(s[j], prev); prev = s[j];
+        classify_one<CODEC, true>(zz, kb, TWO ? 1u << (2 * j) : 1u << j);
+        v[j] = zz;
     }
     return kb;
 }
@@ -138,23 +176,29 @@ __device__ __forceinline__ void svb_sizes2(const int16_t* in, uint32_t n, uint32
 {
     constexpr int NW = NTH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t r1 = 0, r2 = 0, r3 = 0;
+    constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
+    uint32_t na = 0, nb = 0, nc = 0;                                  // samples past each class threshold
     for (uint32_t tb = 0; tb < n; tb += NTH * P2_SPT) {
         const uint32_t i0 = tb + (uint32_t)tid * P2_SPT;
         const uint32_t cnt = i0 < n ? min((uint32_t)P2_SPT, n - i0) : 0u;
         if (cnt == 0) continue;
-        uint32_t s[P2_SPT], prev, c1, c2, c3;
+        uint32_t s[P2_SPT], prev;
         load16(in, n, i0, cnt, s, prev);
-        const uint32_t kb = classify16<CODEC, false>(s, prev, nullptr);
-        unit_counts<CODEC>(kb, cnt, c1, c2, c3);
-        r1 += c1; r2 += c2; r3 += c3;
+#pragma unroll
+        for (int j = 0; j < P2_SPT; ++j) { count_one<CODEC>(delta_zigzag(s[j], prev), na, nb, nc); prev = s[j]; }   // past the end: zz = 0
     }
+    uint32_t r1, r2, r3;                                              // per-thread unit counts; the n valid samples are added at the end
+    if (TWO) { const uint32_t n1 = na - nb, n2 = nb - nc; if (CODEC == RNSC_VBZ0) { r1 = n1 + 2 * n2 + 4 * nc; r2 = r3 = 0; } else { r1 = n1; r2 = n2; r3 = nc; } }
+    else { r1 = 0; r2 = nc; r3 = 0; }
     r1 = __reduce_add_sync(0xffffffffu, r1); r2 = __reduce_add_sync(0xffffffffu, r2); r3 = __reduce_add_sync(0xffffffffu, r3);
     if (lane == 0) { ws->red[0][warp] = r1; ws->red[1][warp] = r2; ws->red[2][warp] = r3; }
     __syncthreads();
     if (tid == 0) {
         uint32_t t1 = 0, t2 = 0, t3 = 0;
         for (int w = 0; w < NW; ++w) { t1 += ws->red[0][w]; t2 += ws->red[1][w]; t3 += ws->red[2][w]; }
+        if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) { t1 = n + t2; t2 = 0; }           // one byte per sample + one per large value
+        else if (CODEC == RNSC_C2) t1 = n;
+        else if (CODEC == RNSC_C3) t1 = n - t2;
         stream_sizes(CODEC, n, t1, t2, t3, sizes);
     }
     __syncthreads();
@@ -236,7 +280,7 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
         if (cnt) {
             uint32_t s[P2_SPT], prev;
             load16(in, n, i0, cnt, s, prev);
-            kb = classify16<CODEC, true>(s, prev, v);
+            kb = classify16<CODEC>(s, prev, v);
             unit_counts<CODEC>(kb, cnt, c1, c2, c3);
         }
         // ---- one barrier: scan of the unit counts; it also separates the previous tile's flush from this tile's scatter
