@@ -199,50 +199,6 @@ __global__ void __launch_bounds__(NT, 2) k_svb_unpack(int codec, const uint8_t* 
     }
 }
 
-template <bool COUNT_ONLY>
-__device__ inline void pack_any(int codec, const int16_t* in, uint32_t n, uint8_t* const* dst, uint32_t* sizes, SvbWs* ws, uint8_t* stage)
-{
-    switch (codec) {
-    case RNSC_VBZ: svb_pack<RNSC_VBZ, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
-    case RNSC_VBZ0: svb_pack<RNSC_VBZ0, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
-    case RNSC_C1: svb_pack<RNSC_C1, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
-    case RNSC_C2: svb_pack<RNSC_C2, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
-    case RNSC_C3: svb_pack<RNSC_C3, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
-    case RNSC_C4: svb_pack<RNSC_C4, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
-    default: svb_pack<RNSC_C5, COUNT_ONLY>(in, n, dst, sizes, ws, stage); break;
-    }
-}
-
-// pass 1: stream sizes of every chunk (5 x u32 per chunk)
-__global__ void __launch_bounds__(NT, 2) k_svb_sizes(int codec, const int16_t* samples, const uint64_t* sample_off, const uint32_t* n,
-                                                     uint32_t nchunks, uint32_t* sizes)
-{
-    __shared__ SvbWs ws;
-    __shared__ uint32_t sz[5];
-    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        __syncthreads();
-        pack_any<true>(codec, samples + sample_off[c], n[c], nullptr, sz, &ws, nullptr);
-        if (threadIdx.x < 5) sizes[5 * (size_t)c + threadIdx.x] = sz[threadIdx.x];
-    }
-}
-
-// pass 2: scatter into the compact stream buffer at the scanned offsets
-__global__ void __launch_bounds__(NT, 2) k_svb_pack(int codec, const int16_t* samples, const uint64_t* sample_off, const uint32_t* n,
-                                                    uint32_t nchunks, uint8_t* streams, const uint64_t* stream_off)
-{
-    RNSC_DYN_SMEM(smem);
-    SvbWs* ws = (SvbWs*)smem;
-    uint8_t* stage = smem + ((sizeof(SvbWs) + 15) & ~(size_t)15);
-    __shared__ uint8_t* dst[5];
-    __shared__ uint32_t sz[5];
-    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        __syncthreads();
-        if (threadIdx.x < 5) dst[threadIdx.x] = streams + stream_off[5 * (size_t)c + threadIdx.x];
-        __syncthreads();
-        pack_any<false>(codec, samples + sample_off[c], n[c], dst, sz, ws, stage);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Second-generation splitter kernels (svb_pack2.cuh): one CTA of P2_NT threads per chunk
 // ---------------------------------------------------------------------------------------------------

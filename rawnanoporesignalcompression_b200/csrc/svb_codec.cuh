@@ -1,5 +1,6 @@
-// svb_codec.cuh -- the splitter stage of every codec (delta + zigzag + classify + scatter/gather), one CTA
-// per chunk, NT threads x SPT consecutive samples per tile.
+// svb_codec.cuh -- the general splitter inverse of every codec (gather + zigzag^-1 + delta^-1), one CTA per chunk,
+// NT threads x SPT consecutive samples per tile; works on generic (shared or global) stream pointers. The fast decoder
+// uses svb_unpack2.cuh, the encoder svb_pack2.cuh.
 //
 // Reference (scalar, one sample at a time):
 //   VBZ  svb16/encode_scalar.hpp:17-66, decode_scalar.hpp:36-75       VBZ0 pgnano/svb16/VBZ_0.hpp:61-172,186-290
@@ -23,24 +24,8 @@ struct SvbWs {
     alignas(16) int16_t tile[TILE + 16];   // sample tile, phase-shifted to the global 16-byte alignment
     int err;
 };
-constexpr int SVB_STAGE_BYTES = 4 * TILE + 16;   // encode only: per-stream staging (nibble streams: one nibble per byte)
 
-// ---- tile <-> global, 16-byte vectors in the aligned body, scalars at the ragged ends ----------------
-// Loads m samples starting at g (2-byte aligned) into tile[phase + i]; returns phase. Also loads the
-// sample before g into tile[phase - 1] when has_prev (tile index space is shifted by 8 so phase-1 >= 0).
-__device__ inline int tile_load(int16_t* tile, const int16_t* g, uint32_t m, bool has_prev)
-{
-    const int phase = (int)(((uintptr_t)g >> 1) & 7) + 8;
-    const int16_t* g0 = g - phase;                        // tile[i] <-> g0[i], g0 16-byte aligned
-    const int ngroups = (phase + (int)m + 7) >> 3;
-    for (int grp = threadIdx.x + 1; grp < ngroups; grp += NT) {   // group 0 is entirely before phase
-        const int lo = grp * 8;
-        if (lo >= phase && lo + 8 <= phase + (int)m) *(V16*)(tile + lo) = *(const V16*)(g0 + lo);
-        else for (int i = lo; i < lo + 8; ++i) if (i >= phase && i < phase + (int)m) tile[i] = g0[i];
-    }
-    if (threadIdx.x == 0) tile[phase - 1] = has_prev ? g[-1] : (int16_t)0;
-    return phase;
-}
+// ---- tile -> global, 16-byte vectors in the aligned body, scalars at the ragged ends; tile[phase + i] <-> g[i] ----
 __device__ inline void tile_store(const int16_t* tile, int16_t* g, uint32_t m, int phase)
 {
     int16_t* g0 = g - phase;
@@ -157,118 +142,6 @@ __device__ int svb_unpack(const View* v, uint32_t n, int16_t* out, SvbWs* ws)
     if (oob || (tid == 0 && rem)) ws->err = RNSC_ERR_REMAINING;
     __syncthreads();
     return ws->err;
-}
-
-// =====================================================================================================
-// encode: samples -> streams
-// =====================================================================================================
-// COUNT_ONLY: returns the 5 stream sizes in sizes[] (thread 0 writes). Otherwise also writes the streams
-// at dst[k] (global pointers; stream k holds exactly sizes[k] bytes).
-template <int CODEC, bool COUNT_ONLY>
-__device__ void svb_pack(const int16_t* in, uint32_t n, uint8_t* const* dst, uint32_t* sizes, SvbWs* ws, uint8_t* stage)
-{
-    constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
-    constexpr bool NIB1 = TWO;                 // stream 1 is a nibble stream
-    const int tid = threadIdx.x;
-    uint32_t run1 = 0, run2 = 0, run3 = 0;     // units written so far (stream 1: nibbles when NIB1)
-    uint8_t* st1 = stage;                      // SVB_STAGE_BYTES of shared memory, layout per codec
-    uint8_t* st2 = stage + (CODEC == RNSC_VBZ || CODEC == RNSC_C1 ? 2 * TILE : TILE + 8);
-    uint8_t* st3 = st2 + TILE;
-    uint8_t* st4 = st3 + TILE;
-    for (uint32_t tb = 0; tb < n; tb += TILE) {
-        const uint32_t m = min((uint32_t)TILE, n - tb);
-        __syncthreads();
-        const int phase = tile_load(ws->tile, in + tb, m, tb > 0);
-        __syncthreads();
-        const uint32_t i0 = tb + (uint32_t)tid * SPT;
-        const int cnt = i0 < n ? (int)min((uint32_t)SPT, n - i0) : 0;
-        uint32_t z[SPT]; uint32_t kb = 0, c1 = 0, c2 = 0, c3 = 0;
-        uint32_t prev = cnt > 0 ? (uint16_t)ws->tile[phase + tid * SPT - 1] : 0;
-#pragma unroll
-        for (int j = 0; j < SPT; ++j) {
-            z[j] = 0;
-            if (j < cnt) {
-                const uint32_t x = (uint16_t)ws->tile[phase + tid * SPT + j];
-                const uint32_t zz = zigzag_enc16((x - prev) & 0xFFFFu); prev = x;
-                if (!TWO) {
-                    const uint32_t k = zz >= 256;
-                    kb |= k << j; z[j] = zz;
-                    if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) c1 += 1 + k;
-                    else if (CODEC == RNSC_C2) { c1 += 1; c2 += k; }
-                    else { c1 += 1 - k; c2 += k; }
-                } else {
-                    uint32_t code, vv = zz;
-                    if (CODEC == RNSC_C4) code = zz == 0 ? 0u : (zz < 16 ? 1u : (zz < 256 ? 2u : 3u));
-                    else if (zz == 0) code = 0;
-                    else if (zz <= 16) { code = 1; vv = zz - 1; }
-                    else if (zz <= 272) { code = 2; vv = zz - 17; }
-                    else { code = 3; vv = zz - 273; }
-                    kb |= code << (2 * j); z[j] = vv;
-                    if (CODEC == RNSC_VBZ0) c1 += nib_units(code);
-                    else { c1 += code == 1; c2 += code == 2; c3 += code == 3; }
-                }
-            }
-        }
-        unsigned long long tot64;
-        const unsigned long long ex64 = block_exclusive_scan<unsigned long long>(
-            (unsigned long long)c1 | ((unsigned long long)c2 << 20) | ((unsigned long long)c3 << 40), ws->scan64_a, &tot64);
-        const uint32_t t1 = (uint32_t)(tot64 & 0xFFFFF), t2 = (uint32_t)((tot64 >> 20) & 0xFFFFF), t3 = (uint32_t)(tot64 >> 40);
-        if (!COUNT_ONLY) {
-            const uint32_t par = NIB1 ? (run1 & 1u) : 0u;   // a pending low nibble sits in st1[0]
-            uint32_t p1 = par + (uint32_t)(ex64 & 0xFFFFF), p2 = (uint32_t)((ex64 >> 20) & 0xFFFFF), p3 = (uint32_t)(ex64 >> 40);
-            // keys: one (1-bit) or two (2-bit) bytes per thread, straight to global
-            if (cnt > 0) {
-                if (TWO) { dst[0][i0 >> 2] = (uint8_t)kb; if (cnt > 4) dst[0][(i0 >> 2) + 1] = (uint8_t)(kb >> 8); }
-                else dst[0][i0 >> 3] = (uint8_t)kb;
-            }
-#pragma unroll
-            for (int j = 0; j < SPT; ++j) {
-                if (j < cnt) {
-                    const uint32_t vv = z[j];
-                    if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) { st1[p1++] = (uint8_t)vv; if ((kb >> j) & 1) st1[p1++] = (uint8_t)(vv >> 8); }
-                    else if (CODEC == RNSC_C2) { st1[p1++] = (uint8_t)vv; if ((kb >> j) & 1) st2[p2++] = (uint8_t)(vv >> 8); }
-                    else if (CODEC == RNSC_C3) { if ((kb >> j) & 1) { st2[p2] = (uint8_t)vv; st3[p2] = (uint8_t)(vv >> 8); p2++; } else st1[p1++] = (uint8_t)vv; }
-                    else {
-                        const uint32_t code = (kb >> (2 * j)) & 3;
-                        if (CODEC == RNSC_VBZ0) { const uint32_t nn = nib_units(code); for (uint32_t q = 0; q < nn; ++q) st1[p1++] = (uint8_t)((vv >> (4 * q)) & 15u); }
-                        else if (code == 1) st1[p1++] = (uint8_t)(vv & 15u);
-                        else if (code == 2) st2[p2++] = (uint8_t)vv;
-                        else if (code == 3) { st3[p3] = (uint8_t)vv; st4[p3] = (uint8_t)(vv >> 8); p3++; }
-                    }
-                }
-            }
-            __syncthreads();
-            // flush staged units to global, coalesced
-            if (NIB1) {
-                const uint32_t tot = par + t1, full = tot >> 1, gbase = run1 >> 1;   // complete bytes already written
-                for (uint32_t i = tid; i < full; i += NT) dst[1][gbase + i] = (uint8_t)(st1[2 * i] | (st1[2 * i + 1] << 4));
-                __syncthreads();
-                if (tid == 0 && (tot & 1u)) st1[0] = st1[tot - 1];   // keep the odd nibble for the next tile
-            } else {
-                for (uint32_t i = tid; i < t1; i += NT) dst[1][run1 + i] = st1[i];
-            }
-            if (CODEC == RNSC_C2) for (uint32_t i = tid; i < t2; i += NT) dst[2][run2 + i] = st2[i];
-            if (CODEC == RNSC_C3) for (uint32_t i = tid; i < t2; i += NT) { dst[2][run2 + i] = st2[i]; dst[3][run2 + i] = st3[i]; }
-            if (CODEC == RNSC_C4 || CODEC == RNSC_C5) {
-                for (uint32_t i = tid; i < t2; i += NT) dst[2][run2 + i] = st2[i];
-                for (uint32_t i = tid; i < t3; i += NT) { dst[3][run3 + i] = st3[i]; dst[4][run3 + i] = st4[i]; }
-            }
-        }
-        run1 += t1; run2 += t2; run3 += t3;
-    }
-    __syncthreads();
-    if (!COUNT_ONLY && NIB1 && tid == 0 && (run1 & 1u)) dst[1][run1 >> 1] = stage[0];   // trailing half byte
-    if (tid == 0) {
-        const uint32_t kl = key_len(CODEC, n);
-        uint32_t s[5] = {kl, 0, 0, 0, 0};
-        if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) s[1] = run1;
-        else if (CODEC == RNSC_VBZ0) s[1] = (run1 + 1) >> 1;
-        else if (CODEC == RNSC_C2) { s[1] = run1; s[2] = run2; }
-        else if (CODEC == RNSC_C3) { s[1] = run1; s[2] = run2; s[3] = run2; }
-        else { s[1] = (run1 + 1) >> 1; s[2] = run2; s[3] = run3; s[4] = run3; }
-        for (int k = 0; k < 5; ++k) sizes[k] = s[k];
-    }
-    __syncthreads();
 }
 
 }  // namespace rnsc
