@@ -15,6 +15,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -153,6 +154,7 @@ struct rnsc_ctx {
     cudaStream_t hi = nullptr;                             // high priority: the general decoder must get its SMs before the persistent CTAs fill them (see launch_decode)
     cudaEvent_t ev_plan = nullptr, ev_hi = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
     PinBuf h_a, h_b;
+    uint8_t* h_arena = nullptr; size_t h_arena_cap = 0;   // frames of the host zstd stage before compaction (grow-only)
 };
 
 namespace {
@@ -334,6 +336,7 @@ void rnsc_destroy(rnsc_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin}) b->release();
     c->h_a.release(); c->h_b.release();
+    free(c->h_arena); c->h_arena = nullptr; c->h_arena_cap = 0;
     if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); } if (c->ev_hi) cudaEventDestroy(c->ev_hi);
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);
@@ -634,43 +637,59 @@ int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const ui
     // ---- zstd frame stage on host threads (byte-identical with the reference's ZSTD_compress(.., 1)) ----
     const uint8_t* hs = (const uint8_t*)c->h_a.p;
     const int nf = codec_frames(codec);
-    std::vector<std::vector<uint8_t>> outs(nchunks);
     Zstd& z = zstd();
+    // one slot per chunk in a grow-only host arena (worst-case frame sizes), then a parallel compaction into `comp`:
+    // no per-chunk allocation, no serial copy
+    std::vector<uint64_t> slot(nchunks + 1);
+    std::vector<uint32_t> csize(nchunks);
+    uint64_t arena_need = 0;
+    for (size_t i = 0; i < nchunks; ++i) {
+        slot[i] = arena_need;
+        if (nf == 1) arena_need += rnsc_max_compressed_size(codec, n[i]);
+        else for (int f = 0; f < nf; ++f) arena_need += z.bound((size_t)(stoff[5 * i + f + 1] - stoff[5 * i + f])) + 8;
+    }
+    slot[nchunks] = arena_need;
+    if (arena_need > c->h_arena_cap) {
+        free(c->h_arena);
+        c->h_arena = (uint8_t*)malloc(arena_need + 64);
+        c->h_arena_cap = c->h_arena ? arena_need : 0;
+        if (!c->h_arena) return fail(RNSC_ERR_NO_DEVICE, "malloc(frame arena %llu) failed", (unsigned long long)arena_need);
+    }
+    uint8_t* const arena = c->h_arena;
     parallel_for(nchunks, c->host_threads, [&](size_t i) {
         const uint64_t* so = &stoff[5 * i];
-        std::vector<uint8_t>& o = outs[i];
+        uint8_t* o = arena + slot[i];
+        const size_t need = (size_t)(slot[i + 1] - slot[i]);
         const size_t cap = rnsc_max_compressed_size(codec, n[i]);
-        status[i] = RNSC_OK;
-        if (nf == 1) {       // keys||data are adjacent in the stream buffer: one frame straight into the destination
-            o.resize(cap);
-            size_t cs = z.compress(o.data(), cap, hs + so[0], (size_t)(so[2] - so[0]), 1);
-            if (z.is_error(cs)) { status[i] = RNSC_ERR_ZSTD_ENCODE; o.clear(); } else o.resize(cs);
+        status[i] = RNSC_OK; csize[i] = 0;
+        if (nf == 1) {       // keys||data are adjacent in the stream buffer: one frame
+            size_t cs = z.compress(o, cap, hs + so[0], (size_t)(so[2] - so[0]), 1);
+            if (z.is_error(cs)) status[i] = RNSC_ERR_ZSTD_ENCODE; else csize[i] = (uint32_t)cs;
             return;
         }
-        size_t need = 0;
-        for (int f = 0; f < nf; ++f) need += z.bound((size_t)(so[f + 1] - so[f])) + 8;
-        o.resize(need);
         size_t op = 0;
         for (int f = 0; f < nf; ++f) {
             const size_t len = (size_t)(so[f + 1] - so[f]);
             const size_t hdr = f + 1 < nf ? 8 : 0;
-            size_t cs = z.compress(o.data() + op + hdr, need - op - hdr, hs + so[f], len, 1);
-            if (z.is_error(cs)) { status[i] = RNSC_ERR_ZSTD_ENCODE; o.clear(); return; }
-            if (hdr) { uint64_t v = cs; memcpy(o.data() + op, &v, 8); }
+            size_t cs = z.compress(o + op + hdr, need - op - hdr, hs + so[f], len, 1);
+            if (z.is_error(cs)) { status[i] = RNSC_ERR_ZSTD_ENCODE; return; }
+            if (hdr) { uint64_t v = cs; memcpy(o + op, &v, 8); }
             op += hdr + cs;
         }
         // destination capacity max(2n+26,1024): C4/C5 report it (C5.hpp:420-427); C1-C3 overrun in the
         // reference, which is reported as the same error here.
-        if (op > cap) { status[i] = RNSC_ERR_DST_TOO_SMALL; o.clear(); return; }
-        o.resize(op);
+        if (op > cap) { status[i] = RNSC_ERR_DST_TOO_SMALL; return; }
+        csize[i] = (uint32_t)op;
     });
     uint64_t op = 0;
-    for (size_t i = 0; i < nchunks; ++i) {
-        comp_off[i] = op;
-        if (op + outs[i].size() > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need more than %zu bytes", comp_cap);
-        if (!outs[i].empty()) memcpy(comp + op, outs[i].data(), outs[i].size());
-        op += outs[i].size();
-    }
+    for (size_t i = 0; i < nchunks; ++i) { comp_off[i] = op; op += csize[i]; }
+    if (op > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need %llu bytes, have %zu", (unsigned long long)op, comp_cap);
+    const size_t group = 64;                                         // chunks per copy task
+    parallel_for((nchunks + group - 1) / group, c->host_threads, [&](size_t g) {
+        for (size_t i = g * group; i < std::min(nchunks, (g + 1) * group); ++i)
+            if (csize[i]) memcpy(comp + comp_off[i], arena + slot[i], csize[i]);
+    });
+    if (c->h_arena_cap > ((size_t)512 << 20)) { free(c->h_arena); c->h_arena = nullptr; c->h_arena_cap = 0; }   // keep only a modest arena between calls
     comp_off[nchunks] = op;
     return RNSC_OK;
 }
