@@ -154,7 +154,6 @@ struct rnsc_ctx {
     cudaStream_t hi = nullptr;                             // high priority: the general decoder must get its SMs before the persistent CTAs fill them (see launch_decode)
     cudaEvent_t ev_plan = nullptr, ev_hi = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
     PinBuf h_a, h_b;
-    uint8_t* h_arena = nullptr; size_t h_arena_cap = 0;   // frames of the host zstd stage before compaction (grow-only)
 };
 
 namespace {
@@ -336,7 +335,6 @@ void rnsc_destroy(rnsc_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin}) b->release();
     c->h_a.release(); c->h_b.release();
-    free(c->h_arena); c->h_arena = nullptr; c->h_arena_cap = 0;
     if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); } if (c->ev_hi) cudaEventDestroy(c->ev_hi);
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);
@@ -579,20 +577,19 @@ int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const ui
     std::lock_guard<std::mutex> lk(c->mu);
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     cudaStream_t st = c->stream;
-    std::vector<uint64_t> soff(nchunks + 1);
-    uint64_t sb = 0;
-    for (size_t i = 0; i < nchunks; ++i) { soff[i] = sb; sb += n[i]; }
-    soff[nchunks] = sb;
-    if (c->d_samples.reserve(sb * 2 + 64) || c->d_off_b.reserve((nchunks + 1) * 8) || c->d_n.reserve(nchunks * 4 + 16) || c->d_status.reserve(nchunks * 4 + 16))
-        return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
-    bool dense = true;
-    for (size_t i = 0; i < nchunks; ++i) if (sample_off[i] - sample_off[0] != soff[i]) { dense = false; break; }
-    if (dense) CUDA_OK(cudaMemcpyAsync(c->d_samples.p, samples + sample_off[0], sb * 2, cudaMemcpyHostToDevice, st));
-    else for (size_t i = 0; i < nchunks; ++i) if (n[i]) CUDA_OK(cudaMemcpyAsync((int16_t*)c->d_samples.p + soff[i], samples + sample_off[i], (size_t)n[i] * 2, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(c->d_off_b.p, soff.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
-    CUDA_OK(cudaMemcpyAsync(c->d_n.p, n, nchunks * 4, cudaMemcpyHostToDevice, st));
-
     if (codec == RNSC_RC) {
+        std::vector<uint64_t> soff(nchunks + 1);
+        uint64_t sb = 0;
+        for (size_t i = 0; i < nchunks; ++i) { soff[i] = sb; sb += n[i]; }
+        soff[nchunks] = sb;
+        if (c->d_samples.reserve(sb * 2 + 64) || c->d_off_b.reserve((nchunks + 1) * 8) || c->d_n.reserve(nchunks * 4 + 16) || c->d_status.reserve(nchunks * 4 + 16))
+            return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
+        bool dense = true;
+        for (size_t i = 0; i < nchunks; ++i) if (sample_off[i] - sample_off[0] != soff[i]) { dense = false; break; }
+        if (dense) CUDA_OK(cudaMemcpyAsync(c->d_samples.p, samples + sample_off[0], sb * 2, cudaMemcpyHostToDevice, st));
+        else for (size_t i = 0; i < nchunks; ++i) if (n[i]) CUDA_OK(cudaMemcpyAsync((int16_t*)c->d_samples.p + soff[i], samples + sample_off[i], (size_t)n[i] * 2, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(c->d_off_b.p, soff.data(), (nchunks + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(c->d_n.p, n, nchunks * 4, cudaMemcpyHostToDevice, st));
         std::vector<uint64_t> slot(nchunks + 1);
         uint64_t tot = 0;
         for (size_t i = 0; i < nchunks; ++i) { slot[i] = tot; tot += (rnsc_max_compressed_size(RNSC_RC, n[i]) + 24 + 15) & ~(size_t)15; }
@@ -620,76 +617,115 @@ int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const ui
         return RNSC_OK;
     }
 
-    // ---- splitter stage on the device ----
-    uint64_t scap = 0;
-    for (size_t i = 0; i < nchunks; ++i) scap += stream_bound(codec, n[i]);
-    if (c->d_streams.reserve(scap + 64) || c->d_stream_off.reserve((5 * nchunks + 1) * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(streams) failed");
-    int r = rnsc_dev_svb_encode(c, codec, (const int16_t*)c->d_samples.p, (const uint64_t*)c->d_off_b.p, (const uint32_t*)c->d_n.p, nchunks,
-                                (uint8_t*)c->d_streams.p, scap, (uint64_t*)c->d_stream_off.p, st);
-    if (r) return r;
-    std::vector<uint64_t> stoff(5 * nchunks + 1);
-    CUDA_OK(cudaMemcpyAsync(stoff.data(), c->d_stream_off.p, stoff.size() * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    const uint64_t total = stoff[5 * nchunks];
-    if (c->h_a.reserve(total + 64)) return fail(RNSC_ERR_NO_DEVICE, "cudaMallocHost(streams) failed");
-    CUDA_OK(cudaMemcpyAsync(c->h_a.p, c->d_streams.p, total, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    // ---- zstd frame stage on host threads (byte-identical with the reference's ZSTD_compress(.., 1)) ----
-    const uint8_t* hs = (const uint8_t*)c->h_a.p;
+    // ---- sliced pipeline: while the host threads run the zstd frame stage of slice k, this thread stages slice k+1
+    //      (H2D, splitter kernels, D2H of the streams into the other pinned buffer) ----
     const int nf = codec_frames(codec);
     Zstd& z = zstd();
-    // one slot per chunk in a grow-only host arena (worst-case frame sizes), then a parallel compaction into `comp`:
-    // no per-chunk allocation, no serial copy
-    std::vector<uint64_t> slot(nchunks + 1);
-    std::vector<uint32_t> csize(nchunks);
-    uint64_t arena_need = 0;
-    for (size_t i = 0; i < nchunks; ++i) {
-        slot[i] = arena_need;
-        if (nf == 1) arena_need += rnsc_max_compressed_size(codec, n[i]);
-        else for (int f = 0; f < nf; ++f) arena_need += z.bound((size_t)(stoff[5 * i + f + 1] - stoff[5 * i + f])) + 8;
-    }
-    slot[nchunks] = arena_need;
-    if (arena_need > c->h_arena_cap) {
-        free(c->h_arena);
-        c->h_arena = (uint8_t*)malloc(arena_need + 64);
-        c->h_arena_cap = c->h_arena ? arena_need : 0;
-        if (!c->h_arena) return fail(RNSC_ERR_NO_DEVICE, "malloc(frame arena %llu) failed", (unsigned long long)arena_need);
-    }
-    uint8_t* const arena = c->h_arena;
-    parallel_for(nchunks, c->host_threads, [&](size_t i) {
-        const uint64_t* so = &stoff[5 * i];
-        uint8_t* o = arena + slot[i];
-        const size_t need = (size_t)(slot[i + 1] - slot[i]);
-        const size_t cap = rnsc_max_compressed_size(codec, n[i]);
-        status[i] = RNSC_OK; csize[i] = 0;
-        if (nf == 1) {       // keys||data are adjacent in the stream buffer: one frame
-            size_t cs = z.compress(o, cap, hs + so[0], (size_t)(so[2] - so[0]), 1);
-            if (z.is_error(cs)) status[i] = RNSC_ERR_ZSTD_ENCODE; else csize[i] = (uint32_t)cs;
-            return;
+    struct SliceJob { size_t c0 = 0, c1 = 0; std::vector<uint64_t> stoff, slot; uint8_t* arena = nullptr; std::thread th; };
+    std::vector<size_t> cut{0};
+    { uint64_t acc = 0; for (size_t i = 0; i < nchunks; ++i) { if (acc && acc + n[i] > slice_samples()) { cut.push_back(i); acc = 0; } acc += n[i]; } }
+    cut.push_back(nchunks);
+    const size_t nsl = cut.size() - 1;
+    std::vector<SliceJob> jobs(nsl);
+    std::vector<uint32_t> csize(nchunks, 0);
+    PinBuf* hb[2] = {&c->h_a, &c->h_b};
+    auto join_all = [&] { for (auto& j : jobs) { if (j.th.joinable()) j.th.join(); } };
+    auto free_all = [&] { for (auto& j : jobs) { free(j.arena); j.arena = nullptr; } };
+    int rc = RNSC_OK;
+    for (size_t k = 0; k < nsl && rc == RNSC_OK; ++k) {
+        SliceJob& J = jobs[k];
+        J.c0 = cut[k]; J.c1 = cut[k + 1];
+        const size_t m = J.c1 - J.c0;
+        const uint32_t* nn = n + J.c0;
+        std::vector<uint64_t> soff(m + 1);
+        uint64_t sb = 0, scap = 0;
+        bool dense = true;
+        for (size_t i = 0; i < m; ++i) { soff[i] = sb; sb += nn[i]; scap += stream_bound(codec, nn[i]); if (sample_off[J.c0 + i] - sample_off[J.c0] != soff[i]) dense = false; }
+        soff[m] = sb;
+        if (c->d_samples.reserve(sb * 2 + 64) || c->d_off_b.reserve((m + 1) * 8) || c->d_n.reserve(m * 4 + 16) || c->d_streams.reserve(scap + 64) || c->d_stream_off.reserve((5 * m + 1) * 8)) {
+            rc = fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed"); break;
         }
-        size_t op = 0;
-        for (int f = 0; f < nf; ++f) {
-            const size_t len = (size_t)(so[f + 1] - so[f]);
-            const size_t hdr = f + 1 < nf ? 8 : 0;
-            size_t cs = z.compress(o + op + hdr, need - op - hdr, hs + so[f], len, 1);
-            if (z.is_error(cs)) { status[i] = RNSC_ERR_ZSTD_ENCODE; return; }
-            if (hdr) { uint64_t v = cs; memcpy(o + op, &v, 8); }
-            op += hdr + cs;
+        cudaError_t e = cudaSuccess;
+        if (dense) e = cudaMemcpyAsync(c->d_samples.p, samples + sample_off[J.c0], sb * 2, cudaMemcpyHostToDevice, st);
+        else for (size_t i = 0; i < m && e == cudaSuccess; ++i) if (nn[i]) e = cudaMemcpyAsync((int16_t*)c->d_samples.p + soff[i], samples + sample_off[J.c0 + i], (size_t)nn[i] * 2, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_off_b.p, soff.data(), (m + 1) * 8, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_n.p, nn, m * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rc = fail(RNSC_ERR_NO_DEVICE, "cudaMemcpyAsync: %s", cudaGetErrorString(e)); break; }
+        // splitter stage on the device
+        rc = rnsc_dev_svb_encode(c, codec, (const int16_t*)c->d_samples.p, (const uint64_t*)c->d_off_b.p, (const uint32_t*)c->d_n.p, m,
+                                 (uint8_t*)c->d_streams.p, scap, (uint64_t*)c->d_stream_off.p, st);
+        if (rc) break;
+        J.stoff.resize(5 * m + 1);
+        e = cudaMemcpyAsync(J.stoff.data(), c->d_stream_off.p, J.stoff.size() * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = fail(RNSC_ERR_NO_DEVICE, "stream offsets: %s", cudaGetErrorString(e)); break; }
+        const uint64_t total = J.stoff[5 * m];
+        if (k >= 2 && jobs[k - 2].th.joinable()) jobs[k - 2].th.join();          // its pinned buffer is free again
+        PinBuf* H = hb[k & 1];
+        if (H->reserve(total + 64)) { rc = fail(RNSC_ERR_NO_DEVICE, "cudaMallocHost(streams) failed"); break; }
+        e = cudaMemcpyAsync(H->p, c->d_streams.p, total, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = fail(RNSC_ERR_NO_DEVICE, "streams D2H: %s", cudaGetErrorString(e)); break; }
+        // one slot per chunk in the slice's arena (worst-case frame sizes): no per-chunk allocation
+        J.slot.resize(m + 1);
+        uint64_t need_all = 0;
+        for (size_t i = 0; i < m; ++i) {
+            J.slot[i] = need_all;
+            if (nf == 1) need_all += rnsc_max_compressed_size(codec, nn[i]);
+            else for (int f = 0; f < nf; ++f) need_all += z.bound((size_t)(J.stoff[5 * i + f + 1] - J.stoff[5 * i + f])) + 8;
         }
-        // destination capacity max(2n+26,1024): C4/C5 report it (C5.hpp:420-427); C1-C3 overrun in the
-        // reference, which is reported as the same error here.
-        if (op > cap) { status[i] = RNSC_ERR_DST_TOO_SMALL; return; }
-        csize[i] = (uint32_t)op;
-    });
+        J.slot[m] = need_all;
+        J.arena = (uint8_t*)malloc(need_all + 64);
+        if (!J.arena) { rc = fail(RNSC_ERR_NO_DEVICE, "malloc(frame arena %llu) failed", (unsigned long long)need_all); break; }
+        // zstd frame stage on host threads (byte-identical with the reference's ZSTD_compress(.., 1))
+        const uint8_t* hs = (const uint8_t*)H->p;
+        const int threads = c->host_threads;
+        auto work = [&J, &z, hs, nn, nf, codec, status, &csize, threads, m]() {
+            parallel_for(m, threads, [&](size_t i) {
+                const uint64_t* so = &J.stoff[5 * i];
+                uint8_t* o = J.arena + J.slot[i];
+                const size_t need = (size_t)(J.slot[i + 1] - J.slot[i]);
+                const size_t cap = rnsc_max_compressed_size(codec, nn[i]);
+                const size_t gi = J.c0 + i;
+                status[gi] = RNSC_OK;
+                if (nf == 1) {       // keys||data are adjacent in the stream buffer: one frame
+                    size_t cs = z.compress(o, cap, hs + so[0], (size_t)(so[2] - so[0]), 1);
+                    if (z.is_error(cs)) status[gi] = RNSC_ERR_ZSTD_ENCODE; else csize[gi] = (uint32_t)cs;
+                    return;
+                }
+                size_t op = 0;
+                for (int f = 0; f < nf; ++f) {
+                    const size_t len = (size_t)(so[f + 1] - so[f]);
+                    const size_t hdr = f + 1 < nf ? 8 : 0;
+                    size_t cs = z.compress(o + op + hdr, need - op - hdr, hs + so[f], len, 1);
+                    if (z.is_error(cs)) { status[gi] = RNSC_ERR_ZSTD_ENCODE; return; }
+                    if (hdr) { uint64_t v = cs; memcpy(o + op, &v, 8); }
+                    op += hdr + cs;
+                }
+                // destination capacity max(2n+26,1024): C4/C5 report it (C5.hpp:420-427); C1-C3 overrun in the
+                // reference, which is reported as the same error here.
+                if (op > cap) { status[gi] = RNSC_ERR_DST_TOO_SMALL; return; }
+                csize[gi] = (uint32_t)op;
+            });
+        };
+        if (nsl == 1) work(); else J.th = std::thread(work);
+    }
+    join_all();
+    if (rc) { free_all(); return rc; }
     uint64_t op = 0;
     for (size_t i = 0; i < nchunks; ++i) { comp_off[i] = op; op += csize[i]; }
-    if (op > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need %llu bytes, have %zu", (unsigned long long)op, comp_cap);
+    if (op > comp_cap) { free_all(); return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need %llu bytes, have %zu", (unsigned long long)op, comp_cap); }
+    // parallel compaction of the slots into the caller's buffer
     const size_t group = 64;                                         // chunks per copy task
+    std::vector<uint32_t> slice_of(nchunks);
+    for (size_t k = 0; k < nsl; ++k) for (size_t i = jobs[k].c0; i < jobs[k].c1; ++i) slice_of[i] = (uint32_t)k;
     parallel_for((nchunks + group - 1) / group, c->host_threads, [&](size_t g) {
-        for (size_t i = g * group; i < std::min(nchunks, (g + 1) * group); ++i)
-            if (csize[i]) memcpy(comp + comp_off[i], arena + slot[i], csize[i]);
+        for (size_t i = g * group; i < std::min(nchunks, (g + 1) * group); ++i) {
+            const SliceJob& J = jobs[slice_of[i]];
+            if (csize[i]) memcpy(comp + comp_off[i], J.arena + J.slot[i - J.c0], csize[i]);
+        }
     });
-    if (c->h_arena_cap > ((size_t)512 << 20)) { free(c->h_arena); c->h_arena = nullptr; c->h_arena_cap = 0; }   // keep only a modest arena between calls
+    free_all();
     comp_off[nchunks] = op;
     return RNSC_OK;
 }
