@@ -139,7 +139,8 @@ class Codec:
         samples = np.ascontiguousarray(samples, dtype=np.int16)
         sample_off = np.ascontiguousarray(sample_off, dtype=np.uint64)
         n = np.ascontiguousarray(n, dtype=np.uint32)
-        cap = int(sum(self.max_compressed_size(cid, int(k)) for k in n)) + 64
+        uniq, counts = np.unique(n, return_counts=True)                # one ABI call per distinct chunk length
+        cap = int(sum(self.max_compressed_size(cid, int(k)) * int(m) for k, m in zip(uniq, counts))) + 64
         out = np.empty(cap, dtype=np.uint8)
         coff = np.zeros(n.size + 1, dtype=np.uint64)
         status = np.zeros(n.size, dtype=np.int32)
