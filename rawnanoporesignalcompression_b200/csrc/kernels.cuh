@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(NT, 2) k_svb_unpack(int codec, const uint8_t* 
 // Second-generation splitter kernels (svb_pack2.cuh): one CTA of P2_NT threads per chunk
 // ---------------------------------------------------------------------------------------------------
 template <int CODEC>
-__global__ void __launch_bounds__(P2_NT, 4) k_svb_sizes2(const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, uint32_t nchunks, uint32_t* sizes)
+__global__ void __launch_bounds__(P2_NT, 1024 / P2_NT) k_svb_sizes2(const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, uint32_t nchunks, uint32_t* sizes)
 {
     __shared__ Pack2Ws<P2_NT> ws;
     for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x)
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(P2_NT, 4) k_svb_sizes2(const int16_t* samples,
 }
 
 template <int CODEC>
-__global__ void __launch_bounds__(P2_NT, 4) k_svb_pack2(const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, uint32_t nchunks,
+__global__ void __launch_bounds__(P2_NT, 1024 / P2_NT) k_svb_pack2(const int16_t* samples, const uint64_t* sample_off, const uint32_t* n, uint32_t nchunks,
                                                         uint8_t* streams, const uint64_t* stream_off)
 {
     RNSC_DYN_SMEM(stage);

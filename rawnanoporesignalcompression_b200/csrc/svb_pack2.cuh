@@ -21,7 +21,10 @@
 namespace rnsc {
 
 constexpr int P2_SPT = 16;
-constexpr int P2_NT = 256;                       // threads per CTA of the second-generation splitter kernels
+#ifndef RNSC_P2_NT
+#define RNSC_P2_NT 128
+#endif
+constexpr int P2_NT = RNSC_P2_NT;                // threads per CTA of the second-generation splitter kernels (128: 721 GB/s C5, 256: 701, 512: 632, 64: 589)
 constexpr int P2_TILE = P2_NT * P2_SPT;
 constexpr int P2_STAGE_BYTES = 4 * P2_TILE + 128;   // VBZ0: up to 4 nibbles (bytes here) per sample; C4/C5: 4 streams of <= TILE units
 
@@ -75,6 +78,15 @@ __device__ __forceinline__ void load16(const int16_t* in, uint32_t n, uint32_t i
 #pragma unroll
         for (int j = 0; j < P2_SPT; ++j) { if ((uint32_t)j < cnt) last = s[j]; else s[j] = last; }
     }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+#ifndef RNSC_EMUL
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
 }
 
 // zigzag of the 16-bit delta between two samples (zero-extended int16 bit patterns): svb16/encode_scalar.hpp:11-14,41-43
@@ -205,16 +217,20 @@ __device__ __forceinline__ void svb_sizes2(const int16_t* in, uint32_t n, uint32
 }
 
 // ---- staging -> global ---------------------------------------------------------------------------------------------
-// st[phase + i] <-> g[i] for i < count, where g - phase is 16-byte aligned (phase < 16).
+// st[phase + i] <-> g[i] for i < count, where g - phase is 16-byte aligned (phase < 16): 128-bit stores for the full
+// 16-byte groups; the ragged head and tail (< 16 bytes each) go out one byte per lane of warp 0 (a byte loop on one
+// thread would hold the whole warp's issue slots for up to 15 iterations per end and stream).
 template <int NTH>
 __device__ __forceinline__ void flush_bytes(uint8_t* g, const uint8_t* st, uint32_t phase, uint32_t count)
 {
     uint8_t* g0 = g - phase;
-    const uint32_t end = phase + count, ngroups = (end + 15) >> 4;
-    for (uint32_t grp = threadIdx.x; grp < ngroups; grp += NTH) {
-        const uint32_t lo = grp * 16;
-        if (lo >= phase && lo + 16 <= end) *(V16*)(g0 + lo) = *(const V16*)(st + lo);
-        else for (uint32_t i = max(lo, phase); i < min(lo + 16, end); ++i) g0[i] = st[i];
+    const uint32_t end = phase + count, body_lo = (phase + 15u) & ~15u, body_hi = end & ~15u;
+    for (uint32_t lo = body_lo + threadIdx.x * 16u; lo < body_hi; lo += NTH * 16u) *(V16*)(g0 + lo) = *(const V16*)(st + lo);
+    if (threadIdx.x < 32) {
+        const uint32_t l = threadIdx.x & 15u;
+        const bool tail = threadIdx.x >= 16;
+        const uint32_t i = (tail ? max(body_hi, body_lo) : phase) + l, lim = tail ? end : min(body_lo, end);
+        if (i < lim) g0[i] = st[i];
     }
 }
 // nibble stream: st[2 * (phase + i)] | st[2 * (phase + i) + 1] << 4 <-> g[i] for i < count
@@ -227,13 +243,16 @@ template <int NTH>
 __device__ __forceinline__ void flush_nibbles(uint8_t* g, const uint8_t* st, uint32_t phase, uint32_t count)
 {
     uint8_t* g0 = g - phase;
-    const uint32_t end = phase + count, ngroups = (end + 15) >> 4;
-    for (uint32_t grp = threadIdx.x; grp < ngroups; grp += NTH) {
-        const uint32_t lo = grp * 16;
-        if (lo >= phase && lo + 16 <= end) {
-            const V16 p = *(const V16*)(st + 2 * lo), q = *(const V16*)(st + 2 * lo + 16);
-            *(V16*)(g0 + lo) = V16{pack_nibbles8(p.x, p.y), pack_nibbles8(p.z, p.w), pack_nibbles8(q.x, q.y), pack_nibbles8(q.z, q.w)};
-        } else for (uint32_t i = max(lo, phase); i < min(lo + 16, end); ++i) g0[i] = (uint8_t)(st[2 * i] | (st[2 * i + 1] << 4));
+    const uint32_t end = phase + count, body_lo = (phase + 15u) & ~15u, body_hi = end & ~15u;
+    for (uint32_t lo = body_lo + threadIdx.x * 16u; lo < body_hi; lo += NTH * 16u) {
+        const V16 p = *(const V16*)(st + 2 * lo), q = *(const V16*)(st + 2 * lo + 16);
+        *(V16*)(g0 + lo) = V16{pack_nibbles8(p.x, p.y), pack_nibbles8(p.z, p.w), pack_nibbles8(q.x, q.y), pack_nibbles8(q.z, q.w)};
+    }
+    if (threadIdx.x < 32) {
+        const uint32_t l = threadIdx.x & 15u;
+        const bool tail = threadIdx.x >= 16;
+        const uint32_t i = (tail ? max(body_hi, body_lo) : phase) + l, lim = tail ? end : min(body_lo, end);
+        if (i < lim) g0[i] = (uint8_t)(st[2 * i] | (st[2 * i + 1] << 4));
     }
 }
 
@@ -280,6 +299,7 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
         if (cnt) {
             uint32_t s[P2_SPT], prev;
             load16(in, n, i0, cnt, s, prev);
+            if (i0 + T < n) prefetch_l1(in + i0 + T);                 // the thread's samples of the next tile: L1 hit after the two barriers
             kb = classify16<CODEC>(s, prev, v);
             unit_counts<CODEC>(kb, cnt, c1, c2, c3);
         }
@@ -321,12 +341,18 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
         if (cnt) {
             if (TWO) {
                 uint8_t* kp = d0 + (i0 >> 2);
-                if (cnt == (uint32_t)P2_SPT && ((uintptr_t)kp & 3) == 0) *(uint32_t*)kp = kb;
-                else for (uint32_t q = 0; q < (cnt + 3) >> 2; ++q) kp[q] = (uint8_t)(kb >> (8 * q));
+                if (cnt == (uint32_t)P2_SPT) {
+                    const uint32_t al = (uint32_t)((uintptr_t)kp & 3);               // same for every thread of the chunk
+                    if (al == 0) *(uint32_t*)kp = kb;
+                    else if (al == 2) { *(uint16_t*)kp = (uint16_t)kb; *(uint16_t*)(kp + 2) = (uint16_t)(kb >> 16); }
+                    else { kp[0] = (uint8_t)kb; kp[1] = (uint8_t)(kb >> 8); kp[2] = (uint8_t)(kb >> 16); kp[3] = (uint8_t)(kb >> 24); }
+                } else for (uint32_t q = 0; q < (cnt + 3) >> 2; ++q) kp[q] = (uint8_t)(kb >> (8 * q));
             } else {
                 uint8_t* kp = d0 + (i0 >> 3);
-                if (cnt == (uint32_t)P2_SPT && ((uintptr_t)kp & 1) == 0) *(uint16_t*)kp = (uint16_t)kb;
-                else for (uint32_t q = 0; q < (cnt + 7) >> 3; ++q) kp[q] = (uint8_t)(kb >> (8 * q));
+                if (cnt == (uint32_t)P2_SPT) {
+                    if (((uintptr_t)kp & 1) == 0) *(uint16_t*)kp = (uint16_t)kb;
+                    else { kp[0] = (uint8_t)kb; kp[1] = (uint8_t)(kb >> 8); }
+                } else for (uint32_t q = 0; q < (cnt + 7) >> 3; ++q) kp[q] = (uint8_t)(kb >> (8 * q));
             }
         }
         // ---- scatter the units into the staging areas ----

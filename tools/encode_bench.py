@@ -6,7 +6,8 @@ from rawnanoporesignalcompression_b200.codec import Codec
 R=int(sys.argv[1]) if len(sys.argv)>1 else 20000
 codecs=[int(c) for c in sys.argv[2].split(',')] if len(sys.argv)>2 else [6,0]
 dev=torch.device('cuda:0')
-cd=Codec(0)
+import os
+cd=Codec(0,lib_path=os.environ['RNSC_LIB']) if os.environ.get('RNSC_LIB') else Codec(0)
 lengths=synth.read_lengths(R,20261018)
 sig=synth.generate_reads(lengths,20261018,synth.R10_4_1,device=dev)
 off,n,_=synth.chunk_table(lengths)
