@@ -368,7 +368,12 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
                 if ((uint32_t)j < cnt) { if ((kb >> j) & 1u) { st2[p2] = (uint8_t)vv; st3[ph3 - ph2 + p2] = (uint8_t)(vv >> 8); p2++; } else st1[p1++] = (uint8_t)vv; }
             } else {
                 const uint32_t code = (kb >> (2 * j)) & 3u;           // samples past the end have code 0
-                if (CODEC == RNSC_VBZ0) { const uint32_t nn = nib_units(code); for (uint32_t q = 0; q < nn; ++q) st1[p1++] = (uint8_t)((vv >> (4 * q)) & 15u); }
+                if (CODEC == RNSC_VBZ0) {                              // 0 / 1 / 2 / 4 nibbles, straight-line
+                    if (code >= 1u) st1[p1] = (uint8_t)(vv & 15u);
+                    if (code >= 2u) st1[p1 + 1] = (uint8_t)((vv >> 4) & 15u);
+                    if (code == 3u) { st1[p1 + 2] = (uint8_t)((vv >> 8) & 15u); st1[p1 + 3] = (uint8_t)(vv >> 12); }
+                    p1 += nib_units(code);
+                }
                 else scatter_c45(kb & (3u << (2 * j)), 1u << (2 * j), vv, q1, q2, q3, q4);
             }
         }
