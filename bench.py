@@ -433,7 +433,7 @@ def run_rnsc(args):
                "encode": {"value": round(wl["encode_gbs"], 3), "unit": UNIT,
                           "note": "whole-chunk encode through rnsc_compress_batch while building the workload: pageable host in/out, device splitter, "
                                   "host libzstd level-1 frame stage (byte-identical to the reference); untimed-region number, for orientation"}}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     cd.close()
@@ -470,10 +470,32 @@ def run_reference(args):
            "gpu_launches": 0,
            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_JSON_FD = None
+
+
+def reserve_stdout():
+    """Keeps the process's real stdout for the ONE JSON line: file descriptor 1 is pointed at stderr, so that banners
+    that libraries write to stdout (NCCL prints its version there) cannot end up next to it."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(out):
+    line = (json.dumps(out) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

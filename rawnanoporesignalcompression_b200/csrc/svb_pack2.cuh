@@ -218,17 +218,17 @@ __device__ __forceinline__ void svb_sizes2(const int16_t* in, uint32_t n, uint32
 
 // ---- staging -> global ---------------------------------------------------------------------------------------------
 // st[phase + i] <-> g[i] for i < count, where g - phase is 16-byte aligned (phase < 16): 128-bit stores for the full
-// 16-byte groups; the ragged head and tail (< 16 bytes each) go out one byte per lane of warp 0 (a byte loop on one
-// thread would hold the whole warp's issue slots for up to 15 iterations per end and stream).
-template <int NTH>
-__device__ __forceinline__ void flush_bytes(uint8_t* g, const uint8_t* st, uint32_t phase, uint32_t count)
+// 16-byte groups; the ragged head and tail (< 16 bytes each) go out one byte per lane of the first warp (a byte loop on
+// one thread would hold the whole warp's issue slots for up to 15 iterations per end and stream). Thread t of nt
+// cooperating threads (nt a multiple of 32, t < nt).
+__device__ __forceinline__ void flush_bytes(uint8_t* g, const uint8_t* st, uint32_t phase, uint32_t count, uint32_t t, uint32_t nt)
 {
     uint8_t* g0 = g - phase;
     const uint32_t end = phase + count, body_lo = (phase + 15u) & ~15u, body_hi = end & ~15u;
-    for (uint32_t lo = body_lo + threadIdx.x * 16u; lo < body_hi; lo += NTH * 16u) *(V16*)(g0 + lo) = *(const V16*)(st + lo);
-    if (threadIdx.x < 32) {
-        const uint32_t l = threadIdx.x & 15u;
-        const bool tail = threadIdx.x >= 16;
+    for (uint32_t lo = body_lo + t * 16u; lo < body_hi; lo += nt * 16u) *(V16*)(g0 + lo) = *(const V16*)(st + lo);
+    if (t < 32) {
+        const uint32_t l = t & 15u;
+        const bool tail = t >= 16;
         const uint32_t i = (tail ? max(body_hi, body_lo) : phase) + l, lim = tail ? end : min(body_lo, end);
         if (i < lim) g0[i] = st[i];
     }
@@ -239,18 +239,17 @@ __device__ __forceinline__ uint32_t pack_nibbles8(uint32_t a, uint32_t b)   // 8
     const uint32_t ta = (a | (a >> 4)) & 0x00FF00FFu, tb = (b | (b >> 4)) & 0x00FF00FFu;
     return __byte_perm(ta, tb, 0x6420);
 }
-template <int NTH>
-__device__ __forceinline__ void flush_nibbles(uint8_t* g, const uint8_t* st, uint32_t phase, uint32_t count)
+__device__ __forceinline__ void flush_nibbles(uint8_t* g, const uint8_t* st, uint32_t phase, uint32_t count, uint32_t t, uint32_t nt)
 {
     uint8_t* g0 = g - phase;
     const uint32_t end = phase + count, body_lo = (phase + 15u) & ~15u, body_hi = end & ~15u;
-    for (uint32_t lo = body_lo + threadIdx.x * 16u; lo < body_hi; lo += NTH * 16u) {
+    for (uint32_t lo = body_lo + t * 16u; lo < body_hi; lo += nt * 16u) {
         const V16 p = *(const V16*)(st + 2 * lo), q = *(const V16*)(st + 2 * lo + 16);
         *(V16*)(g0 + lo) = V16{pack_nibbles8(p.x, p.y), pack_nibbles8(p.z, p.w), pack_nibbles8(q.x, q.y), pack_nibbles8(q.z, q.w)};
     }
-    if (threadIdx.x < 32) {
-        const uint32_t l = threadIdx.x & 15u;
-        const bool tail = threadIdx.x >= 16;
+    if (t < 32) {
+        const uint32_t l = t & 15u;
+        const bool tail = t >= 16;
         const uint32_t i = (tail ? max(body_hi, body_lo) : phase) + l, lim = tail ? end : min(body_lo, end);
         if (i < lim) g0[i] = (uint8_t)(st[2 * i] | (st[2 * i + 1] << 4));
     }
@@ -379,11 +378,19 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
         }
         __syncthreads();
         // ---- flush, 16-byte vectors in the aligned body ----
-        if (NIB1) flush_nibbles<NTH>(g1, st1, ph1, (par + t1) >> 1);
-        else flush_bytes<NTH>(g1, st1, ph1, t1);
-        if (CODEC == RNSC_C2 || CODEC == RNSC_C4 || CODEC == RNSC_C5) flush_bytes<NTH>(d2 + run2, st2, ph2, t2);
-        if (CODEC == RNSC_C3) { flush_bytes<NTH>(d2 + run2, st2, ph2, t2); flush_bytes<NTH>(d3 + run2, st3, ph3, t2); }
-        if (WORD_B && t3) { flush_bytes<NTH>(d3 + run3, st3, ph3, t3); flush_bytes<NTH>(d4 + run3, st4, ph4, t3); }
+        if (WORD_B && NW >= 4) {
+            // C4/C5: the streams are flushed by different warps (nibbles: warp 0; large values: warp 1; bytes: the rest),
+            // so a thread runs one flush's set-up instead of four
+            if (warp == 0) flush_nibbles(g1, st1, ph1, (par + t1) >> 1, (uint32_t)lane, 32u);
+            else if (warp == 1) { if (t3) { flush_bytes(d3 + run3, st3, ph3, t3, (uint32_t)lane, 32u); flush_bytes(d4 + run3, st4, ph4, t3, (uint32_t)lane, 32u); } }
+            else flush_bytes(d2 + run2, st2, ph2, t2, (uint32_t)tid - 64u, (uint32_t)NTH - 64u);
+        } else {
+            if (NIB1) flush_nibbles(g1, st1, ph1, (par + t1) >> 1, (uint32_t)tid, (uint32_t)NTH);
+            else flush_bytes(g1, st1, ph1, t1, (uint32_t)tid, (uint32_t)NTH);
+            if (CODEC == RNSC_C2 || CODEC == RNSC_C4 || CODEC == RNSC_C5) flush_bytes(d2 + run2, st2, ph2, t2, (uint32_t)tid, (uint32_t)NTH);
+            if (CODEC == RNSC_C3) { flush_bytes(d2 + run2, st2, ph2, t2, (uint32_t)tid, (uint32_t)NTH); flush_bytes(d3 + run2, st3, ph3, t2, (uint32_t)tid, (uint32_t)NTH); }
+            if (WORD_B && t3) { flush_bytes(d3 + run3, st3, ph3, t3, (uint32_t)tid, (uint32_t)NTH); flush_bytes(d4 + run3, st4, ph4, t3, (uint32_t)tid, (uint32_t)NTH); }
+        }
         run1 += t1; run2 += t2; run3 += t3;
     }
     __syncthreads();
