@@ -129,3 +129,12 @@ def test_encode_pipeline_many_slices(emul_lib):
     env = dict(os.environ, RNSC_SLICE_SAMPLES="6000")
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "slice_check.py"), emul_lib, "6,0,2,7"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "slices ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_foreign_zstd_frames(ecodec, oracle):
+    """Frames from other zstd levels / with checksums / with two blocks (tests/zstd_foreign.py) through the kernel sources."""
+    import zstd_foreign as zf
+    for name, x in zf.signals():
+        for level, ck in zf.SETTINGS[::2]:
+            assert (ecodec.decompress_signal(zf.vbz_frame(oracle, x, level, ck), x.size, 0) == x).all(), (name, level, ck)
+        assert (ecodec.decompress_signal(zf.c5_container(oracle, x, 19, True), x.size, 6) == x).all(), name

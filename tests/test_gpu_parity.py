@@ -217,3 +217,27 @@ def test_encode_pipeline_many_slices(gpu_codec):
     env = dict(os.environ, RNSC_SLICE_SAMPLES="6000")
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "slice_check.py"), "gpu", "0,1,2,3,4,5,6,7"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "slices ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_foreign_zstd_frames(gpu_codec, oracle):
+    """Chunks whose frames were NOT written by `ZSTD_compress(..., 1)`: other levels, checksummed frames, two-block
+    frames. The reference reads them through ZSTD_decompress (signal_compression.cpp:117, C5.hpp:588-655); the device
+    decoder must return the same samples, one by one and mixed into a batch with stock level-1 chunks."""
+    import zstd_foreign as zf
+    sigs = zf.signals()
+    frames, ns, want = [], [], []
+    for name, x in sigs:
+        for level, ck in zf.SETTINGS:
+            frames.append(zf.vbz_frame(oracle, x, level, ck)); ns.append(x.size); want.append(x)
+        frames.append(oracle.encode(0, x)); ns.append(x.size); want.append(x)
+    got, st = gpu_codec.decompress_batch(frames, ns, 0)
+    assert not st.any(), st
+    assert all((g == w).all() for g, w in zip(got, want))
+    assert (gpu_codec.decompress_signal(frames[2], ns[2], 0) == want[2]).all()
+    conts, ns, want = [], [], []
+    for name, x in sigs:
+        for level, ck in ((19, True), (3, False), (-5, True)):
+            conts.append(zf.c5_container(oracle, x, level, ck)); ns.append(x.size); want.append(x)
+    got, st = gpu_codec.decompress_batch(conts, ns, 6)
+    assert not st.any(), st
+    assert all((g == w).all() for g, w in zip(got, want))

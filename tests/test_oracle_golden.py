@@ -89,3 +89,19 @@ def test_error_semantics(oracle):
     # incompressible full chunk: C4/C5 refuse
     u = recipes.uniform16(102400, 11)
     assert oracle.encode_status(6, u)[0] == 3 and oracle.encode_status(5, u)[0] == 3
+
+
+def test_oracle_zstd_decoder_on_foreign_frames(oracle):
+    """The oracle's own RFC 8878 frame decoder against frames written at other levels / with checksums / two blocks,
+    checked against libzstd's decode of the same bytes and the source samples."""
+    import zstd_foreign as zf
+    for name, x in zf.signals():
+        for level, ck in zf.SETTINGS:
+            f = zf.vbz_frame(oracle, x, level, ck)
+            for own in (True, False):
+                st, y = oracle.decode_status(0, f, x.size, own_zstd=own)
+                assert st == 0 and (y == x).all(), (name, level, ck, own)
+        c = zf.c5_container(oracle, x, 19, True)
+        for own in (True, False):
+            st, y = oracle.decode_status(6, c, x.size, own_zstd=own)
+            assert st == 0 and (y == x).all(), (name, "C5", own)
