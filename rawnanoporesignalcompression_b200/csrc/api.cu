@@ -188,7 +188,7 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
     for (int k = 0; k < 3; ++k) pp.region[k] = (uint32_t)(kFastSmem[k] - kFastWs[k] - unpack2_lut_bytes(codec));
     pp.deftab = (const uint32_t*)c->d_deftab.p;
-    pp.seq_pool = (uint32_t*)c->d_seqpool.p; pp.pool_cap = (uint32_t)std::min<size_t>(pool_cap, 0xFFFFFFFFu); pp.pool_cursor = cnt + 4;
+    pp.seq_pool = (uint32_t*)c->d_seqpool.p; pp.pool_cap = (uint32_t)std::min<size_t>(pool_cap, 0xFFFFFFFFu); pp.pool_cursor = (unsigned long long*)(cnt + 4);   /* words 4-5, 8-byte aligned */
     RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
     // 2. fast kernel over the three size classes, 3. general decoder over what is left. Fork: class B (large chunks, one
     // CTA per SM) stays on the caller's stream and is enqueued first; the other classes and the general decoder go to side

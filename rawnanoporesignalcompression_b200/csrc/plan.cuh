@@ -90,7 +90,7 @@ struct PlanParams {
     uint32_t* counts;            // [0..3] list lengths (atomic), zeroed before the launch
     uint32_t region[3];          // bytes of dynamic region available to a class S / A / B CTA
     const uint32_t* deftab;      // predefined FSE decoding tables: LL[64] OF[32] ML[64]
-    uint32_t* seq_pool; uint32_t pool_cap; uint32_t* pool_cursor;   // bump-allocated sequence storage (SEQ_WORDS words per entry)
+    uint32_t* seq_pool; uint32_t pool_cap; unsigned long long* pool_cursor;   // 64-bit cursor: a hostile batch can ask for more than 2^32 entries; bump-allocated sequence storage (SEQ_WORDS words per entry)
 };
 
 // Per planner thread scratch in shared memory. 161 words: an odd stride, so the same field of the 32 threads of a
@@ -265,8 +265,9 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     warp_converge<true>();
     // ---- sequences: predefined, RLE or FSE-described tables (repeat mode is invalid in a first block) ----
     if (!bad && nseq) {
-        const uint32_t base = atomicAdd(P.pool_cursor, nseq + 1);            // bump allocation in the sequence pool (+1: the tail run)
-        if (base + nseq + 1 > P.pool_cap) bad = true;
+        const unsigned long long base64 = atomicAdd(P.pool_cursor, (unsigned long long)nseq + 1);   // bump allocation in the sequence pool (+1: the tail run)
+        if (base64 + nseq + 1 > P.pool_cap) bad = true;
+        const uint32_t base = bad ? 0u : (uint32_t)base64;
         fp.seq_base = base;
         uint32_t rle[3] = {0, 0, 0};
         const uint32_t* tab[3] = {deftab, deftab, deftab}; int tlog[3] = {0, 0, 0};
