@@ -179,7 +179,7 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     // sequence pool: bump-allocated by the planner; ~1000 sequences per chunk on average covers VBZ (C5 needs ~15)
     const size_t pool_cap = nchunks * 1024 + 4096;
     if (c->d_seqpool.reserve(pool_cap * SEQ_WORDS * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(sequence pool) failed");
-    // counter words: [0..3] list lengths (class S, A, B, general), [4] sequence pool cursor, [8..11] the work cursors of the four kernels
+    // counter words: [0..3] list lengths (class S, A, B, general), [4..5] sequence pool cursor (64-bit), [8..11] the work cursors of the four kernels
     uint32_t* cnt = (uint32_t*)c->d_counter.p;
     CUDA_OK(cudaMemsetAsync(cnt, 0, 64, st));
     // 1. planner: one thread per chunk does every serial step (headers, Huffman tree descriptions, sequences)
