@@ -251,13 +251,18 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
         const int lim = huf ? nw : 0;
         // a position is at most 255 when it is used; the increment past the last symbol of the heaviest class may carry
         // into the (unused) field above it
-        for (int i = 0; i < lim; ++i) {
-            const uint32_t w = sc->weights[i];
-            if (w) {
-                const uint32_t sh = (w & 7u) * 8u;
-                const uint32_t pos = (uint32_t)(((w & 8u) ? p_hi : p_lo) >> sh) & 0xFFu;
-                hp->sorted[pos] = (uint8_t)i;
-                if (w & 8u) p_hi += 1ull << sh; else p_lo += 1ull << sh;
+        // weights are read a word at a time (PlanScratch is 4-byte aligned, weights[] sits at its start and holds 256 bytes)
+        for (int i0 = 0; i0 < lim; i0 += 4) {
+            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(sc->weights + i0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t w = (w4 >> (8 * j)) & 0xFFu;
+                if (w && i0 + j < lim) {
+                    const uint32_t sh = (w & 7u) * 8u;
+                    const uint32_t pos = (uint32_t)(((w & 8u) ? p_hi : p_lo) >> sh) & 0xFFu;
+                    hp->sorted[pos] = (uint8_t)(i0 + j);
+                    if (w & 8u) p_hi += 1ull << sh; else p_lo += 1ull << sh;
+                }
             }
         }
     }
