@@ -91,8 +91,13 @@ int rnsc_decompress_batch(rnsc_ctx* ctx, int codec, const uint8_t* comp, const u
 
 /* ---- device-resident batch (all d_* pointers are device memory; `stream` is a cudaStream_t or NULL for the
  *      context's own stream; calls are asynchronous on that stream unless stated) ---------------------- */
-/* Whole-chunk decode: zstd frames -> streams -> int16, one fused kernel. d_comp must be 16-byte aligned
- * and have 16 readable bytes after the last chunk. max_n = max over n[] (sizes per-CTA scratch). */
+/* Whole-chunk decode: zstd frames -> streams -> int16, one fused launch group. d_comp must be 16-byte aligned
+ * and have 16 readable bytes after the last chunk. max_n = max over n[] (sizes per-CTA scratch).
+ * Calls on one context share its planner scratch: they run one after another on the device even when they
+ * are enqueued on different streams (each call waits for the previous call's completion event); use one
+ * context per stream for decodes that should overlap. Scratch is sized from the data and grows with what
+ * the context has seen: a batch with far more LZ sequences per chunk than any before it is still decoded
+ * correctly, its overflow by the general decoder (rnsc_decode_class_counts out[3]). */
 int rnsc_dev_decode(rnsc_ctx* ctx, int codec, const uint8_t* d_comp, const uint64_t* d_comp_off,
                     const uint32_t* d_n, const uint64_t* d_sample_off, size_t nchunks, uint32_t max_n,
                     int16_t* d_samples, int32_t* d_status, void* stream);

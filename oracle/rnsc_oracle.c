@@ -254,9 +254,13 @@ int orc_decode(int codec, const uint8_t* in, size_t clen, size_t n, int16_t* out
         fp[f] = in + pos; pos += fl[f];
         unsigned long long c = use_own_zstd ? orc_zstd_frame_content_size(fp[f], fl[f]) : z_fcs(fp[f], fl[f]);
         if (c >= (unsigned long long)-2) return 1;
+        /* a valid chunk of n samples never decodes to more than its key bytes + 2 bytes per sample (+ slack): reject
+         * hostile frame headers before sizing the buffer from them, as the kernels do (plan.cuh: fcs > stream_bound) */
+        if (c > (unsigned long long)n / 4 + 2ull * n + 16) return 4;
         d[f] = (size_t)c; total += d[f];
     }
     uint8_t* buf = (uint8_t*)malloc(total + 16); size_t wp = 0; int rc = 0;
+    if (!buf) return 2;
     for (int f = 0; f < nf && !rc; ++f) {
         size_t got = 0;
         if (use_own_zstd) { if (orc_zstd_decode_frame(fp[f], fl[f], buf + wp, d[f], &got)) rc = 2; }

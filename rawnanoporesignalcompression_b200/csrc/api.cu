@@ -148,12 +148,16 @@ struct rnsc_ctx {
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
     DevBuf d_plans, d_lists, d_deftab, d_prof, d_seqpool, d_origin;
     bool profiling = false;
+    uint32_t cost_bit = 1, cost_sym = 12;   // planner's cost model of the Huffman stage (plan.cuh); RNSC_COST_BIT / RNSC_COST_SYM override (tuning)
     Lane lane[2];
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
     cudaStream_t hi = nullptr;                             // high priority: the general decoder must get its SMs before the persistent CTAs fill them (see launch_decode)
     cudaEvent_t ev_plan = nullptr, ev_hi = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_dec_done = nullptr; bool dec_pending = false;   // end of the previous whole-chunk decode: the next one (on any stream) waits for it, they share the scratch
     PinBuf h_a, h_b;
+    PinBuf h_pool_seen;                      // {sequence pool entries the planner asked for, chunks} of the latest finished decode (pinned, written by a D2H copy)
+    size_t pool_per_chunk[2] = {0, 0};       // learned pool demand per chunk: [0] separate-stream codecs, [1] LZ-heavy frames
 };
 
 namespace {
@@ -167,7 +171,7 @@ size_t decode_arena_bytes()
 }
 
 int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t* d_comp_off, const uint32_t* d_n, const uint64_t* d_sample_off,
-                  size_t nchunks, uint32_t max_n, int16_t* d_samples, int32_t* d_status, cudaStream_t st)
+                  size_t nchunks, uint32_t max_n, int16_t* d_samples, int32_t* d_status, cudaStream_t st, size_t comp_bytes_hint = 0)
 {
     if (nchunks == 0) return RNSC_OK;
     const int grid = (int)std::min<size_t>((size_t)c->sm_count * 2, nchunks);
@@ -176,11 +180,27 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     if (c->d_scratch.reserve(stride * (size_t)c->sm_count * 2)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(scratch %zu) failed", stride * (size_t)c->sm_count * 2);
     if (c->d_counter.reserve(256)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(counter) failed");
     if (c->d_plans.reserve(nchunks * sizeof(ChunkPlan)) || c->d_lists.reserve(4 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(plans) failed");
-    // sequence pool: bump-allocated by the planner; ~1000 sequences per chunk on average covers VBZ (C5 needs ~15)
-    const size_t pool_cap = nchunks * 1024 + 4096;
+    // Sequence pool: bump-allocated by the planner, SEQ_WORDS words per LZ sequence. Sized from the data, not from a fixed
+    // worst case: frames that hold keys and payload together (VBZ, VBZ0) or the VBZ payload alone (C1) carry
+    // ~1 sequence per 30-100 compressed bytes, the separate streams of C2-C5 a handful per chunk. The demand of the previous
+    // calls (read back below, a call late) raises the estimate; a batch that still overflows is not an error -- the
+    // overflowing chunks take the general decoder, rnsc_decode_class_counts shows them, and the next call has room.
+    const bool lz_heavy = codec_frames(codec) == 1 || codec == RNSC_C1;
+    size_t per_chunk = lz_heavy ? 1024 : 64;
+    if (c->h_pool_seen.p) {
+        const volatile unsigned long long* seen = (const volatile unsigned long long*)c->h_pool_seen.p;     // {entries asked for, chunks} of an earlier call
+        if (seen[1]) { const size_t d = (size_t)((seen[0] + seen[1] - 1) / seen[1]); c->pool_per_chunk[lz_heavy] = std::max(c->pool_per_chunk[lz_heavy], d + d / 4 + 1); }
+    }
+    per_chunk = std::max(per_chunk, c->pool_per_chunk[lz_heavy]);
+    size_t pool_cap = nchunks * per_chunk + 4096;
+    if (comp_bytes_hint) pool_cap = std::min(pool_cap, std::max<size_t>(comp_bytes_hint / 8, nchunks * 16) + 4096);   // a sequence costs more than a byte in any real frame
     if (c->d_seqpool.reserve(pool_cap * SEQ_WORDS * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(sequence pool) failed");
+    if (!c->h_pool_seen.p) { if (c->h_pool_seen.reserve(64)) return fail(RNSC_ERR_NO_DEVICE, "cudaMallocHost(pool demand) failed"); memset(c->h_pool_seen.p, 0, 64); }
     // counter words: [0..3] list lengths (class S, A, B, general), [4..5] sequence pool cursor (64-bit), [8..11] the work cursors of the four kernels
     uint32_t* cnt = (uint32_t*)c->d_counter.p;
+    // Calls on one context share the plans, lists, counters, sequence pool and side streams: a call enqueued on another
+    // stream than its predecessor must not start before that one has finished (double-buffered callers).
+    if (c->dec_pending) CUDA_OK(cudaStreamWaitEvent(st, c->ev_dec_done, 0));
     CUDA_OK(cudaMemsetAsync(cnt, 0, 64, st));
     // 1. planner: one thread per chunk does every serial step (headers, Huffman tree descriptions, sequences)
     PlanParams pp;
@@ -188,18 +208,28 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
     for (int k = 0; k < 3; ++k) pp.region[k] = (uint32_t)(kFastSmem[k] - kFastWs[k] - unpack2_lut_bytes(codec));
     pp.deftab = (const uint32_t*)c->d_deftab.p;
+    pp.cost_bit = c->cost_bit; pp.cost_sym = c->cost_sym;
+    pp.has_origin = (lz_heavy || c->pool_per_chunk[0] > 64 || c->d_origin.p) ? 1u : 0u;
     pp.seq_pool = (uint32_t*)c->d_seqpool.p; pp.pool_cap = (uint32_t)std::min<size_t>(pool_cap, 0xFFFFFFFFu); pp.pool_cursor = (unsigned long long*)(cnt + 4);   /* words 4-5, 8-byte aligned */
     RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
+    {   // the pool cursor (entries asked for) and the chunk count travel to the pinned mirror; nobody waits for them
+        RNSC_LAUNCH(k_pool_demand, 1, 1, 0, st, (const unsigned long long*)(cnt + 4), (unsigned long long)nchunks, (unsigned long long*)c->d_counter.p + 16);
+        CUDA_OK(cudaMemcpyAsync(c->h_pool_seen.p, (const unsigned long long*)c->d_counter.p + 16, 16, cudaMemcpyDeviceToHost, st));
+    }
     // 2. fast kernel over the three size classes, 3. general decoder over what is left. Fork: class B (large chunks, one
     // CTA per SM) stays on the caller's stream and is enqueued first; the other classes and the general decoder go to side
     // streams and fill SMs as class B CTAs retire. Join before returning to the caller's stream.
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
     fp.plans = (const ChunkPlan*)c->d_plans.p; fp.seq_pool = (const uint32_t*)c->d_seqpool.p; fp.nchunks = (uint32_t)nchunks;
-    // match resolver scratch: one origin word per matched byte, a matched byte count is below the class's region size
+    // match resolver scratch in global memory: one origin word per matched byte of a chunk whose origin words do not fit the
+    // dead bitstream area of its staged bytes. ~400 MB per context, so it exists only where sequence-heavy frames are
+    // expected (LZ-heavy codecs, or a context that has seen such frames); without it the planner routes the chunks that
+    // would need it to the general decoder.
     size_t origin_words[3], origin_base[3], origin_total = 0;
     for (int k = 0; k < 3; ++k) { origin_words[k] = kFastSmem[k]; origin_base[k] = origin_total; origin_total += origin_words[k] * (size_t)c->sm_count * (4 >> k); }
-    if (c->d_origin.reserve(origin_total * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(origin scratch) failed");
+    const bool want_origin = lz_heavy || c->pool_per_chunk[0] > 64;
+    if (want_origin && c->d_origin.reserve(origin_total * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(origin scratch) failed");
     auto set_class = [&](uint32_t cls) { fp.list = (const uint32_t*)c->d_lists.p + (size_t)cls * nchunks; fp.count = cnt + cls; fp.counter = cnt + 8 + cls;
                                          fp.origin = (uint32_t*)c->d_origin.p + origin_base[cls]; fp.origin_stride = origin_words[cls];
                                          fp.prof = c->profiling ? (unsigned long long*)c->d_prof.p + 8 * cls : nullptr;
@@ -225,7 +255,8 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     RNSC_LAUNCH(k_decode_fast<256>, (int)std::min<size_t>((size_t)c->sm_count * 4, nchunks), 256, kFastSmem[0], c->side[1], fp);
     for (int k = 0; k < 2; ++k) { CUDA_OK(cudaEventRecord(c->ev_side[k], c->side[k])); CUDA_OK(cudaStreamWaitEvent(st, c->ev_side[k], 0)); }
     CUDA_OK(cudaStreamWaitEvent(st, c->ev_hi, 0));
-    c->launches += 5;
+    CUDA_OK(cudaEventRecord(c->ev_dec_done, st)); c->dec_pending = true;
+    c->launches += 6;
     CUDA_OK(cudaGetLastError());
     return RNSC_OK;
 }
@@ -289,10 +320,10 @@ rnsc_ctx* rnsc_create(int device)
     rnsc_ctx* c = new rnsc_ctx();
     c->device = device;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed"); return nullptr; }
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rnsc_destroy(c); fail(RNSC_ERR_NO_DEVICE, "cudaGetDeviceProperties failed"); return nullptr; }
     c->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
-    bool ok = cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) == cudaSuccess;
+    if (cudaStreamCreate(&c->stream) != cudaSuccess) { rnsc_destroy(c); fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate failed"); return nullptr; }
+    bool ok = cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->ev_dec_done, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < 3 && ok; ++k) ok = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&c->ev_side[k], cudaEventDisableTiming) == cudaSuccess;
     {
         int least = 0, greatest = 0;
@@ -302,7 +333,7 @@ rnsc_ctx* rnsc_create(int device)
     ok = ok && cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) ok = cudaEventCreateWithFlags(&c->lane[k].ev_in, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->lane[k].ev_dec, cudaEventDisableTiming) == cudaSuccess &&
                                            cudaEventCreateWithFlags(&c->lane[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) { delete c; fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
+    if (!ok) { rnsc_destroy(c); fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
     cudaError_t e2 = cudaSuccess;
     cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[2]);
@@ -317,14 +348,17 @@ rnsc_ctx* rnsc_create(int device)
         e3 = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e1 == cudaSuccess) e1 = e3;
     }
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return nullptr; }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { rnsc_destroy(c); fail(RNSC_ERR_NO_DEVICE, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return nullptr; }
     uint32_t deftab[160];
     host_default_tables(deftab);
     if (c->d_deftab.reserve(sizeof deftab) || cudaMemcpy(c->d_deftab.p, deftab, sizeof deftab, cudaMemcpyHostToDevice) != cudaSuccess) {
-        c->d_deftab.release(); cudaStreamDestroy(c->stream); delete c; fail(RNSC_ERR_NO_DEVICE, "upload of the predefined FSE tables failed"); return nullptr;
+        rnsc_destroy(c); fail(RNSC_ERR_NO_DEVICE, "upload of the predefined FSE tables failed"); return nullptr;
     }
     unsigned hc = std::thread::hardware_concurrency();
     c->host_threads = hc ? (int)hc : 1;
+    if (const char* e = getenv("RNSC_COST_BIT")) c->cost_bit = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("RNSC_COST_SYM")) c->cost_sym = (uint32_t)strtoul(e, nullptr, 10);
+    if (c->cost_bit + c->cost_sym == 0) c->cost_bit = 1;
     return c;
 }
 
@@ -332,12 +366,13 @@ void rnsc_destroy(rnsc_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);      // a half-built context (rnsc_create failure) has null handles
     for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin}) b->release();
-    c->h_a.release(); c->h_b.release();
+    c->h_a.release(); c->h_b.release(); c->h_pool_seen.release();
     if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); } if (c->ev_hi) cudaEventDestroy(c->ev_hi);
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);
+    if (c->ev_dec_done) cudaEventDestroy(c->ev_dec_done);
     for (int k = 0; k < 2; ++k) {
         Lane& L = c->lane[k];
         for (DevBuf* b : {&L.comp, &L.samples, &L.off_a, &L.off_b, &L.n, &L.status}) b->release();
@@ -346,7 +381,7 @@ void rnsc_destroy(rnsc_ctx* c)
     }
     if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
     if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -514,6 +549,9 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
     // H2D of slice i+1, decode of slice i and D2H of slice i-1 overlap (three streams chained by events). Chunk i may
     // live anywhere in `comp`/`samples`; inside a lane the chunks are staged back to back (the kernels accept any
     // byte/sample alignment) with dense offset tables.
+    // The slice loop runs inside a lambda so that EVERY exit (CUDA error, allocation failure, kernel launch failure) passes
+    // the clean-up below: copies into the caller's buffers may still be in flight and lanes marked used.
+    auto run = [&]() -> int {
     size_t first = 0; int slice = 0; int rc = RNSC_OK;
     while (first < nchunks && rc == RNSC_OK) {
         size_t last = first; uint64_t cb = 0, sb = 0; uint32_t max_n = 0;
@@ -548,7 +586,7 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
         CUDA_OK(cudaStreamWaitEvent(st, L.ev_in, 0));
         if (L.used) CUDA_OK(cudaStreamWaitEvent(st, L.ev_out, 0));
         if (codec == RNSC_RC) rc = rnsc_dev_rc_decode(c, (const uint8_t*)L.comp.p, (const uint64_t*)L.off_a.p, (const uint32_t*)L.n.p, (const uint64_t*)L.off_b.p, m, (int16_t*)L.samples.p, (int32_t*)L.status.p, st);
-        else rc = launch_decode(c, codec, (const uint8_t*)L.comp.p, (const uint64_t*)L.off_a.p, (const uint32_t*)L.n.p, (const uint64_t*)L.off_b.p, m, max_n, (int16_t*)L.samples.p, (int32_t*)L.status.p, st);
+        else rc = launch_decode(c, codec, (const uint8_t*)L.comp.p, (const uint64_t*)L.off_a.p, (const uint32_t*)L.n.p, (const uint64_t*)L.off_b.p, m, max_n, (int16_t*)L.samples.p, (int32_t*)L.status.p, st, cb);
         if (rc) break;
         CUDA_OK(cudaEventRecord(L.ev_dec, st));
         // ---- D2H ----
@@ -560,10 +598,13 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
         L.used = true;
         first = last; ++slice;
     }
-    CUDA_OK(cudaStreamSynchronize(c->h2d));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->d2h));
+    return rc;
+    };
+    int rc = run();
+    const cudaError_t e1 = cudaStreamSynchronize(c->h2d), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(c->d2h);
     for (int k = 0; k < 2; ++k) c->lane[k].used = false;
+    if (rc == RNSC_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
+        rc = fail(RNSC_ERR_NO_DEVICE, "rnsc_decompress_batch: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return rc;
 }
 
@@ -607,7 +648,7 @@ int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const ui
         for (size_t i = 0; i < nchunks; ++i) {
             comp_off[i] = op;
             if (status[i] == RNSC_OK) {
-                if (op + csz[i] > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small");
+                if (op + csz[i] > comp_cap) { cudaStreamSynchronize(st); return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small"); }   // earlier copies into `comp` are in flight
                 CUDA_OK(cudaMemcpyAsync(comp + op, (uint8_t*)c->d_comp.p + slot[i], csz[i], cudaMemcpyDeviceToHost, st));
                 op += csz[i];
             }

@@ -89,6 +89,29 @@ __device__ inline void bulk_load(void* dst, const void* src, uint32_t bytes, uns
 __device__ inline void mbar_wait(unsigned long long*, uint32_t) {}
 #endif
 
+// ---- named barriers: a group of whole warps (the threads of one Huffman-coded frame) synchronises on barrier `id` -------
+#ifndef RNSC_EMUL
+__device__ __forceinline__ void bar_named(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ bool bar_named_or(uint32_t id, uint32_t nthreads, bool pred)
+{
+    uint32_t r;
+    asm volatile("{\n.reg .pred q, o;\nsetp.ne.u32 q, %3, 0;\nbar.red.or.pred o, %1, %2, q;\nselp.u32 %0, 1, 0, o;\n}" : "=r"(r) : "r"(id), "r"(nthreads), "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
+#else
+__device__ inline void bar_named(uint32_t id, uint32_t nthreads) { emul::named_barrier((int)id, (int)nthreads); }
+__device__ inline bool bar_named_or(uint32_t id, uint32_t nthreads, bool pred)
+{
+    static int acc[16];
+    acc[id] = 0; emul::named_barrier((int)id, (int)nthreads);
+    if (pred) acc[id] = 1;
+    emul::named_barrier((int)id, (int)nthreads);
+    const bool r = acc[id] != 0;
+    emul::named_barrier((int)id, (int)nthreads);
+    return r;
+}
+#endif
+
 // ---- Huffman table from its recipe: each thread fills 8 consecutive entries with one 16-byte store --------
 // `nthr` threads (t = 0 .. nthr-1) build this table. The weight class of an entry is found by counting class starts
 // <= the entry in registers (the starts are 14 halfwords, fetched as 7 broadcast words); a group of 8 entries that
@@ -172,24 +195,31 @@ __device__ __forceinline__ void bits_ending_at(const uint32_t* w, uint32_t A, ui
     hi = __funnelshift_l(b, a, sh); lo = __funnelshift_l(c, b, sh);
 }
 
-// Rolling variant for a monotonic walk (second pass): four consecutive words stay in registers; when the position moves
-// down across a word boundary the window slides and ONE new word is fetched, one slide ahead of its first use. Between
-// two get() calls A must not grow and must not drop by more than 64 bits. Reads down to word (A - 1) / 32 - 3.
-struct BitWin {
-    const uint32_t* w; uint32_t wi, a, b, c, d;
-    __device__ __forceinline__ void init(const uint32_t* words, uint32_t A)
+// Position-based reader of a backward bitstream in the staged chunk. `ap` = bit address of the next unread bit (the
+// highest one) + 8 x the shared-memory byte address of the region: (ap >> 3) & ~3 is then the shared address of the word
+// that holds the bit and ~ap (mod 32) the left shift that brings it to bit 31 -- a window costs two logic operations,
+// three loads and two funnel shifts, and consuming n bits is one subtraction. Reads down to two words below the bit.
+struct BitPos {
+    uint32_t ap;
+#ifdef RNSC_EMUL
+    const uint32_t* w;
+    __device__ __forceinline__ BitPos(const uint8_t* region, uint32_t A) : ap(A - 1u), w((const uint32_t*)region) {}
+    __device__ __forceinline__ void window(uint32_t& hi, uint32_t& lo) const
     {
-        w = words; wi = (A - 1) >> 5;
-        a = w[wi]; b = w[wi - 1]; c = w[wi - 2]; d = w[wi - 3];
+        const uint32_t wi = ap >> 5, a = w[wi], b = w[wi - 1], c = w[wi - 2];
+        hi = __funnelshift_l(b, a, ~ap); lo = __funnelshift_l(c, b, ~ap);
     }
-    __device__ __forceinline__ void get(uint32_t A, uint32_t& hi, uint32_t& lo)
+#else
+    __device__ __forceinline__ BitPos(const uint8_t* region, uint32_t A) : ap(A - 1u + 8u * (uint32_t)__cvta_generic_to_shared(region)) {}
+    __device__ __forceinline__ void window(uint32_t& hi, uint32_t& lo) const
     {
-        const uint32_t nwi = (A - 1) >> 5;
-        if (nwi < wi) { a = b; b = c; c = d; --wi; d = w[wi - 3]; }
-        if (nwi < wi) { a = b; b = c; c = d; --wi; d = w[wi - 3]; }
-        const uint32_t sh = (32u - (A & 31u)) & 31u;
-        hi = __funnelshift_l(b, a, sh); lo = __funnelshift_l(c, b, sh);
+        const uint32_t ad = (ap >> 3) & ~3u;
+        uint32_t a, b, c;
+        asm volatile("ld.shared.u32 %0, [%3];\nld.shared.u32 %1, [%3+-4];\nld.shared.u32 %2, [%3+-8];" : "=r"(a), "=r"(b), "=r"(c) : "r"(ad));
+        hi = __funnelshift_l(b, a, ~ap); lo = __funnelshift_l(c, b, ~ap);
     }
+#endif
+    __device__ __forceinline__ void consume(uint32_t nbits) { ap -= nbits; }
 };
 
 // One symbol: table entry `ev` = symbol << 8 | code length. The funnel shifts take the entry itself as the shift
@@ -235,31 +265,32 @@ struct HufTab {
          hi = __funnelshift_l(lo, hi, ev); lo = __funnelshift_l(0u, lo, ev); } while (0)
 
 // Advances from consumed-bit position p to the first symbol boundary >= lim; counts the symbols decoded. Nothing is
-// written, so while the limit is far the walk strides over up to two symbols per table access (the skip table).
-__device__ __forceinline__ void huf_walk(const uint32_t* words, uint32_t abit, const HufTab& tab, uint32_t& p, uint32_t lim, uint32_t& cnt)
+// written, so while the limit is far the walk strides over up to two symbols per table access (the skip table). The
+// last < 48 bits go one symbol at a time out of ONE window (48 + a 12-bit peek fit its 64 bits).
+__device__ __forceinline__ void huf_walk(const uint8_t* region, uint32_t abit, const HufTab& tab, uint32_t& p, uint32_t lim, uint32_t& cnt)
 {
     uint32_t hi, lo, e;
+    BitPos bp(region, abit - p);
     if (tab.skip) {
         while (p + 4 * HUF_LOG_MAX <= lim) {
-            bits_ending_at(words, abit - p, hi, lo);
+            bp.window(hi, lo);
             uint32_t sum = 0;                       // bits 0-5: the four length sums (<= 48); above: the symbol counts
 #pragma unroll
             for (int k = 0; k < 4; ++k) { e = tab.lookup_skip(hi); hi = __funnelshift_l(lo, hi, e); lo = __funnelshift_l(0u, lo, e); sum += e; }
-            p += sum & 63u; cnt += sum >> 6;
+            p += sum & 63u; bp.consume(sum & 63u); cnt += sum >> 6;
         }
     } else {
         while (p + 4 * HUF_LOG_MAX <= lim) {
-            bits_ending_at(words, abit - p, hi, lo);
+            bp.window(hi, lo);
             uint32_t adv = 0;                       // the low byte sums the four code lengths (<= 48)
 #pragma unroll
             for (int k = 0; k < 4; ++k) { RNSC_HUF_STEP(hi, lo, tab, e); adv += e; }
-            p += adv & 0xFFu; cnt += 4;
+            p += adv & 0xFFu; bp.consume(adv & 0xFFu); cnt += 4;
         }
     }
-    while (p < lim) {
-        bits_ending_at(words, abit - p, hi, lo);
-        RNSC_HUF_STEP(hi, lo, tab, e);
-        p += e & 0xFFu; cnt += 1;
+    if (p < lim) {
+        bp.window(hi, lo);
+        do { RNSC_HUF_STEP(hi, lo, tab, e); p += e & 0xFFu; cnt += 1; } while (p < lim);
     }
 }
 
@@ -278,8 +309,10 @@ __device__ __forceinline__ uint32_t stash_fetch(const FastParams& P, uint32_t c,
     return P.n[c];
 }
 
-// Decodes every Huffman stream of the chunk (ws->head.st[]) from the staged chunk into the region. Three barriers
-// in the common case. Returns 0 on success (same value in all threads).
+// Decodes every Huffman stream of the chunk (ws->head.st[]) from the staged chunk into the region. The threads of one
+// Huffman-coded frame form a group of whole warps (PlanHead::grp_first) that synchronises on its own named barrier
+// between the passes: a frame of short codes (many symbols per bit, long second pass) does not hold up the others, and
+// the CTA meets again only at the end. Returns 0 on success (same value in all threads).
 template <int NTH>
 __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, PhaseClock& pc)
 {
@@ -287,38 +320,43 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* words = (const uint32_t*)region;
     const PlanHead& hd = ws->head;
-    const uint32_t nst = hd.nst, sub = hd.sub;
+    const uint32_t nst = hd.nst;
     uint32_t j = 0;
     while (j + 1 < nst && (uint32_t)tid >= hd.st_first[j + 1]) ++j;
-    const bool active = (uint32_t)tid < hd.st_first[nst];
+    uint32_t g = 0;
+    while (g + 1 < (uint32_t)PLAN_MAX_HUF && (uint32_t)tid >= hd.grp_first[g + 1]) ++g;
+    const bool member = (uint32_t)tid < hd.grp_first[PLAN_MAX_HUF];       // takes part in its group's barriers
+    const uint32_t bar_id = 1u + g, bar_n = hd.grp_first[g + 1] - hd.grp_first[g];
     const uint32_t t0 = hd.st_first[j], k = (uint32_t)tid - t0;
     const StreamPlan sp = hd.st[j];
-    const uint32_t T = sp.tbits, abit = sp.abit;
+    const uint32_t T = sp.tbits, abit = sp.abit, sub = sp.sub;
     const HufTab tab((const uint16_t*)(region + sp.tab_off), ws->skip_on ? region + sp.skip_off : nullptr, sp.log, sp.pitch);
     const uint32_t s0 = k * sub, lim = min(s0 + sub, T);
+    const bool active = member && s0 < T;                                  // the padding threads of a group only keep its barriers company
     uint32_t my_start = 0, my_end = 0, my_cnt = 0;
     if (active) {
         uint32_t p = s0 > FAST_WARM_BITS ? s0 - FAST_WARM_BITS : 0, dummy = 0;
-        huf_walk(words, abit, tab, p, s0, dummy);
+        huf_walk(region, abit, tab, p, s0, dummy);
         my_start = p;
-        huf_walk(words, abit, tab, p, lim, my_cnt);
+        huf_walk(region, abit, tab, p, lim, my_cnt);
         my_end = p;
     }
     pc.mark(PH_HUF1);
-    uint32_t inc;
-    for (int round = 0;; ++round) {
+    uint32_t inc = 0;
+    bool fail = false;
+    if (member) for (int round = 0;; ++round) {
         inc = warp_inclusive_scan(active ? my_cnt : 0u);
         ws->sub_end[tid] = my_end; ws->sub_inc[tid] = inc;
         if (lane == 31) ws->warp_tot[warp] = inc;
-        __syncthreads();
+        bar_named(bar_id, bar_n);
         // a sub-sequence must start where its predecessor ended; repair the (rare) ones that did not synchronise
         const bool bad = active && k > 0 && ws->sub_end[tid - 1] != my_start;
         const uint32_t want = bad ? ws->sub_end[tid - 1] : 0;
-        if (!__syncthreads_or(bad)) break;
-        if (round >= NTH) return 1;                  // cannot happen for a consistent stream: every round fixes at least one more sub-sequence
+        if (!bar_named_or(bar_id, bar_n, bad)) break;
+        if (round >= NTH) { fail = true; break; }    // cannot happen for a consistent stream: every round fixes at least one more sub-sequence
         if (bad) {
             uint32_t p = want; my_start = p; my_cnt = 0;
-            if (p < lim) huf_walk(words, abit, tab, p, lim, my_cnt);
+            if (p < lim) huf_walk(region, abit, tab, p, lim, my_cnt);
             my_end = p;
         }
     }
@@ -328,15 +366,16 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
     const uint32_t nx = ws->next;
 #pragma unroll
     for (int q = 0; q < PF; ++q) { const uint32_t idx = (uint32_t)tid + (uint32_t)q * NTH; pf[q] = (nx != FAST_NONE && idx < ST_WORDS) ? stash_fetch(P, nx, idx) : 0u; }
-    // output offset inside my stream = CTA exclusive scan of the counts minus the scan value at the stream's first thread
+    // output offset inside my stream = exclusive scan of the counts over the warps minus the scan value at the stream's first
+    // thread: only warps of my own group lie between the two, the (possibly unfinished) totals of other groups cancel
     const uint32_t wt = lane < NW ? ws->warp_tot[lane] : 0u;
     const uint32_t wex = warp_inclusive_scan(wt) - wt;                        // lane w: symbols before warp w
     const uint32_t ex = __shfl_sync(0xffffffffu, wex, warp) + inc - (active ? my_cnt : 0u);
     const uint32_t base = __shfl_sync(0xffffffffu, wex, (int)(t0 >> 5)) + ((t0 & 31u) ? ws->sub_inc[t0 - 1] : 0u);
     const uint32_t off = ex - base;
     pc.mark(PH_HUFSCAN);
-    bool bad = false;
-    if (active && (uint32_t)tid + 1 == hd.st_first[j + 1]) bad = (my_end != T) || (off + my_cnt != sp.count);
+    bool bad = fail;
+    if (active && s0 + sub >= T) bad = bad || (my_end != T) || (off + my_cnt != sp.count);      // the stream's last sub-sequence
     if (active && my_cnt && off < sp.count) {
         uint32_t p = my_start, rem = min(my_cnt, sp.count - off), hi, lo, e;      // clamped: a corrupt stream cannot write outside its output
         uint32_t li = sp.lit0 + off;                                                   // literal index of my first symbol
@@ -354,19 +393,31 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
         }
         if (li + rem <= run_end) {      // all my literals belong to one run (always, without sequences)
             uint8_t* o = region + sp.out + li + shift;
-            while (((uintptr_t)o & 3u) && rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
-            BitWin bw; bw.init(words, abit - p);
-            while (rem >= 4) {
-                bw.get(abit - p, hi, lo);
+            BitPos bp(region, abit - p);
+            // up to three symbols bring the output to a word boundary: one window, predicated steps
+            const uint32_t head = min(rem, (4u - ((uint32_t)(uintptr_t)o & 3u)) & 3u);
+            if (head) {
+                bp.window(hi, lo);
+                uint32_t adv = 0;
+#pragma unroll
+                for (uint32_t q = 0; q < 3; ++q) if (q < head) { RNSC_HUF_STEP(hi, lo, tab, e); adv += e; o[q] = (uint8_t)(e >> 8); }
+                o += head; rem -= head; bp.consume(adv & 0xFFu);
+            }
+            for (; rem >= 4; rem -= 4) {
+                bp.window(hi, lo);
                 uint32_t word = 0, adv = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     RNSC_HUF_STEP(hi, lo, tab, e); adv += e;
                     word = __byte_perm(word, e, q == 0 ? 0x3215u : (q == 1 ? 0x3250u : (q == 2 ? 0x3510u : 0x5210u)));   // byte q <- symbol
                 }
-                *(uint32_t*)o = word; o += 4; p += adv & 0xFFu; rem -= 4;
+                *(uint32_t*)o = word; o += 4; bp.consume(adv & 0xFFu);
             }
-            while (rem) { bits_ending_at(words, abit - p, hi, lo); RNSC_HUF_STEP(hi, lo, tab, e); p += e & 0xFFu; *o++ = (uint8_t)(e >> 8); --rem; }
+            if (rem) {
+                bp.window(hi, lo);
+#pragma unroll
+                for (uint32_t q = 0; q < 3; ++q) if (q < rem) { RNSC_HUF_STEP(hi, lo, tab, e); o[q] = (uint8_t)(e >> 8); }
+            }
         } else {
             // runs can be a few literals long (the key region of a VBZ frame): one symbol at a time from a buffered
             // 64-bit window, switching the output position whenever a run ends (the next run is fetched ahead)

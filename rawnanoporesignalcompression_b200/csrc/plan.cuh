@@ -51,7 +51,7 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
 // One Huffman bitstream: payload bits, absolute bit address of the end mark in the region, symbols, region offset of
 // the frame's output, literal index of its first symbol, its table; and, when LZ sequences follow, where they are in
 // ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
-struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pitch, skip_off, pad2; };   // sop: index of the frame's SeqOp or ~0; pitch: bytes per table entry
+struct StreamPlan { uint32_t tbits, abit, count, out, lit0, tab_off, log, sop, regen, pitch, skip_off, sub; };   // sop: index of the frame's SeqOp or ~0; pitch: bytes per table entry; sub: sub-sequence length in bits
 struct FillOp { uint32_t dst_off, len, value; };                         // RLE block / RLE literals without sequences
 // LZ sequences of a frame: entries [seq_base, seq_base + nseq] of the sequence pool. lit = region offset of raw literals or
 // the RLE byte; meta_off = region offset of the run table the kernel copies there: nruns x {first literal index, shift to
@@ -70,6 +70,7 @@ struct PlanHead {                // what the fast kernel copies to shared memory
     int32_t view_status;
     uint32_t early;                // bit k: the sequences of sop[k] (raw / RLE literals) are executed by the CTA's last warp while the others decode Huffman streams
     uint32_t zone_off, zone_len;   // region bytes that are dead after the Huffman stage (the largest bitstream area): match resolver scratch
+    uint32_t grp_first[PLAN_MAX_HUF + 1];   // thread groups of the Huffman stage, one per Huffman-coded frame: first thread (a multiple of 32)
     uint32_t st_first[PLAN_MAX_STREAMS + 1];
     StreamPlan st[PLAN_MAX_STREAMS];
     FillOp fill[5];
@@ -90,6 +91,8 @@ struct PlanParams {
     uint32_t* counts;            // [0..3] list lengths (atomic), zeroed before the launch
     uint32_t region[3];          // bytes of dynamic region available to a class S / A / B CTA
     const uint32_t* deftab;      // predefined FSE decoding tables: LL[64] OF[32] ML[64]
+    uint32_t has_origin;         // the fast kernel has global scratch for the match resolver's origin words (else: chunks that need it go to the general decoder)
+    uint32_t cost_bit, cost_sym; // Huffman stage cost model: a sub-sequence of b bits holding s symbols costs cost_bit * b + cost_sym * s
     uint32_t* seq_pool; uint32_t pool_cap; unsigned long long* pool_cursor;   // 64-bit cursor: a hostile batch can ask for more than 2^32 entries; bump-allocated sequence storage (SEQ_WORDS words per entry)
 };
 
@@ -411,7 +414,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 sp.count = fp.nstreams == 1 ? fp.regen : (j < 3 ? q : fp.regen - 3 * q);
                 sp.out = fp.dst_off; sp.lit0 = fp.nstreams == 1 ? 0 : j * q;
                 sp.tab_off = pl->h[fp.huf].tab_off; sp.skip_off = pl->h[fp.huf].skip_off; sp.log = pl->h[fp.huf].log;
-                sp.sop = my_sop; sp.regen = fp.regen; sp.pitch = 2; sp.pad2 = 0;
+                sp.sop = my_sop; sp.regen = fp.regen; sp.pitch = 2; sp.sub = 0;
                 if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }
@@ -430,18 +433,53 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     }
     for (int f = nf; f < 5 && nf > 1; ++f) hd->view[f] = ViewPlan{cbase, 0};
     if (n == 0 && tot_fcs) vst = RNSC_ERR_REMAINING;
+    if (!P.has_origin && nseq_tot > FAST_ORDERED_MAX) {     // the pointer-jumping resolver keeps its origin words in the dead bitstream area or in global scratch
+        uint32_t mb = 0;
+        for (uint32_t k = 0; k < nsop; ++k) mb += hd->sop[k].mbytes;
+        if ((unsigned long long)mb * 4 > zone_len) slow = true;
+    }
     if (slow) { plan_emit(P, c, CLS_SLOW); return; }
     // Frames whose sequences do not wait for Huffman literals (C5: Lhigh) get the last warp to themselves during the Huffman stage
     uint32_t early = 0;
     if (nst && nseq_tot <= FAST_ORDERED_MAX) for (uint32_t k = 0; k < nsop; ++k) if (hd->sop[k].ltype != 2) early |= 1u << k;
     const uint32_t nth_h = (early || cls == CLS_B) ? nth - 32 : nth;      // class B: the last warp also fetches the CTA's next chunk index meanwhile
-    uint32_t sub = nst ? (ttot + (nth_h - nst) - 1) / (nth_h - nst) : PLAN_SUB_MIN;
-    if (sub < PLAN_SUB_MIN) sub = PLAN_SUB_MIN;
-    if (cls == CLS_B) sub = ((sub + 31u) >> 5 | 1u) << 5;   // an odd number of 32-bit words: the lanes of a warp start in 32 different banks of the staged
-                                                            // bitstream (worth its rounding loss only where one CTA has the SM to itself)
-    uint32_t first = 0;
-    for (uint32_t s = 0; s < nst; ++s) { hd->st_first[s] = first; first += (hd->st[s].tbits + sub - 1) / sub; }
+    // Thread groups: the streams of one Huffman-coded frame (same table, same statistics) share a group of whole warps, so
+    // that the chain check and the scan of a frame synchronise on a named barrier of their own and frames with short codes
+    // (many symbols per bit: long second pass) do not hold up the others. Warps are dealt out in proportion to each
+    // frame's estimated cost, cost_bit per payload bit (first pass) + cost_sym per symbol (second pass); the warm-up is the
+    // same for every thread and drops out.
+    uint32_t gw[PLAN_MAX_HUF] = {0, 0, 0}, gt[PLAN_MAX_HUF] = {0, 0, 0}, gc[PLAN_MAX_HUF] = {0, 0, 0}, gn[PLAN_MAX_HUF] = {0, 0, 0}, gs0[PLAN_MAX_HUF] = {0, 0, 0};
+    uint32_t ngrp = 0;
+    for (uint32_t s = 0; s < nst; ++s) {
+        if (s == 0 || hd->st[s].tab_off != hd->st[s - 1].tab_off) { gs0[ngrp] = s; ++ngrp; }
+        gt[ngrp - 1] += hd->st[s].tbits; gc[ngrp - 1] += hd->st[s].count; gn[ngrp - 1] += 1;
+    }
+    {
+        const uint32_t nw = nth_h / 32;
+        unsigned long long wsum = 0, wg[PLAN_MAX_HUF];
+        for (uint32_t g = 0; g < ngrp; ++g) { wg[g] = (unsigned long long)P.cost_bit * gt[g] + (unsigned long long)P.cost_sym * gc[g] + 1; wsum += wg[g]; }
+        uint32_t used = 0, big = 0;
+        for (uint32_t g = 0; g < ngrp; ++g) { gw[g] = (uint32_t)((wg[g] * nw + wsum / 2) / wsum); if (gw[g] < 1) gw[g] = 1; used += gw[g]; if (wg[g] > wg[big]) big = g; }
+        while (used > nw) { uint32_t m = 0; for (uint32_t g = 1; g < ngrp; ++g) if (gw[g] > gw[m]) m = g; --gw[m]; --used; }     // nw >= 7 > ngrp: never below one warp
+        if (ngrp) gw[big] += nw - used;
+    }
+    uint32_t first = 0, sub_max = PLAN_SUB_MIN;
+    for (uint32_t g = 0; g < PLAN_MAX_HUF; ++g) {
+        hd->grp_first[g] = first;
+        if (g >= ngrp) continue;
+        const uint32_t nt = gw[g] * 32;
+        uint32_t sub = nt > gn[g] ? (gt[g] + (nt - gn[g]) - 1) / (nt - gn[g]) : gt[g];
+        if (sub < PLAN_SUB_MIN) sub = PLAN_SUB_MIN;
+        if (cls == CLS_B) sub = ((sub + 31u) >> 5 | 1u) << 5;   // an odd number of 32-bit words: the lanes of a warp start in 32 different banks of the staged
+                                                                // bitstream (worth its rounding loss only where one CTA has the SM to itself)
+        if (sub > sub_max) sub_max = sub;
+        uint32_t t = first;
+        for (uint32_t s = gs0[g]; s < gs0[g] + gn[g]; ++s) { hd->st[s].sub = sub; hd->st_first[s] = t; t += (hd->st[s].tbits + sub - 1) / sub; }
+        first += nt;
+    }
+    hd->grp_first[PLAN_MAX_HUF] = first;
     for (uint32_t s = nst; s <= PLAN_MAX_STREAMS; ++s) hd->st_first[s] = first;
+    const uint32_t sub = sub_max;
     hd->need = region; hd->phase = phase; hd->stage_bytes = stage;
     hd->nhuf = nhuf; hd->nst = nst; hd->sub = sub; hd->nfill = nfill; hd->nsop = nsop; hd->nseq = nseq_tot; hd->view_status = vst; hd->early = early; hd->zone_off = zone_off; hd->zone_len = zone_len;
     plan_emit(P, c, cls);

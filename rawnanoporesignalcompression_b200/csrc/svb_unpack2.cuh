@@ -23,22 +23,24 @@ constexpr int U2_SPT = 16;
 
 // C4/C5: what one key byte (four 2-bit codes) says about its four samples. x = byte-permute selectors that pull the
 // samples' units out of the next four nibbles (low half) / bytes (high half) of the stream windows, a zero byte for
-// samples of another class; y = bits to drop from the nibble window | bits to drop from the byte window << 8;
-// z, w = the class offsets (C5: 1 / 17 / 0) of samples 0,1 and 2,3 as 16-bit lanes.
+// samples of another class; y = bits to drop from the nibble window | large values << 5 | bits to drop from the byte
+// window << 8 | selectors of the samples' large values (bytes of the thread's four-byte Llow / Lhigh windows, counted from
+// the group's first one) << 16; z, w = the class offsets (C5: 1 / 17 / 273) of samples 0,1 and 2,3 as 16-bit lanes.
 struct alignas(16) KeyLut { uint32_t x, y, z, w; };
 
 template <int CODEC>
 __device__ inline KeyLut make_key_lut(uint32_t kbyte)
 {
-    uint32_t selS = 0, selM = 0, nS = 0, nM = 0, off[4];
+    uint32_t selS = 0, selM = 0, selL = 0, nS = 0, nM = 0, nL = 0, off[4];
     for (int j = 0; j < 4; ++j) {
         const uint32_t c = (kbyte >> (2 * j)) & 3u;
         selS |= (c == 1 ? nS : 4u) << (4 * j);
         selM |= (c == 2 ? nM : 4u) << (4 * j);
-        off[j] = CODEC == RNSC_C5 ? (c == 1 ? 1u : (c == 2 ? 17u : 0u)) : 0u;
-        nS += c == 1; nM += c == 2;
+        selL |= (c == 3 ? nL : 4u) << (4 * j);
+        off[j] = CODEC == RNSC_C5 ? (c == 1 ? 1u : (c == 2 ? 17u : (c == 3 ? 273u : 0u))) : 0u;
+        nS += c == 1; nM += c == 2; nL += c == 3;
     }
-    return KeyLut{selS | (selM << 16), (4 * nS) | ((8 * nM) << 8), off[0] | (off[1] << 16), off[2] | (off[3] << 16)};
+    return KeyLut{selS | (selM << 16), (4 * nS) | (nL << 5) | ((8 * nM) << 8) | (selL << 16), off[0] | (off[1] << 16), off[2] | (off[3] << 16)};
 }
 
 template <int NTH>
@@ -187,35 +189,33 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
                 sw[0] = load_bits32(a1, 4 * p1); sw[1] = load_bits32(a1, 4 * (p1 + n1a));
                 load_bits64(a2, 8 * p2, mlo[0], mhi[0]); load_bits64(a2, 8 * (p2 + n2a), mlo[1], mhi[1]);
             }
-            if (c3 <= 4) {
-                // four samples at a time: the key byte's table entry pulls their units out of the windows with two byte
+            // the thread's (up to three) large values: bytes p3.. of the low and high byte streams, pulled into their samples by
+            // the key byte's selectors like the other classes -- no branch, no patching. A high byte of 0xFE or more could
+            // wrap the uint16 sum with the offset 273 (C5.hpp:224-228) into the neighbouring lane: such a thread (corrupt
+            // input only) takes the byte-wise path below.
+            uint32_t lo4 = 0, hi4 = 0;
+            if (m3) { lo4 = load_bits32(a3, 8 * p3); hi4 = load_bits32(a4, 8 * p3); }
+            const uint32_t nhi = ~(hi4 | 0x01010101u);
+            const bool wrap = CODEC == RNSC_C5 && ((nhi - 0x01010101u) & ~nhi & 0x80808080u) != 0;
+            if (c3 <= 3 && !wrap) {
+                // four samples at a time: the key byte's table entry pulls their units out of the windows with byte
                 // permutes; zigzag^-1 runs on two 16-bit lanes per register
-                uint32_t zp[S / 2];
+                uint32_t zp[S / 2], r3x = 0;                                       // r3x: large values consumed so far x 0x1111
 #pragma unroll
                 for (int g = 0; g < S / 4; ++g) {
                     const int h = g >> 1;
                     const KeyLut e = lut[__byte_perm(kb, 0u, 0x4440u | (uint32_t)g)];
                     uint32_t x = sw[h] & 0xFFFFu;                                  // next four nibbles -> four bytes
                     x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu;
-                    const uint32_t zb = __byte_perm(x, 0u, e.x) | __byte_perm(mlo[h], 0u, e.x >> 16);
+                    const uint32_t sel3 = (e.y >> 16) + r3x;                       // selectors stay below 8 (no large value: 4 + at most 3 consumed)
+                    r3x += ((e.y >> 5) & 7u) * 0x1111u;
+                    const uint32_t zb = __byte_perm(x, 0u, e.x) | __byte_perm(mlo[h], 0u, e.x >> 16) | __byte_perm(lo4, 0u, sel3);
+                    const uint32_t zh = __byte_perm(hi4, 0u, sel3);
                     sw[h] = __funnelshift_r(sw[h], 0u, e.y);                       // low 5 bits of e.y: 4 x nibbles used (<= 16)
-                    const uint32_t shm = e.y >> 8;                                 // 8 x bytes used (<= 32)
+                    const uint32_t shm = (e.y >> 8) & 63u;                         // 8 x bytes used (<= 32)
                     mlo[h] = __funnelshift_rc(mlo[h], mhi[h], shm); mhi[h] = __funnelshift_rc(mhi[h], 0u, shm);
-                    zp[2 * g] = __byte_perm(zb, 0u, 0x4140u) + e.z;
-                    zp[2 * g + 1] = __byte_perm(zb, 0u, 0x4342u) + e.w;
-                }
-                if (m3) {   // the thread's (up to four) large values: bytes p3.. of the low and high byte streams, patched into their lanes
-                    const uint32_t lo4 = load_bits32(a3, 8 * p3), hi4 = load_bits32(a4, 8 * p3);
-                    const uint32_t a = __byte_perm(lo4, hi4, 0x5140), b = __byte_perm(lo4, hi4, 0x7362);
-                    uint32_t zq = ((a + OL) & 0xFFFFu) | ((a & 0xFFFF0000u) + (OL << 16));         // uint16 arithmetic (C5.hpp:224-228)
-                    uint32_t zq2 = ((b + OL) & 0xFFFFu) | ((b & 0xFFFF0000u) + (OL << 16));
-                    for (uint32_t mm = m3; mm; mm &= mm - 1u) {
-                        const uint32_t j2 = (uint32_t)__ffs((int)mm) - 1u;         // 2 x sample index
-                        const uint32_t pv = (zq & 0xFFFFu) << ((j2 & 2u) << 3), r = j2 >> 2;
-                        zq = __funnelshift_r(zq, zq2, 16); zq2 >>= 16;
-#pragma unroll
-                        for (int q = 0; q < S / 2; ++q) if (r == (uint32_t)q) zp[q] |= pv;
-                    }
+                    zp[2 * g] = __byte_perm(zb, zh, 0x5140u) + e.z;
+                    zp[2 * g + 1] = __byte_perm(zb, zh, 0x7362u) + e.w;
                 }
 #pragma unroll
                 for (int q = 0; q < S / 2; ++q) {

@@ -19,6 +19,8 @@ static const std::function<void()>* cur_body = nullptr;
 
 // block barrier state
 static unsigned bar_gen = 0; static int bar_arrived = 0;
+// named barriers (bar.sync id, nthreads): released when `want` fibers have arrived
+static unsigned nb_gen[16]; static int nb_arrived[16], nb_want[16];
 // warp exchange state
 struct WarpEx { unsigned gen = 0; unsigned arrived = 0; unsigned want = 0xffffffffu; unsigned long long buf[2][32]; unsigned arrived_mask_done[2] = {0, 0}; };
 static std::vector<WarpEx> warps;
@@ -33,6 +35,13 @@ void block_barrier()
     if (cur == 0) full_hist[0].push_back(fibers[cur].site); else if (cur == 32) full_hist[1].push_back(fibers[cur].site);
     unsigned g = bar_gen; bar_arrived++;
     while (bar_gen == g) yield();
+}
+
+void named_barrier(int id, int count)
+{
+    fibers[cur].site = __builtin_return_address(0); fibers[cur].kind = 3;
+    unsigned g = nb_gen[id]; nb_arrived[id]++; nb_want[id] = count;
+    while (nb_gen[id] == g) yield();
 }
 
 unsigned warp_exchange(unsigned mask, unsigned long long val, unsigned long long* all32)
@@ -58,6 +67,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned bx = 0; bx < grid.x; ++bx) {
         bar_gen = 0; bar_arrived = 0; full_hist[0].clear(); full_hist[1].clear();
+        for (int i = 0; i < 16; ++i) { nb_gen[i] = 0; nb_arrived[i] = 0; nb_want[i] = 0; }
         warps.assign((nt + 31) / 32, WarpEx());
         for (int i = 0; i < nt; ++i) {
             Fiber& f = fibers[i]; f.done = false; f.nbar = 0;
@@ -75,6 +85,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
             }
             // release block barrier when every live fiber has arrived
             if (alive > 0 && bar_arrived >= alive) { bar_arrived = 0; bar_gen++; progressed = 1; }
+            for (int i = 0; i < 16; ++i) if (nb_arrived[i] && nb_arrived[i] >= nb_want[i]) { nb_arrived[i] = 0; nb_gen[i]++; progressed = 1; }
             // release warp exchanges when every live lane of the warp has arrived
             for (size_t w = 0; w < warps.size(); ++w) {
                 WarpEx& W = warps[w]; if (!W.arrived) continue;
@@ -85,6 +96,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                 // every live fiber is parked: either all at a barrier (handled above) or a deadlock
                 bool any = false;
                 for (size_t w = 0; w < warps.size(); ++w) if (warps[w].arrived) any = true;
+                for (int i = 0; i < 16; ++i) if (nb_arrived[i]) { fprintf(stderr, "cuda_emul: named barrier %d stuck: %d/%d arrived\n", i, nb_arrived[i], nb_want[i]); abort(); }
                 if (!any && bar_arrived < alive) { fprintf(stderr, "cuda_emul: deadlock (block %u): %d/%d at barrier\n", bx, bar_arrived, alive); abort(); }
                 if (any && bar_arrived > 0) {
                     fprintf(stderr, "cuda_emul: divergent barrier (block %u)\n", bx);

@@ -39,6 +39,7 @@ static const int warpSize = 32;
 namespace emul {
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 void block_barrier();
+void named_barrier(int id, int count);
 unsigned warp_exchange(unsigned mask, unsigned long long val, unsigned long long* all32);  // returns arrived mask
 }
 
