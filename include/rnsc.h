@@ -2,7 +2,7 @@
  * tomas-gr/RawNanoporeSignalCompression.
  *
  * Plain pointers and sizes only; no exceptions cross this boundary; every entry point is thread-safe
- * when each thread uses its own rnsc_ctx (the pod5-named wrappers serialise on one process context).
+ * when each thread uses its own rnsc_ctx (the pod5-named wrappers use one context per calling thread).
  * The library needs a CUDA device: rnsc_create() fails with RNSC_ERR_NO_DEVICE otherwise -- there is
  * no CPU fallback.
  *
@@ -141,8 +141,15 @@ int rnsc_get_cta_spans(rnsc_ctx* ctx, uint64_t out[RNSC_SPAN_WORDS]);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t rnsc_launch_count(const rnsc_ctx* ctx);
 
-/* ---- names the reference's C API exports for this path (pod5_format/c_api.h:678-711), same signatures,
- *      backed by one lazily created process-wide context; errors via rnsc_last_error(). ------------------ */
+/* The calling thread's own context (created on first use on the current CUDA device, handed on to another thread when
+ * its owner exits). What the pod5-named entry points below and libpod5_rnsc.so (include/pod5_rnsc.h) run on: concurrent
+ * callers -- the reference's AsyncSignalLoader workers, async_signal_loader.cpp:176-220 -- do not serialise. NULL without
+ * a CUDA device (rnsc_last_error() says why). */
+rnsc_ctx* rnsc_thread_context(void);
+
+/* ---- names the reference's C API exports for this path (pod5_format/c_api.h:678-711), same signatures, rnsc_ prefix
+ *      (the un-prefixed names with pod5_error_t values live in libpod5_rnsc.so, include/pod5_rnsc.h: link that library in
+ *      front of the reference's to take the calls over); each runs on rnsc_thread_context(); errors via rnsc_last_error(). */
 typedef int rnsc_pod5_error_t; /* 0 = POD5_OK */
 size_t rnsc_pod5_vbz_compressed_signal_max_size(size_t sample_count);                      /* c_api.cpp:1177 */
 rnsc_pod5_error_t rnsc_pod5_vbz_compress_signal(const int16_t* signal, size_t signal_size, char* compressed_signal_out,

@@ -803,15 +803,31 @@ int rnsc_decompress_chunk(rnsc_ctx* c, int codec, const uint8_t* in, size_t in_s
 // ---------------------------------------------------------------------------------------------------
 // pod5-named entry points (c_api.h:678-711) on one process-wide context
 // ---------------------------------------------------------------------------------------------------
-static std::mutex g_proc_mu;
-static rnsc_ctx* g_proc_ctx = nullptr;
+// One context per calling thread, created on first use on the current device and handed to another thread when its
+// owner exits (AsyncSignalLoader-style worker pools call the per-chunk functions concurrently, async_signal_loader.cpp:
+// 176-220; a single mutexed context would serialise them). Contexts are parked, never destroyed: at process exit the
+// CUDA runtime may already be gone when thread-local destructors run.
+static std::mutex g_pool_mu;
+static std::vector<rnsc_ctx*> g_ctx_pool;
 static std::atomic<int> g_variant{RNSC_C5};
-static rnsc_ctx* proc_ctx()
+namespace {
+struct ThreadCtx {
+    rnsc_ctx* c = nullptr;
+    ~ThreadCtx() { if (c) { std::lock_guard<std::mutex> lk(g_pool_mu); g_ctx_pool.push_back(c); } }
+};
+thread_local ThreadCtx t_ctx;
+}  // namespace
+rnsc_ctx* rnsc_thread_context(void)
 {
-    std::lock_guard<std::mutex> lk(g_proc_mu);
-    if (!g_proc_ctx) g_proc_ctx = rnsc_create(-1);
-    return g_proc_ctx;
+    if (t_ctx.c) return t_ctx.c;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_ctx_pool.empty()) { t_ctx.c = g_ctx_pool.back(); g_ctx_pool.pop_back(); }
+    }
+    if (!t_ctx.c) { t_ctx.c = rnsc_create(-1); if (t_ctx.c) t_ctx.c->host_threads = 1; }     // a per-chunk caller compresses its frames on its own thread
+    return t_ctx.c;
 }
+static rnsc_ctx* proc_ctx() { return rnsc_thread_context(); }
 int rnsc_set_pgnano_variant(int codec) { if (codec < RNSC_VBZ || codec > RNSC_C5) return fail(RNSC_ERR_BAD_ARG, "variant must be one of VBZ, VBZ0, C1..C5"); g_variant = codec; return RNSC_OK; }
 int rnsc_get_pgnano_variant(void) { return g_variant; }
 
