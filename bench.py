@@ -628,6 +628,28 @@ def run_rnsc(args):
         del w5, s_comp, s_out
         torch.cuda.empty_cache()
 
+    # ---- the per-chunk seam (signal_table_writer.cpp:98,107 / signal_table_reader.cpp:133,138, benchmark.cpp:134-190): one call
+    #      per chunk through the C++ functions and the C API names, as a drop-in caller would make them ----
+    seam_exe = os.path.join(ROOT, "integration", "_build", "seam_bench")
+    if not args.no_extra and rank == 0 and os.path.exists(seam_exe):
+        try:
+            import tempfile
+            ls = synth.read_lengths(args.seam_reads, SEED)
+            ssig = synth.generate_reads(ls, SEED, model, device=dev).cpu().numpy()
+            so, sn, _ = synth.chunk_table(ls)
+            with tempfile.TemporaryDirectory() as td:
+                pth = os.path.join(td, "chunks.bin")
+                synth.write_chunk_file(pth, ssig, so, sn)
+                r = subprocess.run([seam_exe, pth, "4"], capture_output=True, text=True, timeout=600)
+            seam = json.loads(r.stdout) if r.returncode == 0 else {"error": r.stderr[-400:]}
+            seam["what"] = (f"reference's per-chunk benchmark loop (one compress + one decompress call per chunk, host buffers) over the first {args.seam_reads} reads "
+                            f"({int(sn.sum())} samples, {len(sn)} chunks): C++ seam (pod5::/pgnano::compress_signal, decompress_signal on arrow buffers) and C API names")
+            seam["cpu_one_core_decode_GBps"] = cpu["one_core_value"] if cpu else None
+            extra["per_chunk_seam"] = seam
+            log("per-chunk seam", seam)
+        except Exception as ex:  # noqa: BLE001
+            extra["per_chunk_seam"] = {"error": str(ex)}
+
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u8",
@@ -714,6 +736,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=1000, help="reads in the bounded CPU sample (>= 1000 chunks: also the encode byte-parity sample)")
     ap.add_argument("--vbz-reads", type=int, default=0, help="reads per GPU of the R9.4.1 VBZ leg (0 = --reads)")
     ap.add_argument("--rc-reads", type=int, default=2000, help="reads per GPU of the range coder leg")
+    ap.add_argument("--seam-reads", type=int, default=200, help="reads of the per-chunk seam leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-reads", type=int, default=0)
     ap.add_argument("--host-threads", type=int, default=0)

@@ -29,7 +29,12 @@ EXPORTS = [
     "rnsc_dev_exclusive_scan_u32", "rnsc_launch_count", "rnsc_decode_class_counts", "rnsc_set_profiling", "rnsc_get_phase_cycles", "rnsc_get_cta_spans",
     "rnsc_pod5_vbz_compressed_signal_max_size", "rnsc_pod5_vbz_compress_signal", "rnsc_pod5_pinanoraw_compress_signal",
     "rnsc_pod5_vbz_decompress_signal", "rnsc_pod5_pinanoraw_decompress_signal", "rnsc_set_pgnano_variant",
-    "rnsc_get_pgnano_variant",
+    "rnsc_get_pgnano_variant", "rnsc_thread_context",
+]
+# libpod5_rnsc.so (include/pod5_rnsc.h): the reference's own C API names for this path
+POD5_EXPORTS = [
+    "pod5_get_error_no", "pod5_get_error_string", "pod5_vbz_compressed_signal_max_size", "pod5_vbz_compress_signal",
+    "pod5_pinanoraw_compress_signal", "pod5_vbz_decompress_signal", "pod5_pinanoraw_decompress_signal",
 ]
 
 
@@ -80,9 +85,28 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "rnsc_pod5_pinanoraw_decompress_signal": (i32, [vp, sz, sz, vp]),
         "rnsc_set_pgnano_variant": (i32, [i32]),
         "rnsc_get_pgnano_variant": (i32, []),
+        "rnsc_thread_context": (vp, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    return lib
+
+
+def load_pod5(path: Optional[str] = None) -> C.CDLL:
+    """libpod5_rnsc.so: pod5_vbz_compress_signal & co. under the reference's names and pod5_error_t convention."""
+    path = path or os.path.join(os.path.dirname(DEFAULT_LIB), "libpod5_rnsc.so")
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    load()                                     # librnsc.so first (same directory; libpod5_rnsc.so finds it through $ORIGIN)
+    lib = C.CDLL(path)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    for name, (res, args) in {
+        "pod5_get_error_no": (i32, []), "pod5_get_error_string": (C.c_char_p, []),
+        "pod5_vbz_compressed_signal_max_size": (sz, [sz]),
+        "pod5_vbz_compress_signal": (i32, [vp, sz, vp, C.POINTER(sz)]), "pod5_pinanoraw_compress_signal": (i32, [vp, sz, vp, C.POINTER(sz)]),
+        "pod5_vbz_decompress_signal": (i32, [vp, sz, sz, vp]), "pod5_pinanoraw_decompress_signal": (i32, [vp, sz, sz, vp]),
+    }.items():
+        fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
     return lib

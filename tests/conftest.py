@@ -29,6 +29,14 @@ def ref_oracle():
 
 
 @pytest.fixture(scope="session")
+def enc_oracle(oracle):
+    """The checker of the GPU parity tests: the reference's own code (oracle/_ref, prebuilt and shipped to the GPU box)
+    when it exists, else the C port that is pinned to it by the CPU suite."""
+    from oracle_binding import RefOracle
+    return RefOracle() if RefOracle.available() else oracle
+
+
+@pytest.fixture(scope="session")
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
         return json.load(f)

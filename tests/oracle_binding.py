@@ -128,6 +128,12 @@ class RefOracle:
                 r = 3
         return r, out[: sz.value].tobytes()
 
+    def encode(self, codec: int, x: np.ndarray) -> bytes:
+        r, b = self.encode_status(codec, x)
+        if r:
+            raise RuntimeError(f"reference encode status {r}")
+        return b
+
     def decode_status(self, codec: int, b: bytes, n: int):
         out = np.zeros(max(n, 1), np.int16)
         bb = np.frombuffer(bytes(b) + b"\0" * 16, np.uint8)

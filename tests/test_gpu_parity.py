@@ -52,10 +52,10 @@ def test_golden_recipes(gpu_codec, golden, codec):
 
 
 @pytest.mark.parametrize("codec", CODECS, ids=NAMES)
-def test_edge_lengths_vs_oracle(gpu_codec, oracle, codec):
+def test_edge_lengths_vs_oracle(gpu_codec, enc_oracle, codec):
     for n in recipes.EDGE_LENGTHS + recipes.FULL_LENGTHS:
         for x in (recipes.walk(n, 1000 + n, 25.0), recipes.extremes(n, 2000 + n)):
-            st, want = oracle.encode_status(codec, x)
+            st, want = enc_oracle.encode_status(codec, x)
             if st:
                 with pytest.raises(Exception):
                     gpu_codec.compress_signal(x, codec)
@@ -102,8 +102,10 @@ def test_error_semantics(gpu_codec, oracle):
         assert e.value.status == 3
 
 
-def test_synthetic_batch_all_codecs(gpu_codec, oracle):
-    """Seeded synthetic nanopore-shaped reads (R10.4.1 and R9.4.1 models), ragged chunking."""
+def test_synthetic_batch_all_codecs(gpu_codec, enc_oracle):
+    """Seeded synthetic nanopore-shaped reads (R10.4.1 and R9.4.1 models), ragged chunking; every chunk's bytes against
+    the reference encoder."""
+    oracle = enc_oracle
     from rawnanoporesignalcompression_b200 import synth
     for model, seed in ((synth.R10_4_1, 20261018), (synth.R9_4_1, 20261019)):
         lengths = synth.read_lengths(12, seed)
@@ -113,7 +115,7 @@ def test_synthetic_batch_all_codecs(gpu_codec, oracle):
         for codec in CODECS:
             comp, st = gpu_codec.compress_batch(chunks, codec)
             assert not st.any()
-            for c, b in zip(chunks[:6], comp[:6]):
+            for c, b in zip(chunks, comp):
                 assert b == oracle.encode(codec, c), NAMES[codec]
             back, st = gpu_codec.decompress_batch(comp, [len(c) for c in chunks], codec)
             assert not st.any() and all((a == b).all() for a, b in zip(back, chunks)), NAMES[codec]
@@ -241,3 +243,31 @@ def test_foreign_zstd_frames(gpu_codec, oracle):
     got, st = gpu_codec.decompress_batch(conts, ns, 6)
     assert not st.any(), st
     assert all((g == w).all() for g, w in zip(got, want))
+
+
+@pytest.mark.parametrize("model_name", ["R10.4.1", "R9.4.1"])
+def test_encode_byte_parity_1000_chunks(gpu_codec, enc_oracle, model_name):
+    """BASELINE config 3 at test scale: more than 1000 chunks (full-size and ragged) of each signal model, every codec, the
+    product encoder's bytes against the reference encoder's chunk by chunk; then the decoder returns the samples."""
+    from rawnanoporesignalcompression_b200 import synth
+    seed = 20261018 if model_name == "R10.4.1" else 20261019
+    lengths = synth.read_lengths(1000, seed, median=24_000)
+    sig = synth.generate_reads(lengths, seed, synth.MODELS[model_name]).numpy()
+    off, n, _ = synth.chunk_table(lengths)
+    assert n.size >= 1000 and (n == synth.DEFAULT_CHUNK_SIZE).any()
+    for codec in range(7):
+        comp, coff, st = gpu_codec.compress_flat(sig, off.astype(np.uint64), n, codec)
+        assert not st.any(), NAMES[codec]
+        for i, (o, c) in enumerate(zip(off, n)):
+            want = enc_oracle.encode(codec, sig[o : o + c])
+            got = comp[int(coff[i]) : int(coff[i + 1])].tobytes()
+            assert got == want, (NAMES[codec], i, int(c))
+        back, _, st = gpu_codec.decompress_flat(np.concatenate([comp, np.zeros(64, np.uint8)]), coff, n, codec)
+        assert not st.any() and (back == sig).all(), NAMES[codec]
+    # range coder: a tenth of the chunks (the reference's coder runs at ~30 MB/s)
+    sel = np.arange(0, n.size, 10)
+    chunks = [sig[off[i] : off[i] + n[i]] for i in sel]
+    comp, st = gpu_codec.compress_batch(chunks, 7)
+    assert not st.any()
+    for c, b in zip(chunks, comp):
+        assert b == enc_oracle.encode(7, c)

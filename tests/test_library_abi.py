@@ -51,3 +51,30 @@ def test_no_cpu_fallback_without_device(librnsc_path):
         assert e.status == _lib.ERR_NO_DEVICE
     else:
         raise AssertionError("Codec() succeeded without a CUDA device")
+
+
+def pod5_declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pod5_rnsc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pod5_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_pod5_shim_exports_the_reference_names():
+    """libpod5_rnsc.so exports the un-prefixed names of c_api.h:49-53,678-711 and reports errors the reference's way
+    (pod5_error_t POD5_ERROR_INVALID = 4, text "Invalid: null passed to C API"; c_api.cpp:104-111) -- no compute here."""
+    from rawnanoporesignalcompression_b200 import _lib
+    assert pod5_declared_symbols() == sorted(_lib.POD5_EXPORTS)
+    lib = _lib.load_pod5()
+    for s in pod5_declared_symbols():
+        assert hasattr(lib, s), f"libpod5_rnsc.so does not export {s}"
+    n = 102400
+    src = n // 8 + 2 * n
+    assert lib.pod5_vbz_compressed_signal_max_size(n) == src + (src >> 8)
+    size = C.c_size_t(16)
+    out = C.create_string_buffer(16)
+    assert lib.pod5_vbz_compress_signal(None, 4, out, C.byref(size)) == 4
+    assert lib.pod5_get_error_no() == 4 and lib.pod5_get_error_string() == b"Invalid: null passed to C API"
+    sig = (C.c_int16 * 4)(1, 2, 3, 4)
+    assert lib.pod5_pinanoraw_compress_signal(sig, 4, None, C.byref(size)) == 4
+    assert lib.pod5_get_error_string() == b"Invalid: null output parameter passed to C API"
+    assert lib.pod5_vbz_compressed_signal_max_size(0) >= 0 and lib.pod5_get_error_no() == 0      # every call resets the record (c_api.cpp:1179)
