@@ -62,6 +62,19 @@ void rnsc_destroy(rnsc_ctx* ctx);
 /* Host threads used for the zstd frame stage of the encoders (default: hardware concurrency). */
 void rnsc_set_host_threads(rnsc_ctx* ctx, int n);
 
+/* Entropy stage of rnsc_compress_batch / rnsc_compress_chunk (codecs VBZ .. C5):
+ *   RNSC_ENTROPY_LIBZSTD (default): the device splitter feeds ZSTD_compress(.., 1) of the image's libzstd.so.1 on host
+ *     threads -- the bytes are identical to the reference's (same library, same call: C5.hpp:337-407,
+ *     signal_compression.cpp:65);
+ *   RNSC_ENTROPY_GPU: the frames are written on the device (csrc/zstd_encode.cuh: raw / RLE / Huffman-literal blocks, no
+ *     sequences). Valid Zstandard frames that libzstd, the reference's decoders and this library decode to the same
+ *     samples; the BYTES differ from libzstd's (decode parity, not byte parity) and the ratio is that of an order-0
+ *     coder (no LZ matches: identical on C2-C5 in practice, a little larger on VBZ). No host work, no libzstd needed. */
+#define RNSC_ENTROPY_LIBZSTD 0
+#define RNSC_ENTROPY_GPU 1
+int rnsc_set_entropy_stage(rnsc_ctx* ctx, int mode);
+int rnsc_get_entropy_stage(const rnsc_ctx* ctx);
+
 /* ---- sizes -------------------------------------------------------------------------------------- */
 /* VBZ: compressed_signal_max_size (signal_compression.cpp:30-35) = ZSTD_compressBound(ceil(n/8)+2n).
  * Cx/RC: Compressor::compressed_signal_max_size (pgnano/compressor.h:39-45) = max(2n+26, 1024). */
@@ -101,6 +114,15 @@ int rnsc_decompress_batch(rnsc_ctx* ctx, int codec, const uint8_t* comp, const u
 int rnsc_dev_decode(rnsc_ctx* ctx, int codec, const uint8_t* d_comp, const uint64_t* d_comp_off,
                     const uint32_t* d_n, const uint64_t* d_sample_off, size_t nchunks, uint32_t max_n,
                     int16_t* d_samples, int32_t* d_status, void* stream);
+/* Whole-chunk encode on the device with the GPU entropy stage (RNSC_ENTROPY_GPU above): int16 samples -> finished chunks
+ * (container + zstd frames), nothing leaves HBM. total_samples = sum of n[] (sizes the scratch). Chunk i is written to
+ * d_comp[d_comp_off[i] .. d_comp_off[i+1]) (d_comp_off: nchunks+1 entries, produced by a device prefix scan of the chunk
+ * sizes); d_status[i] is RNSC_ERR_DST_TOO_SMALL when a chunk exceeds the reference's output capacity
+ * (rnsc_max_compressed_size) or comp_cap. Replaces pgnano::compress_signal / pod5::compress_signal for a caller that keeps
+ * signal on the GPU. Asynchronous on `stream`. */
+int rnsc_dev_encode(rnsc_ctx* ctx, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n,
+                    size_t nchunks, size_t total_samples, uint8_t* d_comp, size_t comp_cap, uint64_t* d_comp_off /* nchunks+1 */,
+                    int32_t* d_status, void* stream);
 /* Splitter stage only (stops before zstd): int16 -> streams. Stream k of chunk i is
  * d_streams[d_stream_off[5*i+k] .. d_stream_off[5*i+k+1]); d_stream_off has 5*nchunks+1 entries and is
  * produced by a device prefix scan of the stream sizes. Returns RNSC_ERR_DST_TOO_SMALL (after a stream

@@ -29,7 +29,7 @@ EXPORTS = [
     "rnsc_dev_exclusive_scan_u32", "rnsc_launch_count", "rnsc_decode_class_counts", "rnsc_set_profiling", "rnsc_get_phase_cycles", "rnsc_get_cta_spans",
     "rnsc_pod5_vbz_compressed_signal_max_size", "rnsc_pod5_vbz_compress_signal", "rnsc_pod5_pinanoraw_compress_signal",
     "rnsc_pod5_vbz_decompress_signal", "rnsc_pod5_pinanoraw_decompress_signal", "rnsc_set_pgnano_variant",
-    "rnsc_get_pgnano_variant", "rnsc_thread_context",
+    "rnsc_get_pgnano_variant", "rnsc_thread_context", "rnsc_set_entropy_stage", "rnsc_get_entropy_stage", "rnsc_dev_encode",
 ]
 # libpod5_rnsc.so (include/pod5_rnsc.h): the reference's own C API names for this path
 POD5_EXPORTS = [
@@ -86,6 +86,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "rnsc_set_pgnano_variant": (i32, [i32]),
         "rnsc_get_pgnano_variant": (i32, []),
         "rnsc_thread_context": (vp, []),
+        "rnsc_set_entropy_stage": (i32, [vp, i32]),
+        "rnsc_get_entropy_stage": (i32, [vp]),
+        "rnsc_dev_encode": (i32, [vp, i32, vp, vp, vp, sz, sz, vp, sz, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -80,6 +80,12 @@ class Codec:
     def set_host_threads(self, n: int):
         self.lib.rnsc_set_host_threads(self.ctx, int(n))
 
+    def set_entropy_stage(self, mode):
+        """'libzstd' / 0 (default: host libzstd level 1, bytes identical to the reference) or 'gpu' / 1 (frames written on the
+        device: valid zstd, decode parity, no host work)."""
+        m = {"libzstd": 0, "gpu": 1}.get(mode, mode) if isinstance(mode, str) else int(mode)
+        self._check(self.lib.rnsc_set_entropy_stage(self.ctx, int(m)))
+
     def decode_class_counts(self, stream=None):
         """(fast 4/SM, fast 2/SM, fast 1/SM, general decoder) chunk counts of the last whole-chunk decode."""
         out = (C.c_uint32 * 4)()
@@ -187,6 +193,12 @@ class Codec:
         samples:int16 out, status:int32 out. Asynchronous on `stream` (default: torch's current stream)."""
         self._check(self.lib.rnsc_dev_decode(self.ctx, codec_id(codec), self._dp(comp), self._dp(comp_off), self._dp(n), self._dp(sample_off),
                                              int(status.numel()), int(max_n), self._dp(samples), self._dp(status), self._stream(stream)))
+
+    def dev_encode(self, codec, samples, sample_off, n, total_samples: int, comp, comp_off, status, stream=None):
+        """Whole-chunk encode with the GPU entropy stage. samples:int16, sample_off:i64, n:int32 [nchunks], comp:u8 out,
+        comp_off:i64 out [nchunks+1], status:int32 out. Asynchronous on `stream`."""
+        self._check(self.lib.rnsc_dev_encode(self.ctx, codec_id(codec), self._dp(samples), self._dp(sample_off), self._dp(n), int(n.numel()), int(total_samples),
+                                             self._dp(comp), int(comp.numel()), self._dp(comp_off), self._dp(status), self._stream(stream)))
 
     def dev_svb_encode(self, codec, samples, sample_off, n, streams, stream_off, stream=None):
         self._check(self.lib.rnsc_dev_svb_encode(self.ctx, codec_id(codec), self._dp(samples), self._dp(sample_off), self._dp(n), int(n.numel()),

@@ -147,6 +147,8 @@ struct rnsc_ctx {
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
     DevBuf d_plans, d_lists, d_deftab, d_prof, d_seqpool, d_origin;
+    DevBuf d_zhist, d_zframes, d_zslots, d_zslot_sz, d_zslot_off, d_zout_sz;   // GPU entropy stage of the encoders (zstd_encode.cuh)
+    int entropy_stage = 0;                    // rnsc_compress_batch: 0 = host libzstd level 1 (byte-identical to the reference), 1 = GPU entropy stage
     bool profiling = false;
     uint32_t cost_bit = 1, cost_sym = 12;   // planner's cost model of the Huffman stage (plan.cuh); RNSC_COST_BIT / RNSC_COST_SYM override (tuning)
     Lane lane[2];
@@ -367,7 +369,7 @@ void rnsc_destroy(rnsc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);      // a half-built context (rnsc_create failure) has null handles
-    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin}) b->release();
+    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin, &c->d_zhist, &c->d_zframes, &c->d_zslots, &c->d_zslot_sz, &c->d_zslot_off, &c->d_zout_sz}) b->release();
     c->h_a.release(); c->h_b.release(); c->h_pool_seen.release();
     if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); } if (c->ev_hi) cudaEventDestroy(c->ev_hi);
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
@@ -386,6 +388,8 @@ void rnsc_destroy(rnsc_ctx* c)
 }
 
 void rnsc_set_host_threads(rnsc_ctx* c, int n) { if (c && n > 0) c->host_threads = n; }
+int rnsc_set_entropy_stage(rnsc_ctx* c, int mode) { if (!c || mode < 0 || mode > 1) return fail(RNSC_ERR_BAD_ARG, "rnsc_set_entropy_stage: mode must be RNSC_ENTROPY_LIBZSTD or RNSC_ENTROPY_GPU"); c->entropy_stage = mode; return RNSC_OK; }
+int rnsc_get_entropy_stage(const rnsc_ctx* c) { return c ? c->entropy_stage : -1; }
 uint64_t rnsc_launch_count(const rnsc_ctx* c) { return c ? c->launches : 0; }
 
 size_t rnsc_max_compressed_size(int codec, size_t n)
@@ -462,12 +466,11 @@ int rnsc_dev_exclusive_scan_u32(rnsc_ctx* c, const uint32_t* d_in, size_t count,
     return RNSC_OK;
 }
 
-int rnsc_dev_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks,
-                        uint8_t* d_streams, size_t streams_cap, uint64_t* d_stream_off, void* stream)
+// sizes -> device prefix scan -> scatter. check_cap: fetch the total (one stream synchronisation) and compare it with the
+// caller's capacity; the internal callers size the buffer by the bound and skip it.
+static int launch_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks,
+                             uint8_t* d_streams, size_t streams_cap, uint64_t* d_stream_off, cudaStream_t st, bool check_cap)
 {
-    if (!c || !svb_codec_ok(codec) || !d_stream_off || (nchunks && (!d_samples || !d_sample_off || !d_n || !d_streams))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_svb_encode: bad argument");
-    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     if (c->d_sizes.reserve(5 * nchunks * sizeof(uint32_t) + 16)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(sizes) failed");
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)1 << 20, nchunks));   // one CTA per chunk: the hardware scheduler balances the sizes
     if (nchunks) {
@@ -478,16 +481,62 @@ int rnsc_dev_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const 
     }
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_sizes.p, (unsigned long long)(5 * nchunks), (unsigned long long*)d_stream_off);
     c->launches += 1;
-    uint64_t total = 0;
-    CUDA_OK(cudaMemcpyAsync(&total, d_stream_off + 5 * nchunks, sizeof total, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    if (total > streams_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "stream buffer too small: need %llu bytes, have %zu", (unsigned long long)total, streams_cap);
+    if (check_cap) {
+        uint64_t total = 0;
+        CUDA_OK(cudaMemcpyAsync(&total, d_stream_off + 5 * nchunks, sizeof total, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (total > streams_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "stream buffer too small: need %llu bytes, have %zu", (unsigned long long)total, streams_cap);
+    }
     if (nchunks) {
 #define RNSC_PACK2(C) case C: RNSC_LAUNCH(k_svb_pack2<C>, grid, P2_NT, (size_t)P2_STAGE_BYTES, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, d_streams, (const uint64_t*)d_stream_off); break
         switch (codec) { RNSC_PACK2(RNSC_VBZ); RNSC_PACK2(RNSC_VBZ0); RNSC_PACK2(RNSC_C1); RNSC_PACK2(RNSC_C2); RNSC_PACK2(RNSC_C3); RNSC_PACK2(RNSC_C4); default: RNSC_PACK2(RNSC_C5); }
 #undef RNSC_PACK2
         c->launches += 1;
     }
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+int rnsc_dev_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks,
+                        uint8_t* d_streams, size_t streams_cap, uint64_t* d_stream_off, void* stream)
+{
+    if (!c || !svb_codec_ok(codec) || !d_stream_off || (nchunks && (!d_samples || !d_sample_off || !d_n || !d_streams))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_svb_encode: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    return launch_svb_encode(c, codec, d_samples, d_sample_off, d_n, nchunks, d_streams, streams_cap, d_stream_off, stream ? (cudaStream_t)stream : c->stream, true);
+}
+
+// Whole-chunk encode on the device: splitter, then the GPU entropy stage (zstd_encode.cuh): valid zstd frames, decodable by
+// libzstd / the reference / this library, NOT byte-identical to libzstd's level-1 output.
+int rnsc_dev_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks, size_t total_samples,
+                    uint8_t* d_comp, size_t comp_cap, uint64_t* d_comp_off, int32_t* d_status, void* stream)
+{
+    if (!c || !svb_codec_ok(codec) || !d_comp_off || (nchunks && (!d_samples || !d_sample_off || !d_n || !d_comp || !d_status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_encode: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (!nchunks) { CUDA_OK(cudaMemsetAsync(d_comp_off, 0, 8, st)); return RNSC_OK; }
+    const int nf = codec_frames(codec);
+    const size_t streams_cap = 2 * total_samples + total_samples / 4 + 16 * nchunks + 64;                     // sum of stream_bound(codec, n)
+    const size_t slots_cap = 2 * total_samples + total_samples / 4 + 1104 * nchunks + 64;                     // sum of the reference's output capacities, 16-byte rounded
+    if (c->d_streams.reserve(streams_cap + 64) || c->d_stream_off.reserve((5 * nchunks + 1) * 8) || c->d_zhist.reserve(nchunks * nf * 256 * sizeof(uint32_t)) ||
+        c->d_zframes.reserve(nchunks * nf * sizeof(ZencFrame)) || c->d_zslots.reserve(slots_cap + 64) || c->d_zslot_sz.reserve(nchunks * 4 + 16) ||
+        c->d_zslot_off.reserve((nchunks + 1) * 8) || c->d_zout_sz.reserve(nchunks * 4 + 16))
+        return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(encoder scratch) failed");
+    int r = launch_svb_encode(c, codec, d_samples, d_sample_off, d_n, nchunks, (uint8_t*)c->d_streams.p, streams_cap, (uint64_t*)c->d_stream_off.p, st, false);
+    if (r) return r;
+    RNSC_LAUNCH(k_zenc_slot_sizes, (int)((nchunks + 255) / 256), 256, 0, st, d_n, (uint32_t)nchunks, codec, (uint32_t*)c->d_zslot_sz.p);
+    RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zslot_sz.p, (unsigned long long)nchunks, (unsigned long long*)c->d_zslot_off.p);
+    ZencParams zp;
+    zp.streams = (const uint8_t*)c->d_streams.p; zp.stream_off = (const uint64_t*)c->d_stream_off.p; zp.n = d_n; zp.nchunks = (uint32_t)nchunks; zp.codec = codec;
+    zp.hist = (uint32_t*)c->d_zhist.p; zp.frames = (ZencFrame*)c->d_zframes.p; zp.slots = (uint8_t*)c->d_zslots.p; zp.slot_off = (const uint64_t*)c->d_zslot_off.p;
+    zp.out_size = (uint32_t*)c->d_zout_sz.p; zp.status = d_status;
+    const int wide = (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 8);
+    RNSC_LAUNCH(k_zenc_histogram, wide, ZE_NT, 0, st, zp);
+    RNSC_LAUNCH(k_zenc_build, (int)((nchunks * nf + 127) / 128), 128, 0, st, zp);
+    RNSC_LAUNCH(k_zenc_emit, (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 6), ZE_NT, 0, st, zp);
+    RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zout_sz.p, (unsigned long long)nchunks, (unsigned long long*)d_comp_off);
+    RNSC_LAUNCH(k_zenc_gather, wide, ZE_NT, 0, st, (const uint8_t*)c->d_zslots.p, (const uint64_t*)c->d_zslot_off.p, (const uint64_t*)d_comp_off, (uint32_t)nchunks, d_comp,
+                (unsigned long long)comp_cap, d_status);
+    c->launches += 7;
     CUDA_OK(cudaGetLastError());
     return RNSC_OK;
 }
@@ -614,7 +663,7 @@ int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const ui
     if (!c || !codec_ok(codec) || !comp_off || (nchunks && (!samples || !sample_off || !n || !comp || !status))) return fail(RNSC_ERR_BAD_ARG, "rnsc_compress_batch: bad argument");
     comp_off[0] = 0;
     if (!nchunks) return RNSC_OK;
-    if (codec != RNSC_RC && !zstd().ok) return fail(RNSC_ERR_NO_ZSTD, "libzstd.so.1 not loadable: %s", dlerror());
+    if (codec != RNSC_RC && c->entropy_stage == 0 && !zstd().ok) return fail(RNSC_ERR_NO_ZSTD, "libzstd.so.1 not loadable: %s", dlerror());
     std::lock_guard<std::mutex> lk(c->mu);
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     cudaStream_t st = c->stream;
@@ -655,6 +704,40 @@ int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const ui
         }
         comp_off[nchunks] = op;
         CUDA_OK(cudaStreamSynchronize(st));
+        return RNSC_OK;
+    }
+
+    if (c->entropy_stage == 1) {
+        // ---- GPU entropy stage: samples in, finished chunks out; nothing but the two copies touches the host ----
+        size_t first = 0; uint64_t op = 0;
+        while (first < nchunks) {
+            size_t last = first; uint64_t sb = 0;
+            while (last < nchunks && (last == first || sb + n[last] <= slice_samples())) { sb += n[last]; ++last; }
+            const size_t m = last - first;
+            std::vector<uint64_t> soff(m + 1), coff(m + 1);
+            bool dense = true; uint64_t a = 0;
+            for (size_t i = 0; i < m; ++i) { soff[i] = a; if (sample_off[first + i] - sample_off[first] != a) dense = false; a += n[first + i]; }
+            soff[m] = a;
+            const size_t ccap = 2 * sb + sb / 4 + 1104 * m + 64;
+            if (c->d_samples.reserve(sb * 2 + 64) || c->d_off_b.reserve((m + 1) * 8) || c->d_n.reserve(m * 4 + 16) || c->d_comp.reserve(ccap + 64) || c->d_off_a.reserve((m + 1) * 8) || c->d_status.reserve(m * 4 + 16))
+                return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
+            if (dense) CUDA_OK(cudaMemcpyAsync(c->d_samples.p, samples + sample_off[first], sb * 2, cudaMemcpyHostToDevice, st));
+            else for (size_t i = 0; i < m; ++i) if (n[first + i]) CUDA_OK(cudaMemcpyAsync((int16_t*)c->d_samples.p + soff[i], samples + sample_off[first + i], (size_t)n[first + i] * 2, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(c->d_off_b.p, soff.data(), (m + 1) * 8, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(c->d_n.p, n + first, m * 4, cudaMemcpyHostToDevice, st));
+            int r = rnsc_dev_encode(c, codec, (const int16_t*)c->d_samples.p, (const uint64_t*)c->d_off_b.p, (const uint32_t*)c->d_n.p, m, sb, (uint8_t*)c->d_comp.p, ccap,
+                                    (uint64_t*)c->d_off_a.p, (int32_t*)c->d_status.p, st);
+            if (r) { cudaStreamSynchronize(st); return r; }
+            CUDA_OK(cudaMemcpyAsync(coff.data(), c->d_off_a.p, (m + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaMemcpyAsync(status + first, c->d_status.p, m * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaStreamSynchronize(st));
+            if (op + coff[m] > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need %llu bytes, have %zu", (unsigned long long)(op + coff[m]), comp_cap);
+            CUDA_OK(cudaMemcpyAsync(comp + op, c->d_comp.p, coff[m], cudaMemcpyDeviceToHost, st));
+            for (size_t i = 0; i < m; ++i) comp_off[first + i] = op + coff[i];
+            CUDA_OK(cudaStreamSynchronize(st));
+            op += coff[m]; first = last;
+        }
+        comp_off[nchunks] = op;
         return RNSC_OK;
     }
 

@@ -6,6 +6,7 @@
 #include "rc_codec.cuh"
 #include "plan.cuh"
 #include "fast_decode.cuh"
+#include "zstd_encode.cuh"
 
 namespace rnsc {
 

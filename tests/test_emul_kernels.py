@@ -138,3 +138,35 @@ def test_foreign_zstd_frames(ecodec, oracle):
         for level, ck in zf.SETTINGS[::2]:
             assert (ecodec.decompress_signal(zf.vbz_frame(oracle, x, level, ck), x.size, 0) == x).all(), (name, level, ck)
         assert (ecodec.decompress_signal(zf.c5_container(oracle, x, 19, True), x.size, 6) == x).all(), name
+
+
+def test_gpu_entropy_stage_frames_decode_everywhere(ecodec, oracle):
+    """RNSC_ENTROPY_GPU (csrc/zstd_encode.cuh): the frames written by the device encoder are valid Zstandard -- libzstd, the
+    oracle's RFC 8878 decoder, the reference's own decompress_signal_* (when built) and this library's decoder return the
+    input samples; chunks that exceed the reference's output capacity report status 3 like the host path."""
+    from oracle_binding import RefOracle
+    from rawnanoporesignalcompression_b200 import synth
+    ref = RefOracle() if RefOracle.available() else None
+    lengths = np.array([3000, 30000, 102400 + 5000, 700, 64, 10, 0, 1], dtype=np.int64)
+    sig = synth.generate_reads(lengths, 99, synth.R10_4_1).numpy()
+    off, n, _ = synth.chunk_table(lengths)
+    chunks = [sig[o : o + c] for o, c in zip(off, n)]
+    chunks += [recipes.walk(20000, 77, 12.0), recipes.extremes(5000, 3), np.zeros(9000, np.int16), np.arange(10000, dtype=np.int16), recipes.uniform16(4000, 5)]
+    ecodec.set_entropy_stage("gpu")
+    try:
+        for codec in range(7):
+            comp, st = ecodec.compress_batch(chunks, codec)
+            for c, b, s in zip(chunks, comp, st):
+                host_st, _ = oracle.encode_status(codec, c)
+                if host_st == 3 and codec in (5, 6):      # C4/C5 "Not enough space in destination buffer" (C5.hpp:420-427)
+                    assert s == 3
+                if s:
+                    assert s == 3
+                    continue
+                for r, y in (oracle.decode_status(codec, b, len(c)), oracle.decode_status(codec, b, len(c), own_zstd=True)) + ((ref.decode_status(codec, b, len(c)),) if ref else ()):
+                    assert r == 0 and (y == c).all(), (codec, len(c))
+            ok = [i for i, s in enumerate(st) if s == 0]
+            dec, st2 = ecodec.decompress_batch([comp[i] for i in ok], [len(chunks[i]) for i in ok], codec)
+            assert not st2.any() and all((a == chunks[i]).all() for a, i in zip(dec, ok))
+    finally:
+        ecodec.set_entropy_stage("libzstd")

@@ -271,3 +271,36 @@ def test_encode_byte_parity_1000_chunks(gpu_codec, enc_oracle, model_name):
     assert not st.any()
     for c, b in zip(chunks, comp):
         assert b == enc_oracle.encode(7, c)
+
+
+@pytest.mark.parametrize("codec", [6, 0, 1, 3], ids=["C5", "VBZ", "VBZ0", "C2"])
+def test_gpu_entropy_stage_device_encode(gpu_codec, enc_oracle, oracle, codec):
+    """rnsc_dev_encode (GPU entropy stage, csrc/zstd_encode.cuh): > 1000 chunks of synthetic signal encoded on the device;
+    every chunk decodes back to its samples through the reference's decoder (oracle/_ref when present, else libzstd via the
+    port) and, as one batch, through this library's fast decoder; sizes stay within 3 % of the host-libzstd encoder."""
+    import torch
+    from rawnanoporesignalcompression_b200 import synth
+    dev = torch.device("cuda:0")
+    lengths = synth.read_lengths(1000, 20261018, median=24_000)
+    sig = synth.generate_reads(lengths, 20261018, synth.R10_4_1, device=dev)
+    off, n, _ = synth.chunk_table(lengths)
+    total = int(lengths.sum())
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev); d_n = torch.from_numpy(n.astype(np.int32)).to(dev)
+    d_comp = torch.empty(2 * total + total // 4 + 1104 * n.size + 64, dtype=torch.uint8, device=dev)
+    d_coff = torch.empty(n.size + 1, dtype=torch.int64, device=dev); d_st = torch.empty(n.size, dtype=torch.int32, device=dev)
+    gpu_codec.dev_encode(codec, sig, d_off, d_n, total, d_comp, d_coff, d_st)
+    torch.cuda.synchronize()
+    assert not d_st.any().item()
+    coff = d_coff.cpu().numpy(); comp = d_comp[: int(coff[-1]) + 64].cpu().numpy(); host = sig.cpu().numpy()
+    for i in range(0, n.size, 3):                                  # every third chunk through the CPU reference decoder
+        b = comp[int(coff[i]) : int(coff[i + 1])].tobytes()
+        r, y = enc_oracle.decode_status(codec, b, int(n[i]))
+        assert r == 0 and (y == host[off[i] : off[i] + n[i]]).all(), i
+    d_out = torch.empty_like(sig); d_st2 = torch.empty_like(d_st)
+    gpu_codec.dev_decode(codec, d_comp, d_coff, d_n, d_off, int(n.max()), d_out, d_st2)
+    torch.cuda.synchronize()
+    assert not d_st2.any().item() and torch.equal(d_out, sig)
+    _, hcoff, hst = gpu_codec.compress_flat(host, off.astype(np.uint64), n, codec)          # host libzstd level 1 (the reference's bytes)
+    assert not hst.any()
+    ratio = float(coff[-1]) / float(hcoff[-1])
+    assert ratio < (1.03 if codec != 0 and codec != 1 else 1.10), ratio
