@@ -531,7 +531,7 @@ int rnsc_dev_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint
     zp.out_size = (uint32_t*)c->d_zout_sz.p; zp.status = d_status;
     const int wide = (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 8);
     RNSC_LAUNCH(k_zenc_histogram, wide, ZE_NT, 0, st, zp);
-    RNSC_LAUNCH(k_zenc_build, (int)((nchunks * nf + 127) / 128), 128, 0, st, zp);
+    RNSC_LAUNCH(k_zenc_build, (int)std::min<size_t>((nchunks * nf + ZE_BUILD_WARPS - 1) / ZE_BUILD_WARPS, (size_t)c->sm_count * 16), 32 * ZE_BUILD_WARPS, 0, st, zp);
     RNSC_LAUNCH(k_zenc_emit, (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 6), ZE_NT, 0, st, zp);
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zout_sz.p, (unsigned long long)nchunks, (unsigned long long*)d_comp_off);
     RNSC_LAUNCH(k_zenc_gather, wide, ZE_NT, 0, st, (const uint8_t*)c->d_zslots.p, (const uint64_t*)c->d_zslot_off.p, (const uint64_t*)d_comp_off, (uint32_t)nchunks, d_comp,

@@ -16,6 +16,12 @@
 
 namespace rnsc {
 
+// (Tried: the Huffman stage as a __noinline__ function of its own, to take its registers out of the chunk loop's
+// allocation -- no spills, but 3 % slower overall on the B200: 483.7 vs 500.6 GB/s on the 20k-read C5 set.)
+#ifndef RNSC_NOINLINE
+#define RNSC_NOINLINE
+#endif
+
 constexpr uint32_t FAST_WARM_BITS = 256;   // speculative warm-up before a sub-sequence
 constexpr uint32_t FAST_NONE = 0xFFFFFFFFu;
 
@@ -294,6 +300,27 @@ __device__ __forceinline__ void huf_walk(const uint8_t* region, uint32_t abit, c
     }
 }
 
+// `nbytes` symbols kept in a thread's slot (32-bit words, 4 symbols each) go to their final place o (any alignment): byte
+// stores up to the next word boundary, then whole words shifted into place, byte stores for what is left. Reads one word
+// past the last one that holds a kept symbol.
+__device__ __forceinline__ void put_kept(uint8_t* o, const uint32_t* slot, uint32_t nbytes)
+{
+    const uint32_t h = min(nbytes, (4u - ((uint32_t)(uintptr_t)o & 3u)) & 3u);
+    const uint32_t w0 = slot[0];
+#pragma unroll
+    for (uint32_t q = 0; q < 3; ++q) if (q < h) o[q] = (uint8_t)(w0 >> (8 * q));
+    uint32_t* ow = (uint32_t*)(o + h);
+    const uint32_t nmid = (nbytes - h) >> 2, sh = 8 * h;
+    uint32_t lo = w0;
+    for (uint32_t j = 0; j < nmid; ++j) { const uint32_t hi = slot[j + 1]; ow[j] = __funnelshift_r(lo, hi, sh); lo = hi; }
+    const uint32_t done = h + 4 * nmid;
+    if (done < nbytes) {
+        const uint32_t t = __funnelshift_r(lo, slot[nmid + 1], sh);
+#pragma unroll
+        for (uint32_t q = 0; q < 3; ++q) if (done + q < nbytes) o[done + q] = (uint8_t)(t >> (8 * q));
+    }
+}
+
 // Plan prefetch: the words the next chunk's start needs (plan head, Huffman table recipes, offset of its compressed
 // bytes) are fetched from global memory during this chunk's Huffman stage and parked in the sub-sequence arrays, so
 // that a chunk does not begin with a chain of dependent global loads.
@@ -314,7 +341,7 @@ __device__ __forceinline__ uint32_t stash_fetch(const FastParams& P, uint32_t c,
 // between the passes: a frame of short codes (many symbols per bit, long second pass) does not hold up the others, and
 // the CTA meets again only at the end. Returns 0 on success (same value in all threads).
 template <int NTH>
-__device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, PhaseClock& pc)
+__device__ RNSC_NOINLINE int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastParams& P, PhaseClock& pc)
 {
     constexpr int NW = NTH / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -334,11 +361,33 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
     const uint32_t s0 = k * sub, lim = min(s0 + sub, T);
     const bool active = member && s0 < T;                                  // the padding threads of a group only keep its barriers company
     uint32_t my_start = 0, my_end = 0, my_cnt = 0;
+    // Symbol slot of this thread: the first symbols of the sub-sequence are decoded for good in the first pass and kept
+    // here (frames without LZ sequences: their literals are one run); the second pass copies them instead of decoding them
+    // again. The rest of the sub-sequence is only counted (skip table).
+    uint32_t* const slot = (uint32_t*)(region + hd.slot_off) + (uint32_t)tid * hd.slot_w;
+    const uint32_t keep_max = sp.sop >= 5 ? 4u * hd.slot_w : 0u;
+    uint32_t kept = 0, p_keep = 0;
     if (active) {
         uint32_t p = s0 > FAST_WARM_BITS ? s0 - FAST_WARM_BITS : 0, dummy = 0;
         huf_walk(region, abit, tab, p, s0, dummy);
         my_start = p;
+        if (keep_max) {
+            BitPos bp(region, abit - p);
+            uint32_t hi, lo, e;
+            while (kept < keep_max && p + 4 * HUF_LOG_MAX <= lim) {
+                bp.window(hi, lo);
+                uint32_t word = 0, adv = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    RNSC_HUF_STEP(hi, lo, tab, e); adv += e;
+                    word = __byte_perm(word, e, q == 0 ? 0x3215u : (q == 1 ? 0x3250u : (q == 2 ? 0x3510u : 0x5210u)));   // byte q <- symbol
+                }
+                slot[kept >> 2] = word; kept += 4; p += adv & 0xFFu; bp.consume(adv & 0xFFu);
+            }
+        }
+        p_keep = p;
         huf_walk(region, abit, tab, p, lim, my_cnt);
+        my_cnt += kept;
         my_end = p;
     }
     pc.mark(PH_HUF1);
@@ -355,7 +404,7 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
         if (!bar_named_or(bar_id, bar_n, bad)) break;
         if (round >= NTH) { fail = true; break; }    // cannot happen for a consistent stream: every round fixes at least one more sub-sequence
         if (bad) {
-            uint32_t p = want; my_start = p; my_cnt = 0;
+            uint32_t p = want; my_start = p; my_cnt = 0; kept = 0; p_keep = p;      // what the slot holds was decoded from a wrong start
             if (p < lim) huf_walk(region, abit, tab, p, lim, my_cnt);
             my_end = p;
         }
@@ -393,6 +442,11 @@ __device__ inline int fast_huffman(FastWs<NTH>* ws, uint8_t* region, const FastP
         }
         if (li + rem <= run_end) {      // all my literals belong to one run (always, without sequences)
             uint8_t* o = region + sp.out + li + shift;
+            if (kept) {                 // symbols kept by the first pass: copy, then go on behind them
+                const uint32_t k = min(kept, rem);
+                put_kept(o, slot, k);
+                o += k; rem -= k; p = p_keep;
+            }
             BitPos bp(region, abit - p);
             // up to three symbols bring the output to a word boundary: one window, predicated steps
             const uint32_t head = min(rem, (4u - ((uint32_t)(uintptr_t)o & 3u)) & 3u);

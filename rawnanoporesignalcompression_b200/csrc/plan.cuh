@@ -17,9 +17,13 @@ namespace rnsc {
 
 constexpr int PLAN_MAX_HUF = 3;       // Huffman-coded literal sections per chunk described in the plan
 constexpr int PLAN_MAX_STREAMS = 4 * PLAN_MAX_HUF;
-constexpr int PLAN_THREADS = 32;      // planner CTA size (one chunk per thread)
+#ifndef RNSC_PLAN_THREADS
+#define RNSC_PLAN_THREADS 32
+#endif
+constexpr int PLAN_THREADS = RNSC_PLAN_THREADS;      // planner CTA size (one chunk per thread)
 constexpr uint32_t REGION_HEAD = 16;  // readable bytes in front of the staged chunk (bit-window over-read)
 constexpr uint32_t PLAN_SUB_MIN = 192;   // minimum Huffman sub-sequence length in bits
+constexpr uint32_t PLAN_SLOT_MAX = 63;   // symbol slot words per Huffman thread at most (252 symbols: more than a sub-sequence holds)
 constexpr uint32_t FAST_ORDERED_MAX = 64;   // chunks with at most this many sequences run them in order, one warp per frame
 
 enum : uint32_t { FK_RAW = 0, FK_RLE = 1, FK_COMP = 2 };
@@ -71,6 +75,7 @@ struct PlanHead {                // what the fast kernel copies to shared memory
     uint32_t early;                // bit k: the sequences of sop[k] (raw / RLE literals) are executed by the CTA's last warp while the others decode Huffman streams
     uint32_t zone_off, zone_len;   // region bytes that are dead after the Huffman stage (the largest bitstream area): match resolver scratch
     uint32_t grp_first[PLAN_MAX_HUF + 1];   // thread groups of the Huffman stage, one per Huffman-coded frame: first thread (a multiple of 32)
+    uint32_t slot_off, slot_w;              // symbol slots of the Huffman stage: region offset, 32-bit words per thread (odd, 0 = none): what is left of the class's region
     uint32_t st_first[PLAN_MAX_STREAMS + 1];
     StreamPlan st[PLAN_MAX_STREAMS];
     FillOp fill[5];
@@ -480,6 +485,16 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     hd->grp_first[PLAN_MAX_HUF] = first;
     for (uint32_t s = nst; s <= PLAN_MAX_STREAMS; ++s) hd->st_first[s] = first;
     const uint32_t sub = sub_max;
+    // Symbol slots: the part of the class's region that this chunk does not need is dealt out to the Huffman threads; the
+    // first pass keeps the first symbols of every sub-sequence there (decoded once, copied by the second pass) -- an odd
+    // number of words per thread, so that the lanes of a warp write to 32 different banks.
+    {
+        const uint32_t so = (region + 3u) & ~3u;
+        uint32_t w = (first && P.region[cls] > so + 8) ? (P.region[cls] - so - 8) / 4 / first : 0;
+        if (w > PLAN_SLOT_MAX) w = PLAN_SLOT_MAX;
+        if (!(w & 1u) && w) --w;
+        hd->slot_off = so; hd->slot_w = w >= 3 ? w : 0;
+    }
     hd->need = region; hd->phase = phase; hd->stage_bytes = stage;
     hd->nhuf = nhuf; hd->nst = nst; hd->sub = sub; hd->nfill = nfill; hd->nsop = nsop; hd->nseq = nseq_tot; hd->view_status = vst; hd->early = early; hd->zone_off = zone_off; hd->zone_len = zone_len;
     plan_emit(P, c, cls);
@@ -487,12 +502,20 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
 
 __global__ void __launch_bounds__(PLAN_THREADS) k_plan_chunks(PlanParams P)
 {
+#ifdef RNSC_PLAN_LOCAL
+    PlanScratch local_scratch;                       // thread-private (local memory, L1): occupancy is no longer bound by shared memory
+#else
     __shared__ PlanScratch scratch[PLAN_THREADS];
+#endif
     __shared__ uint32_t deftab[160];
     for (int i = threadIdx.x; i < 160; i += PLAN_THREADS) deftab[i] = P.deftab[i];
     __syncthreads();
     const uint32_t c = blockIdx.x * PLAN_THREADS + threadIdx.x;
+#ifdef RNSC_PLAN_LOCAL
+    if (c < P.nchunks) plan_chunk(P, c, &local_scratch, deftab);
+#else
     if (c < P.nchunks) plan_chunk(P, c, &scratch[threadIdx.x], deftab);
+#endif
 }
 
 }  // namespace rnsc

@@ -16,12 +16,14 @@
 //
 // Three kernels after the splitter:
 //   k_zenc_histogram  one CTA per chunk: byte histogram of every frame (shared-memory atomics, one copy per warp);
-//   k_zenc_build      ONE THREAD per frame (all frames of the batch at once, like the planner): everything serial --
-//                     sort by count, Huffman tree, length limit, canonical codes in zstd's table order, tree description
-//                     with FSE-compressed weights -- so that 10^5 serial chains overlap instead of stalling a CTA each;
+//   k_zenc_build      one WARP per frame, all frames of the batch at once: rank sort of the symbols by count and the canonical
+//                     codes (zstd's table order) across the lanes, the inherently serial steps (two-queue Huffman tree,
+//                     length limit, FSE-compressed weights of the tree description) on lane 0 out of shared memory -- 10^5
+//                     short serial chains overlap each other instead of stalling a CTA each;
 //   k_zenc_emit       one CTA per chunk: per frame, bit lengths per thread, a suffix scan (zstd's Huffman streams are
-//                     written last symbol first), bit packing through shared memory, headers, container (A.1-A.8: u64
-//                     size prefixes), into the chunk's slot; k_zenc_gather then compacts the slots.
+//                     written last symbol first), bits packed in registers and written straight into the chunk's slot
+//                     (plain stores for a thread's whole words, atomic OR for the ragged ones), headers, container (A.1-A.8:
+//                     u64 size prefixes); k_zenc_gather then compacts the slots.
 #pragma once
 #include "block_prims.cuh"
 #include "svb_codec.cuh"
@@ -32,7 +34,6 @@ constexpr int ZE_NT = 256;                       // threads per CTA of the histo
 constexpr uint32_t ZE_BLOCK_MAX = 128u << 10;    // Block_Maximum_Size
 constexpr uint32_t ZE_HUF_MIN = 64;              // shorter frames are not worth a tree description: raw
 constexpr uint32_t ZE_LOG_MAX = 11;              // HUF_TABLELOG_DEFAULT of the literals' Huffman codes
-constexpr uint32_t ZE_SEG_SMEM = 32u << 10;      // shared-memory bit buffer of one Huffman stream: a quarter of the largest block at < 8 bits per symbol
 enum : uint32_t { ZM_RAW = 0, ZM_RLE = 1, ZM_HUF = 2 };
 
 // What k_zenc_build leaves per frame for k_zenc_emit.
@@ -111,34 +112,41 @@ __global__ void __launch_bounds__(ZE_NT) k_zenc_histogram(ZencParams P)
 // -------------------------------------------------------------------------------------------------------------
 // 2. serial part, one thread per frame
 // -------------------------------------------------------------------------------------------------------------
-// LSB-first bit writer into a small byte buffer (FSE table description and FSE bitstream of the weights)
+// LSB-first bit writer into a small word buffer in shared memory (FSE table description + FSE bitstream of the weights)
 struct ZeBits {
-    uint8_t* p; uint32_t cap; uint32_t pos; unsigned long long acc; uint32_t fill; bool ovf;
-    __device__ void init(uint8_t* buf, uint32_t capacity) { p = buf; cap = capacity; pos = 0; acc = 0; fill = 0; ovf = false; }
-    __device__ void add(uint32_t v, uint32_t nb) { acc |= (unsigned long long)(v & ((1u << nb) - 1u)) << fill; fill += nb; while (fill >= 8) { if (pos < cap) p[pos] = (uint8_t)acc; else ovf = true; ++pos; acc >>= 8; fill -= 8; } }
-    __device__ uint32_t close_bytes() { if (fill) { if (pos < cap) p[pos] = (uint8_t)acc; else ovf = true; ++pos; acc = 0; fill = 0; } return pos; }
+    uint32_t* p; uint32_t cap; uint32_t pos; unsigned long long acc; uint32_t fill;
+    __device__ __forceinline__ void init(uint32_t* buf, uint32_t cap_words) { p = buf; cap = cap_words; pos = 0; acc = 0; fill = 0; }
+    __device__ __forceinline__ void add(uint32_t v, uint32_t nb)
+    {
+        acc |= (unsigned long long)(v & ((1u << nb) - 1u)) << fill; fill += nb;
+        if (fill >= 32) { if (pos < cap) p[pos] = (uint32_t)acc; ++pos; acc >>= 32; fill -= 32; }
+    }
+    __device__ __forceinline__ void pad_to_byte() { fill = (fill + 7u) & ~7u; if (fill >= 32) { if (pos < cap) p[pos] = (uint32_t)acc; ++pos; acc >>= 32; fill -= 32; } }
+    __device__ __forceinline__ uint32_t bytes() const { return 4 * pos + ((fill + 7) >> 3); }
+    __device__ __forceinline__ void flush() { if (fill && pos < cap) p[pos] = (uint32_t)acc; }
 };
 
 // FSE-compressed Huffman weights (RFC 8878 4.2.1.1 / HUF_compressWeights): returns the bytes written to out (<= cap) or 0
 // when this representation is not usable (fewer than two weights, one distinct value, no gain possible).
-__device__ inline uint32_t ze_fse_weights(const uint8_t* w, uint32_t n, uint8_t* out, uint32_t cap)
+struct ZeFseWs { uint8_t tsym[64]; uint16_t state_tab[64]; uint32_t cumul[14]; int dnb[13], dfs[13], norm[13]; uint32_t cnt[13]; uint32_t out[36]; };   // scratch of ze_fse_weights (shared memory: dynamically indexed local arrays cost an L2 round trip per access)
+
+// One thread. F.cnt[0..maxw] = how often each weight value occurs among w[0..n) (counted by the warp). The description is
+// left in F.out (bytes, little endian words); returns its length (<= 127) or 0.
+__device__ inline uint32_t ze_fse_weights(const uint8_t* w, uint32_t n, uint32_t maxw, ZeFseWs& F)
 {
     if (n < 2) return 0;
-    uint32_t cnt[13];
-    for (int i = 0; i < 13; ++i) cnt[i] = 0;
-    uint32_t maxw = 0;
-    for (uint32_t i = 0; i < n; ++i) { cnt[w[i]]++; if (w[i] > maxw) maxw = w[i]; }
+    const uint32_t* cnt = F.cnt;
     uint32_t present = 0, big = 0;
     for (uint32_t s = 0; s <= maxw; ++s) { if (cnt[s]) ++present; if (cnt[s] > cnt[big]) big = s; }
     if (present < 2) return 0;
     const uint32_t tl = n >= 32 ? 6u : 5u, size = 1u << tl;           // any log in 5..6 is valid; the alphabet has <= 13 symbols
     // normalised counts: proportional, every present symbol at least 1, the remainder to the most frequent one
-    int norm[13]; int sum = 0;
+    int* norm = F.norm; int sum = 0;
     for (uint32_t s = 0; s <= maxw; ++s) { norm[s] = cnt[s] ? (int)max(1u, (cnt[s] * size) / n) : 0; sum += norm[s]; }
     norm[big] += (int)size - sum;
     if (norm[big] < 1) return 0;
     // ---- table description (FSE_writeNCount; mirror of fse_read_ncount in zstd_decode.cuh) ----
-    ZeBits b; b.init(out, cap);
+    ZeBits b; b.init(F.out, 36);
     b.add(tl - 5, 4);
     {
         int remaining = (int)size + 1, threshold = (int)size, nbBits = (int)tl + 1; bool prev0 = false;
@@ -160,10 +168,10 @@ __device__ inline uint32_t ze_fse_weights(const uint8_t* w, uint32_t n, uint8_t*
             while (remaining < threshold) { --nbBits; threshold >>= 1; }
         }
     }
-    const uint32_t hdr = b.close_bytes();
+    b.pad_to_byte();                                                  // the bitstream of the weights starts at the next byte
     // ---- compression table (FSE_buildCTable) ----
-    uint8_t tsym[64]; uint16_t state_tab[64]; uint32_t cumul[14];
-    int dnb[13], dfs[13];
+    uint8_t* tsym = F.tsym; uint16_t* state_tab = F.state_tab; uint32_t* cumul = F.cumul;
+    int* dnb = F.dnb; int* dfs = F.dfs;
     {
         const uint32_t step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
         uint32_t pos = 0;
@@ -181,113 +189,207 @@ __device__ inline uint32_t ze_fse_weights(const uint8_t* w, uint32_t n, uint8_t*
         }
     }
     // ---- weights, last to first, two interleaved states (FSE_compress_usingCTable) ----
-    ZeBits e; e.init(out + hdr, cap > hdr ? cap - hdr : 0);
     auto init_state = [&](uint32_t sym) -> uint32_t {                // FSE_initCState2: the symbol's state that costs the most bits next time
         const uint32_t nb = (uint32_t)(dnb[sym] + (1 << 15)) >> 16;
         const uint32_t value = (nb << 16) - (uint32_t)dnb[sym];
         return state_tab[(int)(value >> nb) + dfs[sym]];
     };
-    auto encode = [&](uint32_t& st, uint32_t sym) { const uint32_t nb = (uint32_t)((int)st + dnb[sym]) >> 16; e.add(st, nb); st = state_tab[(int)(st >> nb) + dfs[sym]]; };
+    auto encode = [&](uint32_t& st, uint32_t sym) { const uint32_t nb = (uint32_t)((int)st + dnb[sym]) >> 16; b.add(st, nb); st = state_tab[(int)(st >> nb) + dfs[sym]]; };
     uint32_t ip = n, s1, s2;
     if (n & 1) { s1 = init_state(w[--ip]); s2 = init_state(w[--ip]); encode(s1, w[--ip]); }
     else { s2 = init_state(w[--ip]); s1 = init_state(w[--ip]); }
     while (ip > 0) { encode(s2, w[--ip]); encode(s1, w[--ip]); }
-    e.add(s2, tl); e.add(s1, tl);
-    e.add(1, 1);                                                      // end mark
-    const uint32_t body = e.close_bytes();
-    if (b.ovf || e.ovf) return 0;
-    return hdr + body;
+    b.add(s2, tl); b.add(s1, tl);
+    b.add(1, 1);                                                      // end mark
+    b.flush();
+    const uint32_t total_bytes = b.bytes();
+    if (b.pos >= b.cap || total_bytes > 127) return 0;
+    return total_bytes;
 }
 
-__global__ void __launch_bounds__(128) k_zenc_build(ZencParams P)
+// Scratch of one frame's build, in shared memory: thread-private arrays of this size in LOCAL memory (the first version,
+// one thread per frame) made every access an L2 round trip -- 2.7 ms for the 110k frames of a 20k-read batch.
+struct ZencBuildWs {
+    uint32_t key[256];           // present symbols: count << 8 | symbol, sorted ascending
+    uint32_t wgt[256];           // weights of the internal nodes of the Huffman tree
+    uint16_t par[512];           // parent (index among the internal nodes) of leaf i / of internal node 256 + j
+    uint8_t depth[256], len[256], wts[256];
+    ZeFseWs fse;
+};
+constexpr int ZE_BUILD_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * ZE_BUILD_WARPS) k_zenc_build(ZencParams P)
 {
+    __shared__ ZencBuildWs wsa[ZE_BUILD_WARPS];
     const int nf = codec_frames(P.codec);
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)P.nchunks * nf) return;
-    const uint32_t c = (uint32_t)(idx / nf); const int f = (int)(idx % nf);
-    uint64_t a, b; ze_frame_range(nf, P.stream_off + 5 * (size_t)c, f, a, b);
-    const uint32_t size = (uint32_t)(b - a);
-    ZencFrame* fr = P.frames + idx;
-    fr->mode = ZM_RAW; fr->rle_byte = 0; fr->log = 0; fr->desc_len = 0; fr->est_bytes = size;
-    if (size < ZE_HUF_MIN || size > ZE_BLOCK_MAX) return;
-    const uint32_t* hist = P.hist + idx * 256;
-    // ---- present symbols, sorted by (count, symbol) ascending: shell sort of packed keys ----
-    uint32_t key[256]; uint32_t m = 0, maxsym = 0;
-    for (uint32_t s = 0; s < 256; ++s) { const uint32_t k = hist[s]; if (k) { key[m++] = (k << 8) | s; maxsym = s; } }
-    if (m == 0) return;
-    if (m == 1) { fr->mode = ZM_RLE; fr->rle_byte = key[0] & 0xFF; return; }
-    for (uint32_t gap = m >> 1; gap; gap = gap == 2 ? 1 : (gap * 5) / 11) {
-        for (uint32_t i = gap; i < m; ++i) { const uint32_t v = key[i]; uint32_t j = i; while (j >= gap && key[j - gap] > v) { key[j] = key[j - gap]; j -= gap; } key[j] = v; }
-        if (gap == 1) break;
-    }
-    // ---- Huffman tree by the two-queue method: leaves in key order, internal nodes are created in non-decreasing weight ----
-    uint32_t wgt[256];           // weights of the internal nodes (m - 1 of them)
-    uint16_t par[512];           // parent (index among internal nodes) of leaf i (0..m-1) / internal node j (256 + j)
-    {
-        uint32_t li = 0, qi = 0, qn = 0;
-        while (qn < m - 1) {
-            uint32_t sum = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    ZencBuildWs& w = wsa[threadIdx.x >> 5];
+    const size_t nframes = (size_t)P.nchunks * nf;
+    for (size_t idx = (size_t)blockIdx.x * ZE_BUILD_WARPS + (threadIdx.x >> 5); idx < nframes; idx += (size_t)gridDim.x * ZE_BUILD_WARPS) {
+        const uint32_t c = (uint32_t)(idx / nf); const int f = (int)(idx % nf);
+        uint64_t a, b; ze_frame_range(nf, P.stream_off + 5 * (size_t)c, f, a, b);
+        const uint32_t size = (uint32_t)(b - a);
+        ZencFrame* fr = P.frames + idx;
+        __syncwarp();
+        if (lane == 0) { fr->mode = ZM_RAW; fr->rle_byte = 0; fr->log = 0; fr->desc_len = 0; fr->est_bytes = size; }
+        __syncwarp();
+        if (size < ZE_HUF_MIN || size > ZE_BLOCK_MAX) continue;
+        const uint32_t* hist = P.hist + idx * 256;
+        // ---- the warp: present symbols (8 per lane), a cheap bound of the coded size, rank sort by (count, symbol) ----
+        uint32_t mine[8], npres = 0, maxs = 0;
+        float entropy = 0.f;                                          // order-0 entropy of the frame in bits: no prefix code does better
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const bool leaf = li < m && (qi >= qn || (key[li] >> 8) <= wgt[qi]);
-                if (leaf) { sum += key[li] >> 8; par[li++] = (uint16_t)qn; } else { sum += wgt[qi]; par[256 + qi++] = (uint16_t)qn; }
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t sym = lane * 8 + k, cnt = hist[sym];
+            mine[k] = cnt ? ((cnt << 8) | sym) : 0u;
+            if (cnt) { ++npres; maxs = sym; entropy += (float)cnt * log2f((float)size / (float)cnt); }
+        }
+        const uint32_t inc = warp_inclusive_scan(npres);
+        const uint32_t m = __shfl_sync(0xffffffffu, inc, 31);
+        maxs = __reduce_max_sync(0xffffffffu, maxs);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) entropy += __shfl_xor_sync(0xffffffffu, entropy, d);
+        if (m == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (mine[k]) { fr->mode = ZM_RLE; fr->rle_byte = mine[k] & 0xFF; }
+        }
+        if (m <= 1) continue;
+        // nothing to gain (nibble pairs, noise): even the entropy bound saves less than ~2 % -- leave the frame raw
+        if (entropy * 0.125f + 24.f >= (float)size * 0.98f) continue;
+        {
+            uint32_t pos = inc - npres;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (mine[k]) w.key[pos++] = mine[k];           // unsorted, compact
+        }
+        __syncwarp();
+        // bitonic sort of the 256-entry key array (absent symbols: 0xFFFFFFFF, they end up behind the m present ones): 36
+        // stages of 128 compare-exchanges, four per lane
+        for (uint32_t i = m + lane; i < 256; i += 32) w.key[i] = 0xFFFFFFFFu;
+        __syncwarp();
+        for (uint32_t k = 2; k <= 256; k <<= 1)
+            for (uint32_t j = k >> 1; j; j >>= 1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t x = lane + 32 * t;                 // pair index 0..127 -> the lower element of the pair
+                    const uint32_t i = ((x & ~(j - 1)) << 1) | (x & (j - 1)), l = i | j;
+                    const uint32_t a0 = w.key[i], b0 = w.key[l];
+                    const bool up = (i & k) == 0;
+                    if ((a0 > b0) == up) { w.key[i] = b0; w.key[l] = a0; }
+                }
+                __syncwarp();
             }
-            wgt[qn++] = sum;
+        // ---- lane 0: Huffman tree by the two-queue method: leaves in key order, internal nodes are created in non-decreasing weight ----
+        if (lane == 0) {
+            constexpr uint32_t INF = 0xFFFFFFFFu;
+            uint32_t li = 0, qi = 0, qn = 0, lw = w.key[0] >> 8, iw = INF;        // heads of the two queues stay in registers
+            while (qn < m - 1) {
+                uint32_t sum = 0;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (lw <= iw) { sum += lw; w.par[li++] = (uint16_t)qn; lw = li < m ? w.key[li] >> 8 : INF; }
+                    else { sum += iw; w.par[256 + qi++] = (uint16_t)qn; iw = qi < qn ? w.wgt[qi] : INF; }
+                }
+                w.wgt[qn] = sum;
+                if (iw == INF && qi == qn) iw = sum;                  // the internal queue was empty: the new node is its head
+                ++qn;
+            }
+            w.depth[m - 2] = 0;                                       // the root is the last internal node
+            for (int j = (int)m - 3; j >= 0; --j) w.depth[j] = (uint8_t)(w.depth[w.par[256 + j]] + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w.len[lane * 8 + k] = 0;
+        __syncwarp();
+        uint32_t maxlen = 0;
+        for (uint32_t i = lane; i < m; i += 32) { const uint32_t l = w.depth[w.par[i]] + 1u; w.len[w.key[i] & 0xFF] = (uint8_t)l; maxlen = max(maxlen, l); }
+        maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+        __syncwarp();
+        if (maxlen > ZE_LOG_MAX) {
+            // length limit (rare: very skewed histograms): cut at ZE_LOG_MAX, then repair the Kraft sum -- lengthen the rarest
+            // symbols that still can be lengthened until the code fits, then give spare code space back to the most frequent ones
+            uint32_t ok = 1, kraft = 0, nfull = 0;
+            for (uint32_t i = lane; i < m; i += 32) { uint8_t& l = w.len[w.key[i] & 0xFF]; if (l > ZE_LOG_MAX) l = ZE_LOG_MAX; kraft += 1u << (ZE_LOG_MAX - l); nfull += l == ZE_LOG_MAX; }
+            kraft = __reduce_add_sync(0xffffffffu, kraft); nfull = __reduce_add_sync(0xffffffffu, nfull);       // lengths do not grow along the sorted order: the first nfull symbols are at the limit
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t full = 1u << ZE_LOG_MAX;
+                while (kraft > full)
+                    for (uint32_t i = nfull; i < m && kraft > full; ++i) { uint8_t& l = w.len[w.key[i] & 0xFF]; if (l < ZE_LOG_MAX) { kraft -= 1u << (ZE_LOG_MAX - l - 1); ++l; } }
+                for (int i = (int)m - 1; i >= 0 && kraft < full; --i) { uint8_t& l = w.len[w.key[i] & 0xFF]; while (l > 1 && kraft + (1u << (ZE_LOG_MAX - l)) <= full) { kraft += 1u << (ZE_LOG_MAX - l); --l; } }
+                ok = kraft == full;
+            }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            __syncwarp();
+            if (!ok) continue;                                        // cannot happen; raw is always valid
+            maxlen = 0;
+            for (uint32_t i = lane; i < m; i += 32) maxlen = max(maxlen, (uint32_t)w.len[w.key[i] & 0xFF]);
+            maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+        }
+        const uint32_t L = maxlen;
+        // ---- codes in the order of zstd's decoding table (HUF_readDTableX1): ascending weight = descending length, symbols
+        //      in natural order inside a weight; a symbol of weight wt owns 2^(wt-1) consecutive entries. Per lane: 8
+        //      consecutive symbols; first entry of each = entries of lighter symbols + entries of equal weight in front ----
+        uint32_t cntw[13];                                            // entries of weight wt among my 8 symbols
+#pragma unroll
+        for (int k = 0; k < 13; ++k) cntw[k] = 0;
+        uint32_t lens[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { lens[k] = w.len[lane * 8 + k]; if (lens[k]) { const uint32_t wt = L + 1 - lens[k]; for (int q = 1; q < 13; ++q) if ((uint32_t)q == wt) cntw[q] += 1u << (wt - 1); } }
+        uint32_t before[13], startw[13];                              // exclusive scan over the lanes, per weight; total per weight
+        uint32_t run = 0;
+#pragma unroll
+        for (int q = 1; q < 13; ++q) { const uint32_t i2 = warp_inclusive_scan(cntw[q]); before[q] = i2 - cntw[q]; startw[q] = run; run += __shfl_sync(0xffffffffu, i2, 31); }
+        unsigned long long bits = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint16_t cw = 0;
+            if (lens[k]) {
+                const uint32_t wt = L + 1 - lens[k];
+                uint32_t e = 0;
+#pragma unroll
+                for (int q = 1; q < 13; ++q) if ((uint32_t)q == wt) { e = startw[q] + before[q]; before[q] += 1u << (wt - 1); }
+                cw = (uint16_t)((lens[k] << 11) | (e >> (wt - 1)));
+                bits += (unsigned long long)hist[lane * 8 + k] * lens[k];
+            }
+            fr->code[lane * 8 + k] = cw;
+            w.wts[lane * 8 + k] = lens[k] ? (uint8_t)(L + 1 - lens[k]) : 0;
+        }
+        bits += __shfl_xor_sync(0xffffffffu, bits, 16); bits += __shfl_xor_sync(0xffffffffu, bits, 8); bits += __shfl_xor_sync(0xffffffffu, bits, 4);
+        bits += __shfl_xor_sync(0xffffffffu, bits, 2); bits += __shfl_xor_sync(0xffffffffu, bits, 1);
+        __syncwarp();
+        // ---- tree description = weights of symbols 0 .. maxsym-1 (the last one is implied): counted by the warp, coded by lane 0 ----
+        if (lane < 13) w.fse.cnt[lane] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (lane * 8 + k < maxs) atomicAdd(&w.fse.cnt[lens[k] ? L + 1 - lens[k] : 0], 1u);
+        uint32_t maxw = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (lane * 8 + k < maxs && lens[k]) maxw = max(maxw, L + 1 - lens[k]);
+        maxw = __reduce_max_sync(0xffffffffu, maxw);
+        __syncwarp();
+        uint32_t dl = 0, have = 1;
+        if (lane == 0) {
+            const uint32_t maxsym = maxs;
+            dl = ze_fse_weights(w.wts, maxsym, maxw, w.fse);
+            if (dl && dl < 128 && (maxsym > 128 || dl < (maxsym + 1) / 2)) fr->desc[0] = (uint8_t)dl;
+            else if (maxsym <= 128) {                                 // direct: 4 bits per weight, first weight in the high nibble
+                fr->desc[0] = (uint8_t)(127 + maxsym);
+                dl = (maxsym + 1) / 2;
+                for (uint32_t i = 0; i < dl; ++i) fr->desc[1 + i] = (uint8_t)((w.wts[2 * i] << 4) | (2 * i + 1 < maxsym ? w.wts[2 * i + 1] : 0));
+                dl |= 0x80000000u;                                    // already written
+            } else have = 0;                                          // no representation: raw
+        }
+        dl = __shfl_sync(0xffffffffu, dl, 0); have = __shfl_sync(0xffffffffu, have, 0);
+        __syncwarp();
+        if (have && !(dl & 0x80000000u)) for (uint32_t i = lane; i < dl; i += 32) fr->desc[1 + i] = (uint8_t)(w.fse.out[i >> 2] >> (8 * (i & 3)));
+        dl &= 0x7FFFFFFFu;
+        if (lane == 0) {
+            if (have) {
+                fr->desc_len = 1 + dl; fr->log = L; fr->est_bytes = (uint32_t)((bits + 7) >> 3);
+                // worth it only if the literals section beats a raw block (ZSTD_minGain-like margin)
+                if (fr->desc_len + fr->est_bytes + 16 + (size >> 6) < size) fr->mode = ZM_HUF;
+            }
         }
     }
-    uint8_t depth[256];          // of the internal nodes; the root is the last one
-    depth[m - 2] = 0;
-    for (int j = (int)m - 3; j >= 0; --j) depth[j] = (uint8_t)(depth[par[256 + j]] + 1);
-    uint8_t len[256];            // code length per SYMBOL
-    for (uint32_t s = 0; s < 256; ++s) len[s] = 0;
-    uint32_t maxlen = 0;
-    for (uint32_t i = 0; i < m; ++i) { const uint32_t l = depth[par[i]] + 1u; len[key[i] & 0xFF] = (uint8_t)l; if (l > maxlen) maxlen = l; }
-    if (maxlen > ZE_LOG_MAX) {
-        // length limit: cut at ZE_LOG_MAX, then repair the Kraft sum -- lengthen the rarest symbols that still can be
-        // lengthened until the code fits, then give spare code space back to the most frequent symbols that can use it
-        uint32_t kraft = 0;
-        for (uint32_t i = 0; i < m; ++i) { uint8_t& l = len[key[i] & 0xFF]; if (l > ZE_LOG_MAX) l = ZE_LOG_MAX; kraft += 1u << (ZE_LOG_MAX - l); }
-        const uint32_t full = 1u << ZE_LOG_MAX;
-        while (kraft > full) {
-            for (uint32_t i = 0; i < m && kraft > full; ++i) { uint8_t& l = len[key[i] & 0xFF]; if (l < ZE_LOG_MAX) { kraft -= 1u << (ZE_LOG_MAX - l - 1); ++l; } }
-        }
-        for (int i = (int)m - 1; i >= 0 && kraft < full; --i) { uint8_t& l = len[key[i] & 0xFF]; while (l > 1 && kraft + (1u << (ZE_LOG_MAX - l)) <= full) { kraft += 1u << (ZE_LOG_MAX - l); --l; } }
-        if (kraft != full) return;                                    // cannot happen; raw is always valid
-        maxlen = 0;
-        for (uint32_t i = 0; i < m; ++i) maxlen = max(maxlen, (uint32_t)len[key[i] & 0xFF]);
-    }
-    const uint32_t L = maxlen;
-    // ---- codes in the order of zstd's decoding table (HUF_readDTableX1): ascending weight = descending length, symbols
-    //      in natural order inside a weight; a symbol of weight w owns 2^(w-1) consecutive entries ----
-    uint32_t start[14]; for (int k = 0; k < 14; ++k) start[k] = 0;
-    for (uint32_t s = 0; s <= maxsym; ++s) if (len[s]) start[L + 1 - len[s] + 1] += 1u << (L - len[s]);      // entries of weight w, accumulated at w + 1
-    for (uint32_t k = 1; k < 14; ++k) start[k] += start[k - 1];      // start[w] = first entry of weight w
-    unsigned long long bits = 0;
-    for (uint32_t s = 0; s < 256; ++s) {
-        uint16_t cw = 0;
-        if (s <= maxsym && len[s]) {
-            const uint32_t w = L + 1 - len[s];
-            const uint32_t e = start[w]; start[w] += 1u << (w - 1);
-            cw = (uint16_t)((len[s] << 11) | (e >> (w - 1)));
-            bits += (unsigned long long)hist[s] * len[s];
-        }
-        fr->code[s] = cw;
-    }
-    // ---- tree description: weights of symbols 0 .. maxsym-1 (the last one is implied) ----
-    uint8_t wts[256];
-    for (uint32_t s = 0; s < maxsym; ++s) wts[s] = len[s] ? (uint8_t)(L + 1 - len[s]) : 0;
-    uint32_t dl = ze_fse_weights(wts, maxsym, fr->desc + 1, 127);
-    if (dl && dl < 128 && (maxsym > 128 || dl < (maxsym + 1) / 2)) fr->desc[0] = (uint8_t)dl;
-    else if (maxsym <= 128) {                                         // direct: 4 bits per weight, first weight in the high nibble
-        fr->desc[0] = (uint8_t)(127 + maxsym);
-        dl = (maxsym + 1) / 2;
-        for (uint32_t i = 0; i < dl; ++i) fr->desc[1 + i] = (uint8_t)((wts[2 * i] << 4) | (2 * i + 1 < maxsym ? wts[2 * i + 1] : 0));
-    } else return;                                                    // no representation: raw
-    fr->desc_len = 1 + dl;
-    fr->log = L;
-    fr->est_bytes = (uint32_t)((bits + 7) >> 3);
-    // worth it only if the literals section beats a raw block (ZSTD_minGain-like margin)
-    if (fr->desc_len + fr->est_bytes + 16 + (size >> 6) < size) fr->mode = ZM_HUF;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -320,13 +422,42 @@ __device__ inline uint32_t ze_frame_header(uint8_t* o, uint32_t size)
 }
 __device__ inline void ze_block_header(uint8_t* o, uint32_t last, uint32_t type, uint32_t size) { const uint32_t v = last | (type << 1) | (size << 3); o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); }
 
+// Calls f(byte) for the bytes p[b-1], p[b-2], .. p[a] (last first: the order zstd's Huffman streams are written in). The
+// middle of the range is read as aligned 32-bit words, at most three bytes at either end one by one; every lane walks the
+// same three loops (ranges of a warp have the same length up to one symbol), so the lanes do not serialise on their
+// alignment. (16-byte blocks with a predicated body for the ragged ones were tried: the ranges are 25..250 symbols, the
+// two bodies ran for almost every block and the kernel was 2.4 x slower.)
+template <typename F>
+__device__ __forceinline__ void ze_for_bytes_rev(const uint8_t* p, uint32_t a, uint32_t b, F f)
+{
+    const uint32_t nt = min(b - a, (uint32_t)((uintptr_t)(p + b) & 3u));
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k) if (k < nt) f((uint32_t)p[b - 1 - k]);
+    uint32_t i = b - nt;
+    for (uint32_t nw = (i - a) >> 2; nw; --nw) { i -= 4; const uint32_t v = *(const uint32_t*)(p + i); f(v >> 24); f((v >> 16) & 0xFFu); f((v >> 8) & 0xFFu); f(v & 0xFFu); }
+    const uint32_t rest = i - a;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k) if (k < rest) f((uint32_t)p[i - 1 - k]);
+}
+
+// Zeroes bytes [0, n) at dst (any alignment), all threads of the CTA.
+__device__ inline void ze_zero(uint8_t* dst, uint32_t n)
+{
+    const int tid = threadIdx.x;
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    if ((uint32_t)tid < head) dst[tid] = 0;
+    const uint32_t nw = (n - head) >> 2;
+    uint32_t* d = (uint32_t*)(dst + head);
+    for (uint32_t i = tid; i < nw; i += ZE_NT) d[i] = 0;
+    const uint32_t done = head + (nw << 2);
+    if (done + (uint32_t)tid < n) dst[done + tid] = 0;
+}
+
 struct ZencWs {
     uint32_t warp_tot[ZE_NT / 32];
-    uint32_t seg_bits[4];
     uint32_t pos;                // bytes of the chunk's slot written so far
     uint32_t fail;
     uint16_t code[256];
-    uint32_t buf[ZE_SEG_SMEM / 4 + 4];
 };
 
 __global__ void __launch_bounds__(ZE_NT) k_zenc_emit(ZencParams P)
@@ -349,32 +480,38 @@ __global__ void __launch_bounds__(ZE_NT) k_zenc_emit(ZencParams P)
             const uint32_t pre = f + 1 < nf ? 8u : 0u;                 // u64 size prefix of every frame but the last (A.3-A.7)
             const uint32_t base = ws.pos;
             uint32_t mode = fr->mode;
-            // ---- Huffman: bit lengths per thread and stream, suffix scans ----
-            uint32_t nstr = 1, q = size, sbytes[4] = {0, 0, 0, 0}, my_bits[4] = {0, 0, 0, 0}, my_start[4] = {0, 0, 0, 0};
-            uint32_t r0[4], r1[4];                                    // my symbol range in every stream
+            // ---- Huffman: the frame's 1 or 4 streams at once, a quarter of the CTA each; bit lengths per thread, suffix scan ----
+            uint32_t nstr = 1, q = size, sbytes[4] = {0, 0, 0, 0}, tot_bits[4] = {0, 0, 0, 0};
+            uint32_t my_bits = 0, my_start = 0, r0 = 0, r1 = 0, my_j = 0;
             if (mode == ZM_HUF) {
                 for (int i = tid; i < 256; i += ZE_NT) ws.code[i] = fr->code[i];
                 __syncthreads();
                 nstr = size >= 256 ? 4u : 1u; q = nstr == 4 ? (size + 3) / 4 : size;
-                for (uint32_t j = 0; j < nstr; ++j) {
-                    const uint32_t s0 = j * q, s1 = min(size, s0 + q), m = s1 - s0, per = (m + ZE_NT - 1) / ZE_NT;
-                    r0[j] = min(s1, s0 + (uint32_t)tid * per); r1[j] = min(s1, r0[j] + per);
-                    uint32_t bits = 0;
-                    for (uint32_t i = r0[j]; i < r1[j]; ++i) bits += ws.code[src[i]] >> 11;
-                    my_bits[j] = bits;
-                    // exclusive SUFFIX sum over the threads: the stream's last symbol is written first (lowest bits)
-                    const uint32_t inc = warp_inclusive_scan(bits);
-                    if (lane == 31) ws.warp_tot[warp] = inc;
-                    __syncthreads();
-                    uint32_t before = 0, total = 0;
+                const uint32_t G = ZE_NT / nstr;                        // threads per stream (whole warps)
+                my_j = (uint32_t)tid / G;
+                const uint32_t t = (uint32_t)tid % G, s0 = my_j * q, s1 = min(size, s0 + q), per = (s1 - s0 + G - 1) / G;
+                r0 = min(s1, s0 + t * per); r1 = min(s1, r0 + per);
+                uint32_t bits = 0;
+                ze_for_bytes_rev(src, r0, r1, [&](uint32_t sym) { bits += ws.code[sym] >> 11; });
+                my_bits = bits;
+                // exclusive SUFFIX sum over the stream's threads: its last symbol is written first (lowest bits)
+                const uint32_t inc = warp_inclusive_scan(bits);
+                if (lane == 31) ws.warp_tot[warp] = inc;
+                __syncthreads();
+                uint32_t before = 0;
+                const uint32_t wps = G / 32, gw0 = my_j * wps;
 #pragma unroll
-                    for (int k = 0; k < ZE_NT / 32; ++k) { const uint32_t t = ws.warp_tot[k]; total += t; if (k < warp) before += t; }
-                    my_start[j] = total - (before + inc);              // bits of all symbols behind my range
-                    if (tid == 0) ws.seg_bits[j] = total;
-                    __syncthreads();
-                    sbytes[j] = (ws.seg_bits[j] + 1 + 7) >> 3;
-                    if (sbytes[j] > ZE_SEG_SMEM || (nstr == 4 && j < 3 && sbytes[j] > 0xFFFF)) mode = ZM_RAW;      // does not fit the bit buffer / the jump table
+                for (int k = 0; k < ZE_NT / 32; ++k) {
+                    const uint32_t tw = ws.warp_tot[k];
+                    tot_bits[(uint32_t)k / wps < 4 ? (uint32_t)k / wps : 3] += tw;
+                    if ((uint32_t)k >= gw0 && k < warp) before += tw;
                 }
+                my_start = tot_bits[my_j] - (before + inc);             // bits of all symbols behind my range
+                for (uint32_t j = 0; j < nstr; ++j) {
+                    sbytes[j] = (tot_bits[j] + 1 + 7) >> 3;
+                    if (nstr == 4 && j < 3 && sbytes[j] > 0xFFFF) mode = ZM_RAW;      // does not fit the jump table
+                }
+                __syncthreads();
             }
             uint32_t lit_comp = 0, lhs = 0;
             if (mode == ZM_HUF) {
@@ -419,31 +556,29 @@ __global__ void __launch_bounds__(ZE_NT) k_zenc_emit(ZencParams P)
                     if (nstr == 4) for (int j = 0; j < 3; ++j) { d[2 * j] = (uint8_t)sbytes[j]; d[2 * j + 1] = (uint8_t)(sbytes[j] >> 8); }
                     blk[3 + lhs + lit_comp] = 0;                          // sequences section: Number_of_Sequences = 0
                 }
+                // The streams lie back to back behind the jump table. Their bytes are zeroed, then every thread ORs / stores its
+                // bits straight into the slot: whole 32-bit words of its own as plain stores, the two ragged words at the ends
+                // of its range -- shared with the neighbouring threads or the neighbouring bytes -- with atomic OR.
                 uint8_t* sdst = blk + 3 + lhs + fr->desc_len + (nstr == 4 ? 6u : 0u);
-                for (uint32_t j = 0; j < nstr; ++j) {
-                    const uint32_t nwords = (sbytes[j] + 3) >> 2;
-                    for (uint32_t i = tid; i < nwords; i += ZE_NT) ws.buf[i] = 0;
-                    __syncthreads();
-                    if (tid == 0) atomicOr(&ws.buf[ws.seg_bits[j] >> 5], 1u << (ws.seg_bits[j] & 31));      // end mark above the first symbol's code
-                    // my symbols, last first, appended LSB-first from bit my_start: whole words are mine alone and go out as
-                    // plain stores, the two ragged words are shared with the neighbours (atomic OR)
-                    if (r1[j] > r0[j] && my_bits[j]) {
-                        uint32_t bit = my_start[j];
-                        unsigned long long acc = 0; uint32_t fill = bit & 31, wi = bit >> 5; bool first = true;
-                        for (uint32_t i = r1[j]; i-- > r0[j];) {
-                            const uint32_t cw = ws.code[src[i]];
-                            acc |= (unsigned long long)(cw & 0x7FFu) << fill; fill += cw >> 11;
-                            if (fill >= 32) {
-                                if (first) { atomicOr(&ws.buf[wi], (uint32_t)acc); first = false; } else ws.buf[wi] = (uint32_t)acc;
-                                ++wi; acc >>= 32; fill -= 32;
-                            }
+                ze_zero(sdst, sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3]);
+                __syncthreads();
+                uint8_t* mine = sdst;
+                for (uint32_t j = 0; j < my_j; ++j) mine += sbytes[j];
+                uint32_t* wbase = (uint32_t*)((uintptr_t)mine & ~(uintptr_t)3);
+                const uint32_t bit0 = 8u * (uint32_t)((uintptr_t)mine & 3u);
+                if ((uint32_t)tid % (ZE_NT / nstr) == 0) { const uint32_t eb = bit0 + tot_bits[my_j]; atomicOr(wbase + (eb >> 5), 1u << (eb & 31)); }      // end mark above the first symbol's code
+                if (my_bits) {
+                    const uint32_t bit = bit0 + my_start;
+                    unsigned long long acc = 0; uint32_t fill = bit & 31, wi = bit >> 5; bool first = true;
+                    ze_for_bytes_rev(src, r0, r1, [&](uint32_t sym) {
+                        const uint32_t cw = ws.code[sym];
+                        acc |= (unsigned long long)(cw & 0x7FFu) << fill; fill += cw >> 11;
+                        if (fill >= 32) {
+                            if (first) { atomicOr(wbase + wi, (uint32_t)acc); first = false; } else wbase[wi] = (uint32_t)acc;
+                            ++wi; acc >>= 32; fill -= 32;
                         }
-                        if (fill) atomicOr(&ws.buf[wi], (uint32_t)acc);
-                    }
-                    __syncthreads();
-                    ze_copy(sdst, (const uint8_t*)ws.buf, sbytes[j]);
-                    sdst += sbytes[j];
-                    __syncthreads();
+                    });
+                    if (fill) atomicOr(wbase + wi, (uint32_t)acc);
                 }
             }
             __syncthreads();

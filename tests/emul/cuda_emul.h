@@ -8,6 +8,7 @@
 // the product library (librnsc.so is built by nvcc only and fails loudly without a CUDA device).
 #pragma once
 #include <ucontext.h>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -72,6 +73,9 @@ inline int __all_sync(unsigned mask, int p) { unsigned long long all[32]; unsign
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     unsigned long long all[32]; unsigned arrived = emul::warp_exchange(mask, v, all); unsigned r = 0;
     for (int i = 0; i < 32; ++i) if ((arrived >> i) & 1) r += (unsigned)all[i]; return r; }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    unsigned long long all[32]; unsigned arrived = emul::warp_exchange(mask, v, all); unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if (((arrived >> i) & 1) && (unsigned)all[i] > r) r = (unsigned)all[i]; return r; }
 inline unsigned __activemask() { return 0xffffffffu; }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

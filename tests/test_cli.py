@@ -84,3 +84,53 @@ def test_cli_main_exit_codes(tmp_path, gpu_codec, capsys):
     bytes_, samples = capsys.readouterr().out.strip().split(";")
     assert int(samples) == 1548931 and int(bytes_) > 0
     assert cli.main([str(tmp_path / "missing.pod5"), out, "--VBZ"]) == 1
+
+
+# ---- streaming repack (stream_convert.py): record batches through the codec in bounded memory -------------------
+def _streaming_checks(tmp_path, codec, entropy_modes):
+    from rawnanoporesignalcompression_b200 import stream_convert as sc
+    a = str(tmp_path / "s_a.pod5"); b = str(tmp_path / "s_b.pod5"); u = str(tmp_path / "s_u.pod5"); ref = str(tmp_path / "s_ref.pod5")
+    # tiny groups (40k samples): the 22 rows / 1 record batch of the fixture still go through the group machinery
+    nbytes, nsamples = sc.convert_streaming(FIXTURE, a, "pgnano", "C5", codec, group_samples=40_000)
+    assert nsamples == 1548931 and 0 < nbytes < 2 * nsamples
+    cli.convert(FIXTURE, ref, "pgnano", "C5", codec)
+    ta, tr = pc.read_pod5(a), pc.read_pod5(ref)
+    assert ta.signal.equals(tr.signal)                                     # same bytes as the whole-file converter (host-libzstd entropy stage)
+    assert ta.raw[pc.CONTENT_READS] == tr.raw[pc.CONTENT_READS] and ta.raw[pc.CONTENT_RUN_INFO] == tr.raw[pc.CONTENT_RUN_INFO]
+    sc.convert_streaming(a, b, "VBZ", "C5", codec, group_samples=500_000)
+    ok, why = cli.files_equal(FIXTURE, b, "C5", codec)
+    assert ok, why
+    sc.convert_streaming(a, u, "uncompressed", "C5", codec)
+    ok, why = cli.files_equal(FIXTURE, u, "C5", codec)
+    assert ok, why
+    sc.convert_streaming(u, b, "pgnano", "C5", codec, group_samples=300_000)          # uncompressed input
+    assert pc.read_pod5(b).signal.equals(tr.signal)
+    for mode in entropy_modes:                                                         # device transcode: other bytes, same samples
+        g = str(tmp_path / f"s_g_{mode}.pod5")
+        sc.convert_streaming(FIXTURE, g, "pgnano", "C5", codec, group_samples=600_000, entropy=mode)
+        ok, why = cli.files_equal(FIXTURE, g, "C5", codec)
+        assert ok, why
+
+
+def test_streaming_repack_on_emulated_kernels(tmp_path, emul_lib):
+    from rawnanoporesignalcompression_b200.codec import Codec
+    cd = Codec(0, lib_path=emul_lib)
+    try:
+        _streaming_checks(tmp_path, cd, [])
+    finally:
+        cd.close()
+
+
+@pytest.mark.gpu
+def test_streaming_repack_gpu(tmp_path, gpu_codec):
+    _streaming_checks(tmp_path, gpu_codec, ["gpu"])
+    # a multi-batch synthetic file written group by group, repacked by the device transcode and back
+    from rawnanoporesignalcompression_b200 import stream_convert as sc, synth
+    src = str(tmp_path / "syn.pod5"); p = str(tmp_path / "syn_p.pod5"); v = str(tmp_path / "syn_v.pod5")
+    size, total = sc.write_synthetic_pod5(src, gpu_codec, 600, 20261018, synth.R10_4_1, "VBZ", template=FIXTURE, reads_per_group=128)
+    assert pc.read_pod5(src).signal.num_rows > 600
+    nb, ns = sc.convert_streaming(src, p, "pgnano", "C5", gpu_codec, group_samples=4_000_000, entropy="gpu")
+    assert ns == total
+    sc.convert_streaming(p, v, "VBZ", "C5", gpu_codec, group_samples=3_000_000)
+    ok, why = cli.files_equal(src, v, "C5", gpu_codec)
+    assert ok, why

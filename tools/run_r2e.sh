@@ -1,0 +1,24 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+TAG=${1:-r2e}
+C=/tmp/wl_c5.npz; V=/tmp/wl_vbz.npz
+L=gpurun_out/${TAG}_variants.log
+: > $L
+python tools/decode_bench.py 20000 6 --model R10.4.1 --cache $C --lib tools/variants/librnsc_r1.so --tag r1 >> $L 2>&1
+python tools/decode_bench.py 20000 6 --model R10.4.1 --cache $C --phases --tag new >> $L 2>&1
+for v in planlocal32 planlocal128 plan64; do
+  python tools/decode_bench.py 20000 6 --model R10.4.1 --cache $C --lib tools/variants/librnsc_$v.so --tag $v >> $L 2>&1
+done
+python tools/decode_bench.py 20000 0 --model R9.4.1 --cache $V --tag new >> $L 2>&1
+python tools/decode_bench.py 20000 0 --model R9.4.1 --cache $V --lib tools/variants/librnsc_planlocal128.so --tag planlocal128 >> $L 2>&1
+python tools/dev_encode_bench.py 20000 6 >> $L 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_zenc|k_svb|k_exclusive" -s 21 -c 27 --csv --log-file gpurun_out/${TAG}_enc_launches.csv python tools/dev_encode_bench.py 20000 6 --steps 3 > gpurun_out/${TAG}_ncu_enc.log 2>&1
+python tools/dev_encode_bench.py 20000 0 --model R9.4.1 >> $L 2>&1
+cat $L
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/r2e_enc_launches.csv')) if len(r)>5]
+h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
+for r in rows[1:]: print(r[ki][:50], r[vi])
+PY
