@@ -34,10 +34,30 @@ class UsageError(SystemExit):
         super().__init__(1)
 
 
+OPTIONS = {"entropy": "libzstd", "group_samples": 0, "whole_file": False}      # extensions picked up by main(): --entropy libzstd|gpu, --group-samples N, --whole-file
+
+
 def parse_args(argv: Sequence[str], cwd: Optional[str] = None) -> Tuple[str, str, str, str]:
-    """(input path, output path, compression, pgnano variant). copy.cpp:18-62 plus the --variant extension."""
+    """(input path, output path, compression, pgnano variant). copy.cpp:18-62 plus the --variant extension (and, for main(),
+    --entropy libzstd|gpu: who writes the zstd frames; --group-samples N: samples per streaming group; --whole-file: the
+    non-streaming converter)."""
     args = list(argv)
     variant = "C5"
+    OPTIONS.update(entropy="libzstd", group_samples=0, whole_file=False)
+    for flag, key, conv in (("--entropy", "entropy", str), ("--group-samples", "group_samples", int)):
+        if flag in args:
+            i = args.index(flag)
+            if i + 1 >= len(args):
+                raise UsageError(f"{flag} needs a value")
+            try:
+                OPTIONS[key] = conv(args[i + 1])
+            except ValueError:
+                raise UsageError(f"bad value for {flag}") from None
+            del args[i : i + 2]
+    if OPTIONS["entropy"] not in ("libzstd", "gpu"):
+        raise UsageError("--entropy must be libzstd or gpu")
+    if "--whole-file" in args:
+        args.remove("--whole-file"); OPTIONS["whole_file"] = True
     if "--variant" in args:
         i = args.index("--variant")
         if i + 1 >= len(args):
@@ -162,7 +182,11 @@ def files_equal(path_a: str, path_b: str, variant: str = "C5", codec=None) -> Tu
 def main(argv: Optional[Sequence[str]] = None) -> int:
     in_path, out_path, comp, variant = parse_args(sys.argv[1:] if argv is None else argv)
     try:
-        nbytes, nsamples = convert(in_path, out_path, comp, variant)
+        if OPTIONS["whole_file"]:
+            nbytes, nsamples = convert(in_path, out_path, comp, variant)
+        else:       # record batches stream through the codec in bounded memory (stream_convert.py)
+            from .stream_convert import DEFAULT_GROUP_SAMPLES, convert_streaming
+            nbytes, nsamples = convert_streaming(in_path, out_path, comp, variant, None, OPTIONS["group_samples"] or DEFAULT_GROUP_SAMPLES, OPTIONS["entropy"])
     except Exception as e:  # noqa: BLE001  (pod5_management_utils.h:32-37 prints the error and exits 1)
         print(f"Error: {e}", file=sys.stderr)
         return 1

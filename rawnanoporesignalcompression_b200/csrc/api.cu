@@ -147,6 +147,7 @@ struct rnsc_ctx {
     std::mutex mu;   // host-buffer entry points serialise on the context's staging
     DevBuf d_samples, d_comp, d_off_a, d_off_b, d_n, d_status, d_sizes, d_streams, d_stream_off, d_scratch, d_counter, d_aux;
     DevBuf d_plans, d_lists, d_deftab, d_prof, d_seqpool, d_origin;
+    DevBuf d_slab;                            // rnsc_dev_encode: slab offsets (u64) and sizes (u32) of the one-pass splitter
     DevBuf d_zhist, d_zframes, d_zslots, d_zslot_sz, d_zslot_off, d_zout_sz;   // GPU entropy stage of the encoders (zstd_encode.cuh)
     int entropy_stage = 0;                    // rnsc_compress_batch: 0 = host libzstd level 1 (byte-identical to the reference), 1 = GPU entropy stage
     bool profiling = false;
@@ -337,6 +338,7 @@ rnsc_ctx* rnsc_create(int device)
                                            cudaEventCreateWithFlags(&c->lane[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { rnsc_destroy(c); fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
+    { cudaError_t e0 = cudaFuncSetAttribute(k_zenc_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZE_BUILD_SMEM); if (e1 == cudaSuccess) e1 = e0; }
     cudaError_t e2 = cudaSuccess;
     cudaError_t e3 = cudaFuncSetAttribute(k_decode_fast<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem[2]);
     if (e1 == cudaSuccess) e1 = e3;
@@ -369,7 +371,7 @@ void rnsc_destroy(rnsc_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);      // a half-built context (rnsc_create failure) has null handles
-    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin, &c->d_zhist, &c->d_zframes, &c->d_zslots, &c->d_zslot_sz, &c->d_zslot_off, &c->d_zout_sz}) b->release();
+    for (DevBuf* b : {&c->d_samples, &c->d_comp, &c->d_off_a, &c->d_off_b, &c->d_n, &c->d_status, &c->d_sizes, &c->d_streams, &c->d_stream_off, &c->d_scratch, &c->d_counter, &c->d_aux, &c->d_plans, &c->d_lists, &c->d_deftab, &c->d_prof, &c->d_seqpool, &c->d_origin, &c->d_zhist, &c->d_zframes, &c->d_zslots, &c->d_zslot_sz, &c->d_zslot_off, &c->d_zout_sz, &c->d_slab}) b->release();
     c->h_a.release(); c->h_b.release(); c->h_pool_seen.release();
     if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); } if (c->ev_hi) cudaEventDestroy(c->ev_hi);
     for (int i = 0; i < 3; ++i) { if (c->side[i]) { cudaStreamSynchronize(c->side[i]); cudaStreamDestroy(c->side[i]); } if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]); }
@@ -515,23 +517,34 @@ int rnsc_dev_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     if (!nchunks) { CUDA_OK(cudaMemsetAsync(d_comp_off, 0, 8, st)); return RNSC_OK; }
     const int nf = codec_frames(codec);
-    const size_t streams_cap = 2 * total_samples + total_samples / 4 + 16 * nchunks + 64;                     // sum of stream_bound(codec, n)
+    const size_t streams_cap = 4 * total_samples + 128 * nchunks + 64;                                        // >= the sum of the chunks' slabs (slab_layout: keys + every stream at its upper bound)
     const size_t slots_cap = 2 * total_samples + total_samples / 4 + 1104 * nchunks + 64;                     // sum of the reference's output capacities, 16-byte rounded
-    if (c->d_streams.reserve(streams_cap + 64) || c->d_stream_off.reserve((5 * nchunks + 1) * 8) || c->d_zhist.reserve(nchunks * nf * 256 * sizeof(uint32_t)) ||
+    if (c->d_streams.reserve(streams_cap + 64) || c->d_stream_off.reserve((5 * nchunks + 1) * 8) || c->d_sizes.reserve(5 * nchunks * sizeof(uint32_t) + 16) ||
+        c->d_slab.reserve(nchunks * 4 + 16 + (nchunks + 1) * 8) || c->d_zhist.reserve(nchunks * nf * 256 * sizeof(uint32_t)) ||
         c->d_zframes.reserve(nchunks * nf * sizeof(ZencFrame)) || c->d_zslots.reserve(slots_cap + 64) || c->d_zslot_sz.reserve(nchunks * 4 + 16) ||
         c->d_zslot_off.reserve((nchunks + 1) * 8) || c->d_zout_sz.reserve(nchunks * 4 + 16))
         return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(encoder scratch) failed");
-    int r = launch_svb_encode(c, codec, d_samples, d_sample_off, d_n, nchunks, (uint8_t*)c->d_streams.p, streams_cap, (uint64_t*)c->d_stream_off.p, st, false);
-    if (r) return r;
+    // splitter into per-chunk slabs: one pass over the samples (no size pass, no scan of the stream sizes)
+    uint64_t* slab_off = (uint64_t*)c->d_slab.p; uint32_t* slab_sz = (uint32_t*)((uint8_t*)c->d_slab.p + (nchunks + 1) * 8);
+    RNSC_LAUNCH(k_slab_sizes, (int)((nchunks + 255) / 256), 256, 0, st, d_n, (uint32_t)nchunks, codec, slab_sz);
+    RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)slab_sz, (unsigned long long)nchunks, (unsigned long long*)slab_off);
+    {
+        const int grid = (int)std::min<size_t>((size_t)1 << 30, nchunks);
+#define RNSC_SLAB(C) case C: RNSC_LAUNCH(k_svb_pack_slab<C>, grid, P2_NT, (size_t)P2_STAGE_BYTES, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, (uint8_t*)c->d_streams.p, (const uint64_t*)slab_off, (unsigned long long*)c->d_stream_off.p, (uint32_t*)c->d_sizes.p); break
+        switch (codec) { RNSC_SLAB(RNSC_VBZ); RNSC_SLAB(RNSC_VBZ0); RNSC_SLAB(RNSC_C1); RNSC_SLAB(RNSC_C2); RNSC_SLAB(RNSC_C3); RNSC_SLAB(RNSC_C4); default: RNSC_SLAB(RNSC_C5); }
+#undef RNSC_SLAB
+    }
+    c->launches += 3;
     RNSC_LAUNCH(k_zenc_slot_sizes, (int)((nchunks + 255) / 256), 256, 0, st, d_n, (uint32_t)nchunks, codec, (uint32_t*)c->d_zslot_sz.p);
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zslot_sz.p, (unsigned long long)nchunks, (unsigned long long*)c->d_zslot_off.p);
     ZencParams zp;
     zp.streams = (const uint8_t*)c->d_streams.p; zp.stream_off = (const uint64_t*)c->d_stream_off.p; zp.n = d_n; zp.nchunks = (uint32_t)nchunks; zp.codec = codec;
+    zp.stream_size = (const uint32_t*)c->d_sizes.p;
     zp.hist = (uint32_t*)c->d_zhist.p; zp.frames = (ZencFrame*)c->d_zframes.p; zp.slots = (uint8_t*)c->d_zslots.p; zp.slot_off = (const uint64_t*)c->d_zslot_off.p;
     zp.out_size = (uint32_t*)c->d_zout_sz.p; zp.status = d_status;
     const int wide = (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 8);
     RNSC_LAUNCH(k_zenc_histogram, wide, ZE_NT, 0, st, zp);
-    RNSC_LAUNCH(k_zenc_build, (int)std::min<size_t>((nchunks * nf + ZE_BUILD_WARPS - 1) / ZE_BUILD_WARPS, (size_t)c->sm_count * 16), 32 * ZE_BUILD_WARPS, 0, st, zp);
+    RNSC_LAUNCH(k_zenc_build, (int)std::min<size_t>((nchunks * nf + ZE_BUILD_WARPS * ZE_BUILD_SLOTS - 1) / (ZE_BUILD_WARPS * ZE_BUILD_SLOTS), (size_t)c->sm_count * 16), 32 * ZE_BUILD_WARPS, ZE_BUILD_SMEM, st, zp);
     RNSC_LAUNCH(k_zenc_emit, (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 6), ZE_NT, 0, st, zp);
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zout_sz.p, (unsigned long long)nchunks, (unsigned long long*)d_comp_off);
     RNSC_LAUNCH(k_zenc_gather, wide, ZE_NT, 0, st, (const uint8_t*)c->d_zslots.p, (const uint64_t*)c->d_zslot_off.p, (const uint64_t*)d_comp_off, (uint32_t)nchunks, d_comp,

@@ -275,7 +275,7 @@ __device__ __forceinline__ void scatter_c45(uint32_t t, uint32_t one, uint32_t v
 // ---- pass 2: write the streams of a chunk at dst[0..4] (global; stream k gets exactly the size pass 1 reported) ------
 // `stage` = P2_STAGE_BYTES of shared memory, 16-byte aligned.
 template <int CODEC, int NTH>
-__device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t* const* dst, Pack2Ws<NTH>* ws, uint8_t* stage)
+__device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t* const* dst, Pack2Ws<NTH>* ws, uint8_t* stage, uint32_t* runs_out = nullptr)
 {
     constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
     constexpr bool NIB1 = TWO;                                        // stream 1 is a nibble stream
@@ -395,6 +395,7 @@ __device__ __forceinline__ void svb_pack2(const int16_t* in, uint32_t n, uint8_t
     }
     __syncthreads();
     if (NIB1 && tid == 0 && (run1 & 1u)) d1[run1 >> 1] = (uint8_t)ws->carry[flip ^ 1];   // trailing half byte
+    if (runs_out && tid == 0) { runs_out[0] = run1; runs_out[1] = run2; runs_out[2] = run3; }        // units written per stream group (for callers that did not run the size pass)
     __syncthreads();
 }
 

@@ -51,9 +51,11 @@ struct ZencFrame {
 __host__ __device__ inline uint32_t ze_highbit(uint32_t v) { uint32_t r = 0; while (v >>= 1) ++r; return r; }
 
 // frame f of a chunk = stream f, except for the codecs that put keys and payload in ONE frame (VBZ, VBZ0: A.1, A.2)
-__host__ __device__ inline void ze_frame_range(int nf, const uint64_t* so, int f, uint64_t& a, uint64_t& b)
+// (sz == nullptr: dense streams, stream k ends where k+1 starts; else slab layout: start and size per stream, kernels.cuh)
+__host__ __device__ inline void ze_frame_range(int nf, const uint64_t* so, const uint32_t* sz, int f, uint64_t& a, uint64_t& b)
 {
-    if (nf == 1) { a = so[0]; b = so[2]; } else { a = so[f]; b = so[f + 1]; }
+    if (sz) { a = so[f]; b = a + sz[f] + (nf == 1 ? sz[1] : 0u); }
+    else if (nf == 1) { a = so[0]; b = so[2]; } else { a = so[f]; b = so[f + 1]; }
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -61,6 +63,7 @@ __host__ __device__ inline void ze_frame_range(int nf, const uint64_t* so, int f
 // -------------------------------------------------------------------------------------------------------------
 struct ZencParams {
     const uint8_t* streams; const uint64_t* stream_off;      // splitter output: stream k of chunk i = [stream_off[5i+k], stream_off[5i+k+1])
+    const uint32_t* stream_size = nullptr;                   // slab layout: stream k of chunk i = stream_size[5i+k] bytes at stream_off[5i+k]
     const uint32_t* n; uint32_t nchunks; int codec;
     uint32_t* hist;                                          // [nchunks][nf][256]
     ZencFrame* frames;                                       // [nchunks][nf]
@@ -75,8 +78,9 @@ __global__ void __launch_bounds__(ZE_NT) k_zenc_histogram(ZencParams P)
     const int nf = codec_frames(P.codec);
     for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) {
         const uint64_t* so = P.stream_off + 5 * (size_t)c;
+        const uint32_t* ssz = P.stream_size ? P.stream_size + 5 * (size_t)c : nullptr;
         for (int f = 0; f < nf; ++f) {
-            uint64_t a, b; ze_frame_range(nf, so, f, a, b);
+            uint64_t a, b; ze_frame_range(nf, so, ssz, f, a, b);
             const uint32_t size = (uint32_t)(b - a);
             uint32_t* out = P.hist + ((size_t)c * nf + f) * 256;
             if (size < ZE_HUF_MIN || size > ZE_BLOCK_MAX) continue;        // raw without looking (k_zenc_build applies the same test)
@@ -215,71 +219,93 @@ struct ZencBuildWs {
     uint16_t par[512];           // parent (index among the internal nodes) of leaf i / of internal node 256 + j
     uint8_t depth[256], len[256], wts[256];
     ZeFseWs fse;
+    uint32_t m, maxs, L, kraft, nfull, maxw, dl, have, size, live;   // state of the frame between the stages
+    unsigned long long bits;
 };
-constexpr int ZE_BUILD_WARPS = 8;
+constexpr int ZE_BUILD_WARPS = 4;        // warps per CTA
+constexpr int ZE_BUILD_SLOTS = 4;        // frames a warp builds at once: the serial stages run on ZE_BUILD_SLOTS lanes together
+constexpr size_t ZE_BUILD_SMEM = sizeof(ZencBuildWs) * ZE_BUILD_WARPS * ZE_BUILD_SLOTS;
 
+// A warp takes ZE_BUILD_SLOTS frames per round. The stages that parallelise (histogram scan, entropy bound, bitonic sort,
+// length assignment, canonical codes, weight counts) run with all 32 lanes, one frame after the other; the inherently
+// serial stages (two-queue Huffman tree, Kraft repair of the length limit, FSE coding of the weights) run ONCE, on lanes
+// 0, 8, 16, 24 at the same time, one frame each -- a serial stage costs the warp's issue slots once for four frames.
 __global__ void __launch_bounds__(32 * ZE_BUILD_WARPS) k_zenc_build(ZencParams P)
 {
-    __shared__ ZencBuildWs wsa[ZE_BUILD_WARPS];
+    RNSC_DYN_SMEM(smem_raw);
+    ZencBuildWs* wsa = (ZencBuildWs*)smem_raw + (threadIdx.x >> 5) * ZE_BUILD_SLOTS;
     const int nf = codec_frames(P.codec);
     const uint32_t lane = threadIdx.x & 31u;
-    ZencBuildWs& w = wsa[threadIdx.x >> 5];
     const size_t nframes = (size_t)P.nchunks * nf;
-    for (size_t idx = (size_t)blockIdx.x * ZE_BUILD_WARPS + (threadIdx.x >> 5); idx < nframes; idx += (size_t)gridDim.x * ZE_BUILD_WARPS) {
-        const uint32_t c = (uint32_t)(idx / nf); const int f = (int)(idx % nf);
-        uint64_t a, b; ze_frame_range(nf, P.stream_off + 5 * (size_t)c, f, a, b);
-        const uint32_t size = (uint32_t)(b - a);
-        ZencFrame* fr = P.frames + idx;
+    const size_t warp_id = (size_t)blockIdx.x * ZE_BUILD_WARPS + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * ZE_BUILD_WARPS;
+    const uint32_t my_slot = lane >> 3;                               // the slot a leader lane (lane % 8 == 0) serves
+    const bool leader = (lane & 7u) == 0 && my_slot < (uint32_t)ZE_BUILD_SLOTS;
+    for (size_t idx0 = warp_id * ZE_BUILD_SLOTS; idx0 < nframes; idx0 += nwarps * ZE_BUILD_SLOTS) {
         __syncwarp();
-        if (lane == 0) { fr->mode = ZM_RAW; fr->rle_byte = 0; fr->log = 0; fr->desc_len = 0; fr->est_bytes = size; }
-        __syncwarp();
-        if (size < ZE_HUF_MIN || size > ZE_BLOCK_MAX) continue;
-        const uint32_t* hist = P.hist + idx * 256;
-        // ---- the warp: present symbols (8 per lane), a cheap bound of the coded size, rank sort by (count, symbol) ----
-        uint32_t mine[8], npres = 0, maxs = 0;
-        float entropy = 0.f;                                          // order-0 entropy of the frame in bits: no prefix code does better
+        // ---- stage A (all lanes, slot by slot): histogram -> keys, entropy bound, sort ----
+        for (int q = 0; q < ZE_BUILD_SLOTS; ++q) {
+            ZencBuildWs& w = wsa[q];
+            const size_t idx = idx0 + q;
+            if (lane == 0) w.live = 0;
+            if (idx >= nframes) { __syncwarp(); continue; }
+            const uint32_t c = (uint32_t)(idx / nf); const int f = (int)(idx % nf);
+            uint64_t a0, b0; ze_frame_range(nf, P.stream_off + 5 * (size_t)c, P.stream_size ? P.stream_size + 5 * (size_t)c : nullptr, f, a0, b0);
+            const uint32_t size = (uint32_t)(b0 - a0);
+            ZencFrame* fr = P.frames + idx;
+            if (lane == 0) { fr->mode = ZM_RAW; fr->rle_byte = 0; fr->log = 0; fr->desc_len = 0; fr->est_bytes = size; }
+            __syncwarp();
+            if (size < ZE_HUF_MIN || size > ZE_BLOCK_MAX) continue;
+            const uint32_t* hist = P.hist + idx * 256;
+            uint32_t mine[8], npres = 0, maxs = 0;
+            float entropy = 0.f;                                      // order-0 entropy of the frame in bits: no prefix code does better
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t sym = lane * 8 + k, cnt = hist[sym];
-            mine[k] = cnt ? ((cnt << 8) | sym) : 0u;
-            if (cnt) { ++npres; maxs = sym; entropy += (float)cnt * log2f((float)size / (float)cnt); }
-        }
-        const uint32_t inc = warp_inclusive_scan(npres);
-        const uint32_t m = __shfl_sync(0xffffffffu, inc, 31);
-        maxs = __reduce_max_sync(0xffffffffu, maxs);
-#pragma unroll
-        for (int d = 16; d; d >>= 1) entropy += __shfl_xor_sync(0xffffffffu, entropy, d);
-        if (m == 1) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) if (mine[k]) { fr->mode = ZM_RLE; fr->rle_byte = mine[k] & 0xFF; }
-        }
-        if (m <= 1) continue;
-        // nothing to gain (nibble pairs, noise): even the entropy bound saves less than ~2 % -- leave the frame raw
-        if (entropy * 0.125f + 24.f >= (float)size * 0.98f) continue;
-        {
-            uint32_t pos = inc - npres;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) if (mine[k]) w.key[pos++] = mine[k];           // unsorted, compact
-        }
-        __syncwarp();
-        // bitonic sort of the 256-entry key array (absent symbols: 0xFFFFFFFF, they end up behind the m present ones): 36
-        // stages of 128 compare-exchanges, four per lane
-        for (uint32_t i = m + lane; i < 256; i += 32) w.key[i] = 0xFFFFFFFFu;
-        __syncwarp();
-        for (uint32_t k = 2; k <= 256; k <<= 1)
-            for (uint32_t j = k >> 1; j; j >>= 1) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint32_t x = lane + 32 * t;                 // pair index 0..127 -> the lower element of the pair
-                    const uint32_t i = ((x & ~(j - 1)) << 1) | (x & (j - 1)), l = i | j;
-                    const uint32_t a0 = w.key[i], b0 = w.key[l];
-                    const bool up = (i & k) == 0;
-                    if ((a0 > b0) == up) { w.key[i] = b0; w.key[l] = a0; }
-                }
-                __syncwarp();
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t sym = lane * 8 + k, cnt = hist[sym];
+                mine[k] = cnt ? ((cnt << 8) | sym) : 0u;
+                if (cnt) { ++npres; maxs = sym; entropy += (float)cnt * log2f((float)size / (float)cnt); }
             }
-        // ---- lane 0: Huffman tree by the two-queue method: leaves in key order, internal nodes are created in non-decreasing weight ----
-        if (lane == 0) {
+            const uint32_t inc = warp_inclusive_scan(npres);
+            const uint32_t m = __shfl_sync(0xffffffffu, inc, 31);
+            maxs = __reduce_max_sync(0xffffffffu, maxs);
+#pragma unroll
+            for (int d = 16; d; d >>= 1) entropy += __shfl_xor_sync(0xffffffffu, entropy, d);
+            if (m == 1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (mine[k]) { fr->mode = ZM_RLE; fr->rle_byte = mine[k] & 0xFF; }
+            }
+            if (m <= 1) continue;
+            // nothing to gain (nibble pairs, noise): even the entropy bound saves less than ~2 % -- leave the frame raw
+            if (entropy * 0.125f + 24.f >= (float)size * 0.98f) continue;
+            {
+                uint32_t pos = inc - npres;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (mine[k]) w.key[pos++] = mine[k];       // unsorted, compact
+            }
+            // bitonic sort of the 256-entry key array (absent symbols: 0xFFFFFFFF, they end up behind the m present ones): 36
+            // stages of 128 compare-exchanges, four per lane
+            for (uint32_t i = m + lane; i < 256; i += 32) w.key[i] = 0xFFFFFFFFu;
+            __syncwarp();
+            for (uint32_t k = 2; k <= 256; k <<= 1)
+                for (uint32_t j = k >> 1; j; j >>= 1) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t x = lane + 32 * t;             // pair index 0..127 -> the lower element of the pair
+                        const uint32_t i = ((x & ~(j - 1)) << 1) | (x & (j - 1)), l = i | j;
+                        const uint32_t ka = w.key[i], kb = w.key[l];
+                        const bool up = (i & k) == 0;
+                        if ((ka > kb) == up) { w.key[i] = kb; w.key[l] = ka; }
+                    }
+                    __syncwarp();
+                }
+            if (lane == 0) { w.m = m; w.maxs = maxs; w.size = size; w.live = 1; }
+            __syncwarp();
+        }
+        __syncwarp();
+        // ---- stage B (leaders, all slots at once): Huffman tree by the two-queue method -- leaves in key order, internal
+        //      nodes are created in non-decreasing weight ----
+        if (leader && wsa[my_slot].live) {
+            ZencBuildWs& w = wsa[my_slot];
+            const uint32_t m = w.m;
             constexpr uint32_t INF = 0xFFFFFFFFu;
             uint32_t li = 0, qi = 0, qn = 0, lw = w.key[0] >> 8, iw = INF;        // heads of the two queues stay in registers
             while (qn < m - 1) {
@@ -296,80 +322,97 @@ __global__ void __launch_bounds__(32 * ZE_BUILD_WARPS) k_zenc_build(ZencParams P
             w.depth[m - 2] = 0;                                       // the root is the last internal node
             for (int j = (int)m - 3; j >= 0; --j) w.depth[j] = (uint8_t)(w.depth[w.par[256 + j]] + 1);
         }
+        __syncwarp();
+        // ---- stage C (all lanes, slot by slot): code lengths per symbol, cut at ZE_LOG_MAX, Kraft sum ----
+        for (int q = 0; q < ZE_BUILD_SLOTS; ++q) {
+            ZencBuildWs& w = wsa[q];
+            if (!w.live) continue;
+            const uint32_t m = w.m;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) w.len[lane * 8 + k] = 0;
-        __syncwarp();
-        uint32_t maxlen = 0;
-        for (uint32_t i = lane; i < m; i += 32) { const uint32_t l = w.depth[w.par[i]] + 1u; w.len[w.key[i] & 0xFF] = (uint8_t)l; maxlen = max(maxlen, l); }
-        maxlen = __reduce_max_sync(0xffffffffu, maxlen);
-        __syncwarp();
-        if (maxlen > ZE_LOG_MAX) {
-            // length limit (rare: very skewed histograms): cut at ZE_LOG_MAX, then repair the Kraft sum -- lengthen the rarest
-            // symbols that still can be lengthened until the code fits, then give spare code space back to the most frequent ones
-            uint32_t ok = 1, kraft = 0, nfull = 0;
-            for (uint32_t i = lane; i < m; i += 32) { uint8_t& l = w.len[w.key[i] & 0xFF]; if (l > ZE_LOG_MAX) l = ZE_LOG_MAX; kraft += 1u << (ZE_LOG_MAX - l); nfull += l == ZE_LOG_MAX; }
-            kraft = __reduce_add_sync(0xffffffffu, kraft); nfull = __reduce_add_sync(0xffffffffu, nfull);       // lengths do not grow along the sorted order: the first nfull symbols are at the limit
+            for (int k = 0; k < 8; ++k) w.len[lane * 8 + k] = 0;
             __syncwarp();
-            if (lane == 0) {
-                const uint32_t full = 1u << ZE_LOG_MAX;
-                while (kraft > full)
-                    for (uint32_t i = nfull; i < m && kraft > full; ++i) { uint8_t& l = w.len[w.key[i] & 0xFF]; if (l < ZE_LOG_MAX) { kraft -= 1u << (ZE_LOG_MAX - l - 1); ++l; } }
-                for (int i = (int)m - 1; i >= 0 && kraft < full; --i) { uint8_t& l = w.len[w.key[i] & 0xFF]; while (l > 1 && kraft + (1u << (ZE_LOG_MAX - l)) <= full) { kraft += 1u << (ZE_LOG_MAX - l); --l; } }
-                ok = kraft == full;
+            uint32_t kraft = 0, nfull = 0, maxlen = 0;
+            for (uint32_t i = lane; i < m; i += 32) {
+                uint32_t l = w.depth[w.par[i]] + 1u;
+                maxlen = max(maxlen, l);
+                if (l > ZE_LOG_MAX) l = ZE_LOG_MAX;
+                w.len[w.key[i] & 0xFF] = (uint8_t)l; kraft += 1u << (ZE_LOG_MAX - l); nfull += l == ZE_LOG_MAX;
             }
-            ok = __shfl_sync(0xffffffffu, ok, 0);
+            kraft = __reduce_add_sync(0xffffffffu, kraft); nfull = __reduce_add_sync(0xffffffffu, nfull); maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+            if (lane == 0) { w.kraft = maxlen > ZE_LOG_MAX ? kraft : 0u; w.nfull = nfull; }      // kraft 0: no repair needed
             __syncwarp();
-            if (!ok) continue;                                        // cannot happen; raw is always valid
-            maxlen = 0;
-            for (uint32_t i = lane; i < m; i += 32) maxlen = max(maxlen, (uint32_t)w.len[w.key[i] & 0xFF]);
-            maxlen = __reduce_max_sync(0xffffffffu, maxlen);
         }
-        const uint32_t L = maxlen;
-        // ---- codes in the order of zstd's decoding table (HUF_readDTableX1): ascending weight = descending length, symbols
-        //      in natural order inside a weight; a symbol of weight wt owns 2^(wt-1) consecutive entries. Per lane: 8
-        //      consecutive symbols; first entry of each = entries of lighter symbols + entries of equal weight in front ----
-        uint32_t cntw[13];                                            // entries of weight wt among my 8 symbols
+        __syncwarp();
+        // ---- stage D (leaders): length limit (very skewed histograms) -- repair the Kraft sum: lengthen the rarest symbols that
+        //      still can be lengthened until the code fits (lengths do not grow along the sorted order: the first nfull symbols
+        //      are at the limit), then give spare code space back to the most frequent ones ----
+        if (leader && wsa[my_slot].live && wsa[my_slot].kraft) {
+            ZencBuildWs& w = wsa[my_slot];
+            const uint32_t m = w.m, full = 1u << ZE_LOG_MAX;
+            uint32_t kraft = w.kraft;
+            while (kraft > full)
+                for (uint32_t i = w.nfull; i < m && kraft > full; ++i) { uint8_t& l = w.len[w.key[i] & 0xFF]; if (l < ZE_LOG_MAX) { kraft -= 1u << (ZE_LOG_MAX - l - 1); ++l; } }
+            for (int i = (int)m - 1; i >= 0 && kraft < full; --i) { uint8_t& l = w.len[w.key[i] & 0xFF]; while (l > 1 && kraft + (1u << (ZE_LOG_MAX - l)) <= full) { kraft += 1u << (ZE_LOG_MAX - l); --l; } }
+            if (kraft != full) w.live = 0;                            // cannot happen; raw is always valid
+        }
+        __syncwarp();
+        // ---- stage E (all lanes, slot by slot): codes in the order of zstd's decoding table (HUF_readDTableX1): ascending weight
+        //      = descending length, symbols in natural order inside a weight; a symbol of weight wt owns 2^(wt-1) consecutive
+        //      entries. Per lane 8 consecutive symbols; first entry of each = entries of lighter symbols + entries of equal
+        //      weight in front. Then the weights of the tree description and how often each value occurs. ----
+        for (int q = 0; q < ZE_BUILD_SLOTS; ++q) {
+            ZencBuildWs& w = wsa[q];
+            if (!w.live) continue;
+            const size_t idx = idx0 + q;
+            ZencFrame* fr = P.frames + idx;
+            const uint32_t* hist = P.hist + idx * 256;
+            const uint32_t maxs = w.maxs;
+            uint32_t lens[8], L = 0;
 #pragma unroll
-        for (int k = 0; k < 13; ++k) cntw[k] = 0;
-        uint32_t lens[8];
+            for (int k = 0; k < 8; ++k) { lens[k] = w.len[lane * 8 + k]; L = max(L, lens[k]); }
+            L = __reduce_max_sync(0xffffffffu, L);
+            uint32_t cntw[13];                                        // entries of weight wt among my 8 symbols
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { lens[k] = w.len[lane * 8 + k]; if (lens[k]) { const uint32_t wt = L + 1 - lens[k]; for (int q = 1; q < 13; ++q) if ((uint32_t)q == wt) cntw[q] += 1u << (wt - 1); } }
-        uint32_t before[13], startw[13];                              // exclusive scan over the lanes, per weight; total per weight
-        uint32_t run = 0;
+            for (int k = 0; k < 13; ++k) cntw[k] = 0;
 #pragma unroll
-        for (int q = 1; q < 13; ++q) { const uint32_t i2 = warp_inclusive_scan(cntw[q]); before[q] = i2 - cntw[q]; startw[q] = run; run += __shfl_sync(0xffffffffu, i2, 31); }
-        unsigned long long bits = 0;
+            for (int k = 0; k < 8; ++k) if (lens[k]) { const uint32_t wt = L + 1 - lens[k]; for (int t = 1; t < 13; ++t) if ((uint32_t)t == wt) cntw[t] += 1u << (wt - 1); }
+            uint32_t before[13], startw[13];                          // exclusive scan over the lanes, per weight; total per weight
+            uint32_t run = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint16_t cw = 0;
-            if (lens[k]) {
-                const uint32_t wt = L + 1 - lens[k];
-                uint32_t e = 0;
+            for (int t = 1; t < 13; ++t) { const uint32_t i2 = warp_inclusive_scan(cntw[t]); before[t] = i2 - cntw[t]; startw[t] = run; run += __shfl_sync(0xffffffffu, i2, 31); }
+            unsigned long long bits = 0;
+            if (lane < 13) w.fse.cnt[lane] = 0;
+            __syncwarp();
+            uint32_t maxw = 0;
 #pragma unroll
-                for (int q = 1; q < 13; ++q) if ((uint32_t)q == wt) { e = startw[q] + before[q]; before[q] += 1u << (wt - 1); }
-                cw = (uint16_t)((lens[k] << 11) | (e >> (wt - 1)));
-                bits += (unsigned long long)hist[lane * 8 + k] * lens[k];
+            for (int k = 0; k < 8; ++k) {
+                uint16_t cw = 0;
+                const uint32_t wt = lens[k] ? L + 1 - lens[k] : 0u;
+                if (lens[k]) {
+                    uint32_t e = 0;
+#pragma unroll
+                    for (int t = 1; t < 13; ++t) if ((uint32_t)t == wt) { e = startw[t] + before[t]; before[t] += 1u << (wt - 1); }
+                    cw = (uint16_t)((lens[k] << 11) | (e >> (wt - 1)));
+                    bits += (unsigned long long)hist[lane * 8 + k] * lens[k];
+                }
+                fr->code[lane * 8 + k] = cw;
+                w.wts[lane * 8 + k] = (uint8_t)wt;
+                if (lane * 8 + k < maxs) { atomicAdd(&w.fse.cnt[wt], 1u); maxw = max(maxw, wt); }
             }
-            fr->code[lane * 8 + k] = cw;
-            w.wts[lane * 8 + k] = lens[k] ? (uint8_t)(L + 1 - lens[k]) : 0;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+            maxw = __reduce_max_sync(0xffffffffu, maxw);
+            if (lane == 0) { w.L = L; w.bits = bits; w.maxw = maxw; }
+            __syncwarp();
         }
-        bits += __shfl_xor_sync(0xffffffffu, bits, 16); bits += __shfl_xor_sync(0xffffffffu, bits, 8); bits += __shfl_xor_sync(0xffffffffu, bits, 4);
-        bits += __shfl_xor_sync(0xffffffffu, bits, 2); bits += __shfl_xor_sync(0xffffffffu, bits, 1);
         __syncwarp();
-        // ---- tree description = weights of symbols 0 .. maxsym-1 (the last one is implied): counted by the warp, coded by lane 0 ----
-        if (lane < 13) w.fse.cnt[lane] = 0;
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (lane * 8 + k < maxs) atomicAdd(&w.fse.cnt[lens[k] ? L + 1 - lens[k] : 0], 1u);
-        uint32_t maxw = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (lane * 8 + k < maxs && lens[k]) maxw = max(maxw, L + 1 - lens[k]);
-        maxw = __reduce_max_sync(0xffffffffu, maxw);
-        __syncwarp();
-        uint32_t dl = 0, have = 1;
-        if (lane == 0) {
-            const uint32_t maxsym = maxs;
-            dl = ze_fse_weights(w.wts, maxsym, maxw, w.fse);
+        // ---- stage F (leaders): tree description = weights of symbols 0 .. maxsym-1 (the last one is implied), FSE-compressed
+        //      (left in the scratch, copied out by the warp) or direct ----
+        if (leader && wsa[my_slot].live) {
+            ZencBuildWs& w = wsa[my_slot];
+            ZencFrame* fr = P.frames + idx0 + my_slot;
+            const uint32_t maxsym = w.maxs;
+            uint32_t dl = ze_fse_weights(w.wts, maxsym, w.maxw, w.fse), have = 1;
             if (dl && dl < 128 && (maxsym > 128 || dl < (maxsym + 1) / 2)) fr->desc[0] = (uint8_t)dl;
             else if (maxsym <= 128) {                                 // direct: 4 bits per weight, first weight in the high nibble
                 fr->desc[0] = (uint8_t)(127 + maxsym);
@@ -377,16 +420,22 @@ __global__ void __launch_bounds__(32 * ZE_BUILD_WARPS) k_zenc_build(ZencParams P
                 for (uint32_t i = 0; i < dl; ++i) fr->desc[1 + i] = (uint8_t)((w.wts[2 * i] << 4) | (2 * i + 1 < maxsym ? w.wts[2 * i + 1] : 0));
                 dl |= 0x80000000u;                                    // already written
             } else have = 0;                                          // no representation: raw
+            w.dl = dl; w.have = have;
         }
-        dl = __shfl_sync(0xffffffffu, dl, 0); have = __shfl_sync(0xffffffffu, have, 0);
         __syncwarp();
-        if (have && !(dl & 0x80000000u)) for (uint32_t i = lane; i < dl; i += 32) fr->desc[1 + i] = (uint8_t)(w.fse.out[i >> 2] >> (8 * (i & 3)));
-        dl &= 0x7FFFFFFFu;
-        if (lane == 0) {
-            if (have) {
-                fr->desc_len = 1 + dl; fr->log = L; fr->est_bytes = (uint32_t)((bits + 7) >> 3);
+        // ---- stage G (all lanes): the description's bytes, the verdict ----
+        for (int q = 0; q < ZE_BUILD_SLOTS; ++q) {
+            ZencBuildWs& w = wsa[q];
+            if (!w.live || !w.have) continue;
+            ZencFrame* fr = P.frames + idx0 + q;
+            uint32_t dl = w.dl;
+            if (!(dl & 0x80000000u)) for (uint32_t i = lane; i < dl; i += 32) fr->desc[1 + i] = (uint8_t)(w.fse.out[i >> 2] >> (8 * (i & 3)));
+            dl &= 0x7FFFFFFFu;
+            if (lane == 0) {
+                const uint32_t est = (uint32_t)((w.bits + 7) >> 3);
+                fr->desc_len = 1 + dl; fr->log = w.L; fr->est_bytes = est;
                 // worth it only if the literals section beats a raw block (ZSTD_minGain-like margin)
-                if (fr->desc_len + fr->est_bytes + 16 + (size >> 6) < size) fr->mode = ZM_HUF;
+                if (1 + dl + est + 16 + (w.size >> 6) < w.size) fr->mode = ZM_HUF;
             }
         }
     }
@@ -467,13 +516,14 @@ __global__ void __launch_bounds__(ZE_NT) k_zenc_emit(ZencParams P)
     const int nf = codec_frames(P.codec);
     for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) {
         const uint64_t* so = P.stream_off + 5 * (size_t)c;
+        const uint32_t* ssz = P.stream_size ? P.stream_size + 5 * (size_t)c : nullptr;
         uint8_t* slot = P.slots + P.slot_off[c];
         const uint32_t cap = (uint32_t)(P.slot_off[c + 1] - P.slot_off[c]);
         __syncthreads();
         if (tid == 0) { ws.pos = 0; ws.fail = 0; }
         __syncthreads();
         for (int f = 0; f < nf; ++f) {
-            uint64_t a, b; ze_frame_range(nf, so, f, a, b);
+            uint64_t a, b; ze_frame_range(nf, so, ssz, f, a, b);
             const uint32_t size = (uint32_t)(b - a);
             const uint8_t* src = P.streams + a;
             const ZencFrame* fr = P.frames + (size_t)c * nf + f;

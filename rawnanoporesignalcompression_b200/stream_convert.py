@@ -34,7 +34,7 @@ import pyarrow.ipc as ipc
 
 from . import pod5_container as pc
 
-DEFAULT_GROUP_SAMPLES = 48 << 20          # ~96 MiB of int16 per group
+DEFAULT_GROUP_SAMPLES = 32 << 20          # ~64 MiB of int16 per group
 
 
 class _SubFile(io.RawIOBase):
@@ -149,7 +149,7 @@ def _gather_group(batches: List[pa.RecordBatch], ext: str) -> Group:
         col = b.column("signal")
         vals = col.values.to_numpy(zero_copy_only=False)
         o = col.offsets.to_numpy(zero_copy_only=False)
-        parts.append(vals[int(o[0]) - col.values.offset if False else int(o[0]) : int(o[-1])])
+        parts.append(vals[int(o[0]) : int(o[-1])])
     flat = np.concatenate(parts).astype(np.int16, copy=False) if parts else np.zeros(0, np.int16)
     return Group(batches, rows, None, None, flat, n)
 
@@ -165,6 +165,7 @@ class StreamConverter:
         self.samples = 0
         self.groups = 0
         self._torch = None
+        self.seconds = {"read": 0.0, "codec": 0.0, "write": 0.0}      # busy time per stage (the stages overlap)
 
     # ---- codec stage ----------------------------------------------------------------------------------------
     def _transcode_on_device(self, g: Group, in_codec: str):
@@ -265,14 +266,25 @@ class StreamConverter:
             out_schema = pa.schema([in_schema.field("read_id"), sig_field, in_schema.field("samples")], metadata=in_schema.metadata)
             nb = reader.num_record_batches
 
+            import time as _t
+
             def read_group(first: int):
+                t0 = _t.perf_counter()
                 batches, samples, i = [], 0, first
                 while i < nb and (not batches or samples < self.group_samples):
                     b = reader.get_batch(i)
                     batches.append(b)
                     samples += int(np.asarray(b.column("samples").to_numpy(zero_copy_only=False), dtype=np.int64).sum())
                     i += 1
-                return _gather_group(batches, in_ext), i
+                g = _gather_group(batches, in_ext)
+                self.seconds["read"] += _t.perf_counter() - t0
+                return g, i
+
+            def write_group(bs):
+                t0 = _t.perf_counter()
+                for b in bs:
+                    writer.write_batch(b)
+                self.seconds["write"] += _t.perf_counter() - t0
 
             if os.path.exists(out_path):
                 os.remove(out_path)                                       # copy.cpp:113-120
@@ -287,11 +299,13 @@ class StreamConverter:
                 while nxt is not None:
                     g, i = nxt.result()
                     nxt = pool.submit(read_group, i) if i < nb else None      # group k+1 is read while group k is in the codec
+                    t0 = _t.perf_counter()
                     kind, payload = self._codec_stage(g, in_ext)
                     out_b = self._out_batches(g, kind, payload, out_schema)
+                    self.seconds["codec"] += _t.perf_counter() - t0
                     if pending_write is not None:
                         pending_write.result()                                 # group k-1 has left for the file
-                    pending_write = pool.submit(lambda bs=out_b: [writer.write_batch(b) for b in bs])
+                    pending_write = pool.submit(write_group, out_b)
                 if pending_write is not None:
                     pending_write.result()
                 writer.close()
@@ -327,7 +341,44 @@ def convert_streaming(in_path: str, out_path: str, comp: str, variant: str = "C5
     if codec is None:
         from .codec import default_codec
         codec = default_codec()
-    return StreamConverter(codec, comp, variant, group_samples, entropy).convert(in_path, out_path)
+    sc = StreamConverter(codec, comp, variant, group_samples, entropy)
+    res = sc.convert(in_path, out_path)
+    if os.environ.get("RNSC_STREAM_STATS"):
+        import sys
+        print(f"[stream] groups {sc.groups}, busy seconds per stage (overlapped): " + ", ".join(f"{k} {v:.2f}" for k, v in sc.seconds.items()), file=sys.stderr)
+    return res
+
+
+def signal_checksum(path: str, variant: str = "C5", codec=None, group_samples: int = DEFAULT_GROUP_SAMPLES) -> Tuple[int, int, int]:
+    """(crc32 of every decoded sample in file order, samples, signal rows): the signal of a file of any size, decoded group by
+    group in bounded memory -- two files hold the same signal iff the triples agree (check_pod5_files_equal.py:60-64 at scale)."""
+    import zlib
+    if codec is None:
+        from .codec import default_codec
+        codec = default_codec()
+    crc, total, rows = 0, 0, 0
+    with open(path, "rb") as fin:
+        footer, _ = read_footer(fin)
+        se = {e.content_type: e for e in footer.contents}[pc.CONTENT_SIGNAL]
+        reader = ipc.open_file(pa.PythonFile(_SubFile(fin, se.offset, se.length), mode="r"))
+        ext = pc.signal_extension_name(reader.schema)
+        in_codec = "VBZ" if ext == pc.EXT_VBZ else (variant if ext == pc.EXT_PGNANO else None)
+        i, nb = 0, reader.num_record_batches
+        while i < nb:
+            batches, samples = [], 0
+            while i < nb and (not batches or samples < group_samples):
+                b = reader.get_batch(i); batches.append(b); i += 1
+                samples += int(np.asarray(b.column("samples").to_numpy(zero_copy_only=False), dtype=np.int64).sum())
+            g = _gather_group(batches, ext)
+            if in_codec is not None:
+                flat, _, st = codec.decompress_flat(g.comp, g.comp_off, g.n, in_codec)
+                if st.any():
+                    raise pc.Pod5Error("decode status in signal_checksum")
+            else:
+                flat = g.samples_flat
+            crc = zlib.crc32(memoryview(np.ascontiguousarray(flat)).cast("B"), crc)
+            total += int(flat.size); rows += int(g.n.size)
+    return crc, total, rows
 
 
 def write_synthetic_pod5(path: str, codec, n_reads: int, seed: int, model, codec_name: str = "VBZ", template: Optional[str] = None,
