@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
     RNSC_DYN_SMEM(smem);
     FastWs<NTH>* ws = (FastWs<NTH>*)smem;
     KeyLut* lut = (KeyLut*)(smem + ((sizeof(FastWs<NTH>) + 15) & ~(size_t)15));
-    uint8_t* region = (uint8_t*)lut + unpack2_lut_bytes(P.codec);
+    uint8_t* region = (uint8_t*)lut + unpack2_lut_bytes(P.codec, NTH);
     const int tid = threadIdx.x;
     if (tid == 0) { mbar_init(&ws->mbar, 1); ws->stash_tag = FAST_NONE; const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
     unpack2_init<NTH>(P.codec, lut);

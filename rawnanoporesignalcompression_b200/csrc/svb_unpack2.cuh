@@ -20,6 +20,9 @@
 namespace rnsc {
 
 constexpr int U2_SPT = 16;
+// (Tried: 32 samples per thread and tile, decoded as two 16-sample halves, to pay a tile's scans and barrier once per 32
+// samples -- slower: the halves are one dependent chain per thread and the last tile gets coarser; 20k-read C5 decode 508 ->
+// 491 GB/s. Tried: warps whose samples all have key 0 or lie past the end skip the arithmetic -- slower too, 508 -> 501.)
 
 // C4/C5: what one key byte (four 2-bit codes) says about its four samples. x = byte-permute selectors that pull the
 // samples' units out of the next four nibbles (low half) / bytes (high half) of the stream windows, a zero byte for
@@ -27,6 +30,12 @@ constexpr int U2_SPT = 16;
 // window << 8 | selectors of the samples' large values (bytes of the thread's four-byte Llow / Lhigh windows, counted from
 // the group's first one) << 16; z, w = the class offsets (C5: 1 / 17 / 273) of samples 0,1 and 2,3 as 16-bit lanes.
 struct alignas(16) KeyLut { uint32_t x, y, z, w; };
+// The table is read with one 128-bit shared load per four samples, eight lanes per wavefront, and an entry covers four of
+// the 32 banks: lanes whose key bytes differ collide unless their entries lie in different bank groups (measured: 2.7
+// wavefronts per quarter warp with one copy, a third of all shared-memory traffic of the decode). Where a CTA has the
+// shared memory for it the table is therefore REPLICATED: lane l reads copy l mod R, entry i of copy r sits in slot i * R + r,
+// so that the lanes of a quarter warp share a bank group only with the lanes of their own copy (R = 8: never).
+__host__ __device__ constexpr int key_lut_copies(int nth) { return nth >= 1024 ? 4 : (nth >= 512 ? 2 : 1); }
 
 template <int CODEC>
 __device__ inline KeyLut make_key_lut(uint32_t kbyte)
@@ -77,6 +86,16 @@ __device__ __forceinline__ void load_bits64(saddr_t p, uint32_t bit, uint32_t& l
     lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
 }
 
+// two 16-bit lanes added without a carry between them (VIADD.16x2)
+__device__ __forceinline__ uint32_t add16x2(uint32_t a, uint32_t b)
+{
+#ifdef RNSC_EMUL
+    return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16);
+#else
+    uint32_t r; asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+#endif
+}
+
 // sum += zigzag^-1(z) in 32-bit arithmetic (the low 16 bits are what counts): z even -> z/2, z odd -> -(z/2) - 1 = z/2 - z
 __device__ __forceinline__ uint32_t zz_dec(uint32_t z) { return (z >> 1) - (z & 1u) * z; }
 
@@ -95,7 +114,9 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
     if (tid == 0) ws->err = 0;
     const uint8_t *s1 = base + v[1].off, *s2 = base + v[2].off, *s3 = base + v[3].off, *s4 = base + v[4].off;
     const saddr_t a0 = to_saddr(base + v[0].off), a1 = to_saddr(s1), a2 = to_saddr(s2), a3 = to_saddr(s3), a4 = to_saddr(s4);
-    const uint32_t l1 = v[1].len, l2 = v[2].len, l3 = v[3].len, l4 = v[4].len;
+    const saddr_t vs = to_saddr(v);                                    // the views: {off, len} x 5
+    constexpr int LR = key_lut_copies(NTH);
+    const KeyLut* const lutr = lut + (tid & (LR - 1));                 // this lane's copy of the key-byte table
     const uint32_t ph = (uint32_t)(((uintptr_t)out >> 1) & 7);        // samples past a 16-byte boundary
     int16_t* outa = out - ph;                                          // 16-byte aligned; virtual sample vi <-> outa[vi]
     const uint32_t nv = n + ph;
@@ -171,13 +192,18 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
         uint32_t p1, p2;
         if (ONE_STREAM) { p1 = run1 + exA; p2 = 0; run1 += totA; }
         else { p1 = run1 + (exA & 0xFFFFu); p2 = run2 + (exA >> 16); run1 += totA & 0xFFFFu; run2 += totA >> 16; }
-        // ---- one bounds check per thread instead of one per load (over-reads stay inside the padded buffers) ----
+        // ---- one bounds check per TILE, the same in every thread: run1..3 now count the units up to the end of this tile,
+        //      and a thread's reads end at or before them (over-reads stay inside the padded buffers). The stream lengths
+        //      are re-read from shared memory here instead of living in registers across the tile ----
         bool ok;
-        if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) ok = p1 + c1 <= l1;
-        else if (CODEC == RNSC_C2) ok = p1 + c1 <= l1 && p2 + c2 <= l2;
-        else if (CODEC == RNSC_C3) ok = p1 + c1 <= l1 && p2 + c2 <= l2 && p2 + c2 <= l3;
-        else if (CODEC == RNSC_VBZ0) ok = p1 + c1 <= 2 * l1;
-        else ok = p1 + c1 <= 2 * l1 && p2 + c2 <= l2 && p3 + c3 <= l3 && p3 + c3 <= l4;
+        {
+            const uint32_t l1 = ldw(vs + 12), l2 = ldw(vs + 20), l3 = ldw(vs + 28), l4 = ldw(vs + 36);
+            if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) ok = run1 <= l1;
+            else if (CODEC == RNSC_C2) ok = run1 <= l1 && run2 <= l2;
+            else if (CODEC == RNSC_C3) ok = run1 <= l1 && run2 <= l2 && run2 <= l3;
+            else if (CODEC == RNSC_VBZ0) ok = run1 <= 2 * l1;
+            else ok = run1 <= 2 * l1 && run2 <= l2 && run3 <= l3 && run3 <= l4;
+        }
         if (!ok) { oob = true; kb = 0; m1 = m2 = m3 = 0; c3 = 0; }
         // ---- gather, zigzag^-1, thread-local running sum ----
         uint32_t val[S]; uint32_t acc = 0;
@@ -204,7 +230,7 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
 #pragma unroll
                 for (int g = 0; g < S / 4; ++g) {
                     const int h = g >> 1;
-                    const KeyLut e = lut[__byte_perm(kb, 0u, 0x4440u | (uint32_t)g)];
+                    const KeyLut e = lutr[__byte_perm(kb, 0u, 0x4440u | (uint32_t)g) * (uint32_t)LR];
                     uint32_t x = sw[h] & 0xFFFFu;                                  // next four nibbles -> four bytes
                     x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu;
                     const uint32_t sel3 = (e.y >> 16) + r3x;                       // selectors stay below 8 (no large value: 4 + at most 3 consumed)
@@ -284,6 +310,10 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
         }
         // ---- delta^-1: CTA scan of the per-thread sums (mod 2^16, upper half of word B); its lower half and word A scan
         //      the large-value and unit counts of the next tile ----
+        // the running sums leave as 16-bit lanes, packed in pairs BEFORE the barrier (half the registers live across it)
+        uint32_t w[S / 2];
+#pragma unroll
+        for (int q = 0; q < S / 2; ++q) w[q] = __byte_perm(val[2 * q], val[2 * q + 1], 0x5410);
         uint32_t exB, totB;
         {
             uint32_t n1, n2, n3, q1, q2, q3;
@@ -293,20 +323,21 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
         const uint32_t base = carry + (exB >> 16);
         carry += totB >> 16;
         if (WIN) { p3 = run3 + (exB & 0xFFFFu); run3 += totB & 0xFFFFu; }
-        if (cnt == S) {
-            uint32_t w[S / 2];
+        const uint32_t base2 = __byte_perm(base, 0u, 0x1010);            // the carry-in in both lanes
 #pragma unroll
-            for (int q = 0; q < S / 2; ++q) w[q] = __byte_perm(base + val[2 * q], base + val[2 * q + 1], 0x5410);
+        for (int q = 0; q < S / 2; ++q) w[q] = add16x2(w[q], base2);
+        if (cnt == S) {
             V16* dst = (V16*)(outa + v0);
             dst[0] = V16{w[0], w[1], w[2], w[3]};
             dst[1] = V16{w[4], w[5], w[6], w[7]};
         } else if (cnt) {
 #pragma unroll
-            for (int j = 0; j < S; ++j) if ((uint32_t)j >= jlo && (uint32_t)j < jlo + cnt) outa[v0 + j] = (int16_t)(uint16_t)(base + val[j]);
+            for (int j = 0; j < S; ++j) if ((uint32_t)j >= jlo && (uint32_t)j < jlo + cnt) outa[v0 + j] = (int16_t)(uint16_t)(w[j >> 1] >> (16 * (j & 1)));
         }
     }
     // ---- the reference's "Remaining data at end of signal buffer" test (A.8) + out-of-bounds guard ----
     bool rem;
+    const uint32_t l1 = v[1].len, l2 = v[2].len, l3 = v[3].len, l4 = v[4].len;
     if (CODEC == RNSC_VBZ || CODEC == RNSC_C1) rem = run1 != l1;
     else if (CODEC == RNSC_VBZ0) rem = ((run1 + 1) >> 1) != l1;
     else if (CODEC == RNSC_C2) rem = run2 != l2;
@@ -318,14 +349,15 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
 }
 
 // Shared memory the key-byte table of a codec needs in front of the region (only C4 and C5 have one).
-__host__ __device__ inline uint32_t unpack2_lut_bytes(int codec) { return (codec == RNSC_C4 || codec == RNSC_C5) ? 256u * (uint32_t)sizeof(KeyLut) : 0u; }
+__host__ __device__ inline uint32_t unpack2_lut_bytes(int codec, int nth) { return (codec == RNSC_C4 || codec == RNSC_C5) ? 256u * (uint32_t)sizeof(KeyLut) * (uint32_t)key_lut_copies(nth) : 0u; }
 
-// Once per CTA, before the first svb_unpack2; followed by a barrier at the caller. `lut` = unpack2_lut_bytes(codec) bytes.
+// Once per CTA, before the first svb_unpack2; followed by a barrier at the caller. `lut` = unpack2_lut_bytes(codec, NTH) bytes.
 template <int NTH>
 __device__ inline void unpack2_init(int codec, KeyLut* lut)
 {
     if (codec != RNSC_C4 && codec != RNSC_C5) return;
-    for (uint32_t i = threadIdx.x; i < 256; i += NTH) lut[i] = codec == RNSC_C5 ? make_key_lut<RNSC_C5>(i) : make_key_lut<RNSC_C4>(i);
+    constexpr uint32_t LR = key_lut_copies(NTH);
+    for (uint32_t i = threadIdx.x; i < 256 * LR; i += NTH) lut[i] = codec == RNSC_C5 ? make_key_lut<RNSC_C5>(i / LR) : make_key_lut<RNSC_C4>(i / LR);
 }
 
 template <int NTH>
