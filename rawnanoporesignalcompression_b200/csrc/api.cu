@@ -151,6 +151,7 @@ struct rnsc_ctx {
     DevBuf d_zhist, d_zframes, d_zslots, d_zslot_sz, d_zslot_off, d_zout_sz;   // GPU entropy stage of the encoders (zstd_encode.cuh)
     int entropy_stage = 0;                    // rnsc_compress_batch: 0 = host libzstd level 1 (byte-identical to the reference), 1 = GPU entropy stage
     bool profiling = false;
+    uint32_t prof_warp = 0;                   // RNSC_PROF_WARP (tuning): which warp, counted from the end, times the phases
     uint32_t cost_bit = 1, cost_sym = 12;   // planner's cost model of the Huffman stage (plan.cuh); RNSC_COST_BIT / RNSC_COST_SYM override (tuning)
     Lane lane[2];
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -224,6 +225,7 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     // streams and fill SMs as class B CTAs retire. Join before returning to the caller's stream.
     FastParams fp;
     fp.comp = d_comp; fp.comp_off = d_comp_off; fp.n = d_n; fp.sample_off = d_sample_off; fp.samples = d_samples; fp.status = d_status; fp.codec = codec;
+    fp.prof_warp = c->prof_warp;
     fp.plans = (const ChunkPlan*)c->d_plans.p; fp.seq_pool = (const uint32_t*)c->d_seqpool.p; fp.nchunks = (uint32_t)nchunks;
     // match resolver scratch in global memory: one origin word per matched byte of a chunk whose origin words do not fit the
     // dead bitstream area of its staged bytes. ~400 MB per context, so it exists only where sequence-heavy frames are
@@ -360,6 +362,7 @@ rnsc_ctx* rnsc_create(int device)
     }
     unsigned hc = std::thread::hardware_concurrency();
     c->host_threads = hc ? (int)hc : 1;
+    if (const char* e = getenv("RNSC_PROF_WARP")) c->prof_warp = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("RNSC_COST_BIT")) c->cost_bit = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("RNSC_COST_SYM")) c->cost_sym = (uint32_t)strtoul(e, nullptr, 10);
     if (c->cost_bit + c->cost_sym == 0) c->cost_bit = 1;

@@ -16,6 +16,10 @@
 
 namespace rnsc {
 
+// (Tried: symbol slots in GLOBAL memory -- an L2-resident scratch row per slot word, the whole sub-sequence decoded once and
+// the second pass a copy -- for the chunks that leave little shared memory: the copy back is bound by the SM's outstanding
+// L1 misses, ~3 k cycles per round trip of 12 words per thread with every warp asking at once, 6 k cycles per chunk against
+// the 8 k of decoding the symbols again; no gain, 20k-read C5 decode 508 -> 501 GB/s.)
 // (Tried: the Huffman stage as a __noinline__ function of its own, to take its registers out of the chunk loop's
 // allocation -- no spills, but 3 % slower overall on the B200: 483.7 vs 500.6 GB/s on the 20k-read C5 set.)
 #ifndef RNSC_NOINLINE
@@ -33,6 +37,7 @@ struct FastParams {
     uint32_t* origin; unsigned long long origin_stride;   // per-CTA global scratch (words) of the match resolver
     unsigned long long* span;    // optional (same switch): per CTA {start, end in ns, chunks decoded}
     unsigned long long* prof;    // optional (rnsc_set_profiling): 8 phase cycle counters of this size class, summed over CTAs
+    uint32_t prof_warp;          // phases are timed by the first thread of this warp counted from the end (0 = thread 0 keeps the time)
 };
 
 __device__ __forceinline__ unsigned long long global_ns()
@@ -47,9 +52,9 @@ __device__ __forceinline__ unsigned long long global_ns()
 // Phase timing for tuning: thread 0 of every CTA adds the cycles since the previous mark to prof[phase].
 enum { PH_STAGE = 0, PH_HUF1 = 1, PH_HUFSCAN = 2, PH_HUF2 = 3, PH_SEQ = 4, PH_UNPACK = 5, PH_OTHER = 6, PH_CHUNKS = 7 };
 struct PhaseClock {
-    unsigned long long* prof; long long t;
-    __device__ __forceinline__ void start(unsigned long long* p) { prof = p; if (prof && threadIdx.x == 0) t = clock64(); }
-    __device__ __forceinline__ void mark(int phase) { if (prof && threadIdx.x == 0) { const long long n = clock64(); atomicAdd(prof + phase, (unsigned long long)(n - t)); t = n; } }
+    unsigned long long* prof; long long t; uint32_t who;      // who: the thread that keeps the time (0; tuning: the first thread of warp RNSC_PROF_WARP from the end)
+    __device__ __forceinline__ void start(unsigned long long* p, uint32_t w) { prof = p; who = w; if (prof && threadIdx.x == who) t = clock64(); }
+    __device__ __forceinline__ void mark(int phase) { if (prof && threadIdx.x == who) { const long long n = clock64(); atomicAdd(prof + phase, (unsigned long long)(n - t)); t = n; } }
 };
 
 template <int NTH>

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
     unpack2_init<NTH>(P.codec, lut);
     __syncthreads();
     uint32_t parity = 0;
-    PhaseClock pc; pc.start(P.prof);
+    PhaseClock pc; pc.start(P.prof, P.prof_warp ? (uint32_t)NTH - 32u * min(P.prof_warp, (uint32_t)NTH / 32u) : 0u);
     const unsigned long long gt0 = (P.span && tid == 0) ? global_ns() : 0ull;      // profiling: this CTA's life span and chunk count
     uint32_t nch = 0;
     for (;;) {
