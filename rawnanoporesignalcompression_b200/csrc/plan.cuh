@@ -106,14 +106,144 @@ struct PlanParams {
 // written, so they share the weights' bytes: a smaller scratch = more planner CTAs per SM.
 struct PlanScratch {
     union { uint8_t weights[256]; struct { int16_t norm[64]; uint16_t next16[64]; }; };
-    uint32_t fse_w[64]; uint32_t rank_start[16]; uint32_t rank_cnt[16]; int huf_log;
+    uint32_t fse_w[64];
+    // stage: the bytes of a Huffman tree description (<= 127) as words, word 0 = a zero word below them, two more behind them
+    // (plan_read_weights); dead before the weight counts are written
+    union { struct { uint32_t rank_start[16]; uint32_t rank_cnt[16]; int huf_log; }; uint32_t stage[35]; };
 };
-static_assert(sizeof(PlanScratch) == 644, "PlanScratch layout");
+static_assert(sizeof(PlanScratch) == 652, "PlanScratch layout");      // 163 words: odd
 
 __host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 __host__ __device__ inline uint32_t huf_tab_bytes(uint32_t log) { return align16(2u << log); }
 __host__ __device__ inline uint32_t huf_skip_bytes(uint32_t log) { return align16(1u << log); }
 __host__ __device__ inline uint32_t seq_meta_bytes(uint32_t nseq) { return align16((nseq + 1) * 8); }
+
+// The planner's reader of a Huffman tree description (RFC 8878 4.2.1): same results as huf_read_weights (zstd_decode.cuh, kept
+// by the general decoder) -- weights[0 .. nw), the symbol count per weight in rank_cnt, the table log in huf_log, bytes
+// consumed (0 = error) -- at a third of the instructions and without dependent global loads: the description (<= 127 bytes)
+// is copied to the thread's shared scratch first (independent loads), the FSE header and the backward bitstream are read
+// from there with two shared loads and a funnel shift per field, and the per-weight counts and the weight total are kept
+// while the weights are decoded instead of in a second pass. Single exit; every lane of the warp calls it (size = 0 to skip).
+__device__ __forceinline__ uint32_t stage_bits(const uint32_t* stage, uint32_t bit)      // 32 bits from bit `bit` of the staged bytes (word 1 = byte 0)
+{
+    const uint32_t wi = 1u + (bit >> 5);
+    return __funnelshift_r(stage[wi], stage[wi + 1], bit);
+}
+__device__ inline uint32_t plan_read_weights(PlanScratch* sc, const uint8_t* src, uint32_t size, int* nw_out)
+{
+    uint8_t* w = sc->weights; uint32_t nw = 0;
+    bool ok = size >= 1;
+    const uint32_t hb = ok ? ldg8(src) : 0;
+    const bool direct = hb >= 128;
+    uint32_t used = 0;
+    if (ok && direct) { nw = hb - 127; used = 1 + (nw + 1) / 2; if (used > size) ok = false; }
+    if (ok && !direct) { used = 1 + hb; if (used > size || hb < 1) ok = false; }
+    const uint32_t dbytes = ok ? used - 1 : 0;                        // <= 127
+    {
+        const uint32_t nwords = (dbytes + 3) >> 2;
+        for (uint32_t i = 0; i < nwords; ++i) {
+            uint32_t v = gbits32(src + 1, 32 * i);
+            if (4 * i + 4 > dbytes) v &= 0xFFFFFFFFu >> (8 * (4 * i + 4 - dbytes));      // bits past the description read as zero
+            sc->stage[1 + i] = v;
+        }
+        sc->stage[0] = 0; sc->stage[1 + nwords] = 0; sc->stage[2 + nwords] = 0;
+    }
+    unsigned long long c_lo = 0, c_hi = 0;                            // symbols per weight, 8-bit fields (weights 0-7, 8-15): at most 255 weights are listed
+    uint32_t total = 0; bool big = false;
+    auto tally = [&](uint32_t wi) {
+        if (wi > HUF_LOG_MAX) { big = true; wi = 0; }
+        total += (1u << wi) >> 1;
+        const unsigned long long one = 1ull << ((wi & 7u) * 8u);
+        if (wi & 8u) c_hi += one; else c_lo += one;
+    };
+    // ---- direct representation: one 4-bit weight per symbol, first weight in the high nibble ----
+    {
+        const uint32_t lim = (ok && direct) ? nw : 0;
+        for (uint32_t i = 0; i < lim; ++i) { const uint32_t by = (sc->stage[1 + (i >> 3)] >> (8 * ((i >> 1) & 3))) & 0xFFu, wi = (i & 1) ? (by & 15u) : (by >> 4); w[i] = (uint8_t)wi; tally(wi); }
+    }
+    // ---- FSE-compressed weights: normalised counts (FSE_readNCount, <= 13 symbols, accuracy log <= 6) ----
+    int tl = 0, ns = 0; uint32_t h = 0;
+    if (ok && !direct) {
+        const uint32_t tbits = 8 * hb;
+        uint32_t bp = 4;
+        tl = (int)(stage_bits(sc->stage, 0) & 15u) + 5;
+        bool bad = tl > 6;
+        int remaining = (1 << tl) + 1, threshold = 1 << tl, nb = tl + 1, sym = 0; bool prev0 = false;
+        while (!bad && remaining > 1 && sym <= 12) {
+            if (prev0) {
+                int n0 = sym;
+                for (;;) { const uint32_t r = bp < tbits ? stage_bits(sc->stage, bp) & 3u : 0u; bp += 2; n0 += (int)r; if (r != 3 || n0 > 13) break; }
+                if (n0 > 13) { bad = true; break; }
+                while (sym < n0) sc->norm[sym++] = 0;
+                if (sym > 12) break;
+            }
+            const int mx = (2 * threshold - 1) - remaining;
+            const uint32_t v = bp < tbits ? stage_bits(sc->stage, bp) : 0u;
+            int count = (int)(v & ((1u << (nb - 1)) - 1u));
+            if (count < mx) bp += nb - 1;
+            else { count = (int)(v & ((1u << nb) - 1u)); if (count >= threshold) count -= mx; bp += nb; }
+            count--;
+            remaining -= count < 0 ? -count : count;
+            sc->norm[sym++] = (int16_t)count;
+            prev0 = count == 0;
+            while (remaining < threshold) { nb--; threshold >>= 1; }
+        }
+        h = (bp + 7) >> 3;
+        if (bad || remaining != 1 || h > hb) ok = false;
+        ns = sym;
+    }
+    warp_converge<true>();
+    if (ok && !direct) fse_build(sc->fse_w, sc->norm, ns, tl, sc->next16);
+    warp_converge<true>();
+    // ---- two interleaved FSE states over the backward bitstream, bytes [h, hb) of the description ----
+    if (ok && !direct) {
+        const uint32_t last = (sc->stage[1 + ((hb - 1) >> 2)] >> (8 * ((hb - 1) & 3))) & 0xFFu;
+        if (hb == h || last == 0) ok = false;
+        else {
+            const int start = 8 * (int)h;
+            int pos = 8 * (int)hb - (8 - highbit32(last));            // bit address of the end mark = end of the payload
+            // n bits ending at pos (n <= 6); bits below `start` read as zero
+            auto rd = [&](uint32_t n) -> uint32_t {
+                pos -= (int)n;
+                const uint32_t m = (1u << n) - 1u;
+                if (pos >= start) return stage_bits(sc->stage, (uint32_t)pos) & m;
+                const int avail = (int)n - (start - pos);
+                return avail <= 0 ? 0u : ((stage_bits(sc->stage, (uint32_t)start) & ((1u << avail) - 1u)) << (start - pos)) & m;
+            };
+            uint32_t s1 = rd((uint32_t)tl), s2 = rd((uint32_t)tl);
+            for (;;) {
+                if (nw >= 254) { ok = false; break; }
+                uint32_t e = sc->fse_w[s1], wi = e & 0xFFu; w[nw++] = (uint8_t)wi; tally(wi);
+                s1 = (e >> 16) + rd((e >> 8) & 0xFFu);
+                if (pos < start) { if (nw >= 255) ok = false; else { wi = sc->fse_w[s2] & 0xFFu; w[nw++] = (uint8_t)wi; tally(wi); } break; }
+                if (nw >= 254) { ok = false; break; }
+                e = sc->fse_w[s2]; wi = e & 0xFFu; w[nw++] = (uint8_t)wi; tally(wi);
+                s2 = (e >> 16) + rd((e >> 8) & 0xFFu);
+                if (pos < start) { if (nw >= 255) ok = false; else { wi = sc->fse_w[s1] & 0xFFu; w[nw++] = (uint8_t)wi; tally(wi); } break; }
+            }
+        }
+    }
+    warp_converge<true>();
+    // ---- the last weight is implied: the weights must complete a power of two ----
+    uint32_t* cnt = sc->rank_cnt;                                     // (the stage is dead from here on)
+    if (ok) {
+        for (int k = 0; k < 8; ++k) { cnt[k] = (uint32_t)(c_lo >> (8 * k)) & 0xFFu; cnt[8 + k] = (uint32_t)(c_hi >> (8 * k)) & 0xFFu; }
+        if (big || total == 0) ok = false;
+    }
+    if (ok) {
+        const int maxBits = highbit32(total) + 1;
+        const uint32_t rest = (1u << maxBits) - total;
+        if (maxBits > HUF_LOG_MAX || (rest & (rest - 1))) ok = false;
+        else {
+            const uint32_t lastw = (uint32_t)highbit32(rest) + 1;
+            w[nw++] = (uint8_t)lastw; cnt[lastw]++;
+            if (cnt[1] < 2 || (cnt[1] & 1)) ok = false;
+            sc->huf_log = maxBits;
+            *nw_out = (int)nw;
+        }
+    }
+    return ok ? used : 0;
+}
 
 // Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
 // an FSE description). Returns 0 on success. Single exit (the planner runs one chunk per lane).
@@ -208,11 +338,11 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
         fp.ltype = ltype; fp.regen = regen; fp.nstreams = nstreams; fp.nseq = nseq; fp.seq_base = 0; fp.nruns = 0;
         fp.lit_off = ltype == 0 ? boff + lhs : (ltype == 1 ? ldg8(src + lhs) : 0);
     }
-    // ---- Huffman tree description + stream geometry (every lane walks through huf_read_weights) ----
+    // ---- Huffman tree description + stream geometry (every lane walks through plan_read_weights) ----
     bool huf = !bad && ltype == 2;
     if (huf && nhuf >= PLAN_MAX_HUF) { bad = true; huf = false; }
     int nw = 0;
-    const uint32_t u = huf_read_weights<PlanScratch, true>(sc, src + lhs, huf ? comp : 0u, &nw);
+    const uint32_t u = plan_read_weights(sc, src + lhs, huf ? comp : 0u, &nw);
     if (huf && !u) { bad = true; huf = false; }
     if (huf) {
         uint32_t p = lhs + u, left = comp - u;
@@ -242,7 +372,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     unsigned long long p_lo = 0, p_hi = 0;           // running insert position of every class, 8-bit fields (weights 0-7, 8-15)
     if (huf) {
         const int maxBits = sc->huf_log;
-        uint32_t e = 0, s = 0;                       // huf_read_weights left the per-weight symbol counts in rank_cnt
+        uint32_t e = 0, s = 0;                       // plan_read_weights left the per-weight symbol counts in rank_cnt
         for (int k = 1; k <= maxBits; ++k) {
             hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s;
             const uint32_t cnt = sc->rank_cnt[k];
