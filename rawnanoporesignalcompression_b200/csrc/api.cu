@@ -210,7 +210,7 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     PlanParams pp;
     pp.comp = d_comp; pp.comp_off = d_comp_off; pp.n = d_n; pp.nchunks = (uint32_t)nchunks; pp.codec = codec;
     pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
-    for (int k = 0; k < 3; ++k) pp.region[k] = (uint32_t)(kFastSmem[k] - kFastWs[k] - unpack2_lut_bytes(codec, 256 << k));
+    for (int k = 0; k < 3; ++k) pp.region[k] = (uint32_t)(kFastSmem[k] - kFastWs[k] - unpack2_lut_bytes(codec));
     pp.deftab = (const uint32_t*)c->d_deftab.p;
     pp.cost_bit = c->cost_bit; pp.cost_sym = c->cost_sym;
     pp.has_origin = (lz_heavy || c->pool_per_chunk[0] > 64 || c->d_origin.p) ? 1u : 0u;

@@ -741,6 +741,12 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
             }
         }
     }
+    if (hd.lut_off) {      // this chunk has room for the replicated key-byte table: entry i of copy r in slot i * R + r
+        constexpr uint32_t LR = key_lut_copies(NTH);
+        const KeyLut* one = (const KeyLut*)(region - unpack2_lut_bytes(P.codec));
+        KeyLut* rep = (KeyLut*)(region + hd.lut_off);
+        for (uint32_t i = tid; i < 256u * LR; i += NTH) rep[i] = one[i / LR];
+    }
     for (uint32_t i = 0; i < hd.nfill; ++i) { uint8_t* d = region + hd.fill[i].dst_off; for (uint32_t q = tid; q < hd.fill[i].len; q += NTH) d[q] = (uint8_t)hd.fill[i].value; }
     mbar_wait(&ws->mbar, parity);
     __syncthreads();

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
     RNSC_DYN_SMEM(smem);
     FastWs<NTH>* ws = (FastWs<NTH>*)smem;
     KeyLut* lut = (KeyLut*)(smem + ((sizeof(FastWs<NTH>) + 15) & ~(size_t)15));
-    uint8_t* region = (uint8_t*)lut + unpack2_lut_bytes(P.codec, NTH);
+    uint8_t* region = (uint8_t*)lut + unpack2_lut_bytes(P.codec);
     const int tid = threadIdx.x;
     if (tid == 0) { mbar_init(&ws->mbar, 1); ws->stash_tag = FAST_NONE; const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
     unpack2_init<NTH>(P.codec, lut);
@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
         parity ^= 1u;
         const uint32_t n = ws->n;
         if (ws->status == RNSC_OK && n > 0) {
-            const int r = unpack2_any<NTH>(P.codec, region, lut, ws->head.view, n, P.samples + ws->sample_off, &ws->u2);
+            const uint32_t lo = ws->head.lut_off;      // the chunk's replicated key-byte table (fast_decode_chunk built it), or none
+            const int r = unpack2_any<NTH>(P.codec, region, lo ? (const KeyLut*)(region + lo) : lut, lo ? key_lut_copies(NTH) : 1u, ws->head.view, n, P.samples + ws->sample_off, &ws->u2);
             if (r && tid == 0) ws->status = r;
         }
         __syncthreads();

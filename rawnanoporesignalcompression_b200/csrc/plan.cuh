@@ -26,6 +26,9 @@ constexpr uint32_t PLAN_SUB_MIN = 192;   // minimum Huffman sub-sequence length 
 constexpr uint32_t PLAN_SLOT_MAX = 63;   // symbol slot words per Huffman thread at most (252 symbols: more than a sub-sequence holds)
 constexpr uint32_t FAST_ORDERED_MAX = 64;   // chunks with at most this many sequences run them in order, one warp per frame
 
+constexpr uint32_t KEY_LUT_BYTES = 256 * 16;   // one copy of the splitter inverse's key-byte table (svb_unpack2.cuh)
+__host__ __device__ constexpr uint32_t key_lut_copies(uint32_t nth) { return nth >= 1024 ? 4u : (nth >= 512 ? 2u : 1u); }   // copies a chunk of that class gets if it has room
+
 enum : uint32_t { FK_RAW = 0, FK_RLE = 1, FK_COMP = 2 };
 // size classes of the fast kernel (threads per CTA x CTAs per SM): S 256x4, A 512x2, B 1024x1; then the general decoder
 enum : uint32_t { CLS_S = 0, CLS_A = 1, CLS_B = 2, CLS_SLOW = 3, CLS_DONE = 4 };
@@ -75,6 +78,7 @@ struct PlanHead {                // what the fast kernel copies to shared memory
     uint32_t early;                // bit k: the sequences of sop[k] (raw / RLE literals) are executed by the CTA's last warp while the others decode Huffman streams
     uint32_t zone_off, zone_len;   // region bytes that are dead after the Huffman stage (the largest bitstream area): match resolver scratch
     uint32_t grp_first[PLAN_MAX_HUF + 1];   // thread groups of the Huffman stage, one per Huffman-coded frame: first thread (a multiple of 32)
+    uint32_t lut_off;                       // region offset of the chunk's replicated key-byte table (C4 / C5, key_lut_copies(threads) copies), 0 = none: the single copy in front of the region
     uint32_t slot_off, slot_w;              // symbol slots of the Huffman stage: region offset, 32-bit words per thread (odd, 0 = none): what is left of the class's region
     uint32_t st_first[PLAN_MAX_STREAMS + 1];
     StreamPlan st[PLAN_MAX_STREAMS];
@@ -526,6 +530,11 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         if (r2 <= P.region[cls]) for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].skip_off = region; region += huf_skip_bytes(pl->h[h].log); }
     }
     const uint32_t nth = class_threads(cls);
+    hd->lut_off = 0;
+    if ((P.codec == RNSC_C4 || P.codec == RNSC_C5) && key_lut_copies(nth) > 1) {      // replicated key-byte table of the splitter inverse, if the class has room for it
+        const uint32_t bytes = KEY_LUT_BYTES * key_lut_copies(nth);
+        if (region + bytes <= P.region[cls]) { hd->lut_off = region; region += bytes; }
+    }
     // ---- the kernel's program: Huffman streams, fills, sequence ops, views ----
     uint32_t nst = 0, ttot = 0, nfill = 0, nsop = 0, zone_off = 0, zone_len = 0;
     int vst = RNSC_OK;

@@ -32,10 +32,12 @@ constexpr int U2_SPT = 16;
 struct alignas(16) KeyLut { uint32_t x, y, z, w; };
 // The table is read with one 128-bit shared load per four samples, eight lanes per wavefront, and an entry covers four of
 // the 32 banks: lanes whose key bytes differ collide unless their entries lie in different bank groups (measured: 2.7
-// wavefronts per quarter warp with one copy, a third of all shared-memory traffic of the decode). Where a CTA has the
-// shared memory for it the table is therefore REPLICATED: lane l reads copy l mod R, entry i of copy r sits in slot i * R + r,
-// so that the lanes of a quarter warp share a bank group only with the lanes of their own copy (R = 8: never).
-__host__ __device__ constexpr int key_lut_copies(int nth) { return nth >= 1024 ? 4 : (nth >= 512 ? 2 : 1); }
+// wavefronts per quarter warp with one copy, a third of all shared-memory traffic of the decode). Where a chunk leaves the
+// shared memory for it the table is therefore REPLICATED behind the chunk's streams (the planner decides, PlanHead::lut_off):
+// lane l reads copy l mod R, entry i of copy r sits in slot i * R + r, so that the lanes of a quarter warp share a bank group
+// only with the lanes of their own copy. A chunk without the room (the largest, noisiest ones) reads the single copy in
+// front of the region.
+static_assert(sizeof(KeyLut) * 256 == KEY_LUT_BYTES, "key-byte table size (plan.cuh)");
 
 template <int CODEC>
 __device__ inline KeyLut make_key_lut(uint32_t kbyte)
@@ -103,7 +105,7 @@ __device__ __forceinline__ uint32_t zz_dec(uint32_t z) { return (z >> 1) - (z & 
 // caller's shared-memory region (passed as base + offsets and inlined so that the loads compile to shared-space loads,
 // not generic ones). Returns an rnsc_status (same in every thread).
 template <int CODEC, int NTH>
-__device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lut, const ViewPlan* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
+__device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lut, uint32_t lut_copies, const ViewPlan* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
 {
     constexpr bool TWO = (CODEC == RNSC_VBZ0 || CODEC == RNSC_C4 || CODEC == RNSC_C5);
     constexpr bool WIN = (CODEC == RNSC_C4 || CODEC == RNSC_C5);       // register-window fast path
@@ -115,8 +117,8 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
     const uint8_t *s1 = base + v[1].off, *s2 = base + v[2].off, *s3 = base + v[3].off, *s4 = base + v[4].off;
     const saddr_t a0 = to_saddr(base + v[0].off), a1 = to_saddr(s1), a2 = to_saddr(s2), a3 = to_saddr(s3), a4 = to_saddr(s4);
     const saddr_t vs = to_saddr(v);                                    // the views: {off, len} x 5
-    constexpr int LR = key_lut_copies(NTH);
-    const KeyLut* const lutr = lut + (tid & (LR - 1));                 // this lane's copy of the key-byte table
+    const uint32_t LR = lut_copies;                                    // copies of the key-byte table (a power of two)
+    const KeyLut* const lutr = lut + ((uint32_t)tid & (LR - 1u));      // this lane's copy
     const uint32_t ph = (uint32_t)(((uintptr_t)out >> 1) & 7);        // samples past a 16-byte boundary
     int16_t* outa = out - ph;                                          // 16-byte aligned; virtual sample vi <-> outa[vi]
     const uint32_t nv = n + ph;
@@ -230,7 +232,7 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
 #pragma unroll
                 for (int g = 0; g < S / 4; ++g) {
                     const int h = g >> 1;
-                    const KeyLut e = lutr[__byte_perm(kb, 0u, 0x4440u | (uint32_t)g) * (uint32_t)LR];
+                    const KeyLut e = lutr[__byte_perm(kb, 0u, 0x4440u | (uint32_t)g) * LR];
                     uint32_t x = sw[h] & 0xFFFFu;                                  // next four nibbles -> four bytes
                     x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu;
                     const uint32_t sel3 = (e.y >> 16) + r3x;                       // selectors stay below 8 (no large value: 4 + at most 3 consumed)
@@ -349,28 +351,27 @@ __device__ __forceinline__ int svb_unpack2(const uint8_t* base, const KeyLut* lu
 }
 
 // Shared memory the key-byte table of a codec needs in front of the region (only C4 and C5 have one).
-__host__ __device__ inline uint32_t unpack2_lut_bytes(int codec, int nth) { return (codec == RNSC_C4 || codec == RNSC_C5) ? 256u * (uint32_t)sizeof(KeyLut) * (uint32_t)key_lut_copies(nth) : 0u; }
+__host__ __device__ inline uint32_t unpack2_lut_bytes(int codec) { return (codec == RNSC_C4 || codec == RNSC_C5) ? 256u * (uint32_t)sizeof(KeyLut) : 0u; }
 
-// Once per CTA, before the first svb_unpack2; followed by a barrier at the caller. `lut` = unpack2_lut_bytes(codec, NTH) bytes.
+// Once per CTA, before the first svb_unpack2; followed by a barrier at the caller. `lut` = unpack2_lut_bytes(codec) bytes.
 template <int NTH>
 __device__ inline void unpack2_init(int codec, KeyLut* lut)
 {
     if (codec != RNSC_C4 && codec != RNSC_C5) return;
-    constexpr uint32_t LR = key_lut_copies(NTH);
-    for (uint32_t i = threadIdx.x; i < 256 * LR; i += NTH) lut[i] = codec == RNSC_C5 ? make_key_lut<RNSC_C5>(i / LR) : make_key_lut<RNSC_C4>(i / LR);
+    for (uint32_t i = threadIdx.x; i < 256; i += NTH) lut[i] = codec == RNSC_C5 ? make_key_lut<RNSC_C5>(i) : make_key_lut<RNSC_C4>(i);
 }
 
 template <int NTH>
-__device__ __forceinline__ int unpack2_any(int codec, const uint8_t* base, const KeyLut* lut, const ViewPlan* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
+__device__ __forceinline__ int unpack2_any(int codec, const uint8_t* base, const KeyLut* lut, uint32_t lut_copies, const ViewPlan* v, uint32_t n, int16_t* out, Unpack2Ws<NTH>* ws)
 {
     switch (codec) {
-    case RNSC_VBZ: return svb_unpack2<RNSC_VBZ, NTH>(base, lut, v, n, out, ws);
-    case RNSC_VBZ0: return svb_unpack2<RNSC_VBZ0, NTH>(base, lut, v, n, out, ws);
-    case RNSC_C1: return svb_unpack2<RNSC_C1, NTH>(base, lut, v, n, out, ws);
-    case RNSC_C2: return svb_unpack2<RNSC_C2, NTH>(base, lut, v, n, out, ws);
-    case RNSC_C3: return svb_unpack2<RNSC_C3, NTH>(base, lut, v, n, out, ws);
-    case RNSC_C4: return svb_unpack2<RNSC_C4, NTH>(base, lut, v, n, out, ws);
-    default: return svb_unpack2<RNSC_C5, NTH>(base, lut, v, n, out, ws);
+    case RNSC_VBZ: return svb_unpack2<RNSC_VBZ, NTH>(base, lut, lut_copies, v, n, out, ws);
+    case RNSC_VBZ0: return svb_unpack2<RNSC_VBZ0, NTH>(base, lut, lut_copies, v, n, out, ws);
+    case RNSC_C1: return svb_unpack2<RNSC_C1, NTH>(base, lut, lut_copies, v, n, out, ws);
+    case RNSC_C2: return svb_unpack2<RNSC_C2, NTH>(base, lut, lut_copies, v, n, out, ws);
+    case RNSC_C3: return svb_unpack2<RNSC_C3, NTH>(base, lut, lut_copies, v, n, out, ws);
+    case RNSC_C4: return svb_unpack2<RNSC_C4, NTH>(base, lut, lut_copies, v, n, out, ws);
+    default: return svb_unpack2<RNSC_C5, NTH>(base, lut, lut_copies, v, n, out, ws);
     }
 }
 
