@@ -20,6 +20,8 @@ namespace rnsc {
 // the second pass a copy -- for the chunks that leave little shared memory: the copy back is bound by the SM's outstanding
 // L1 misses, ~3 k cycles per round trip of 12 words per thread with every warp asking at once, 6 k cycles per chunk against
 // the 8 k of decoding the symbols again; no gain, 20k-read C5 decode 508 -> 501 GB/s.)
+// (Tried: using a 64-bit window up in the counting walk -- strides until fewer than 12 of its bits are left, 7-10 per three
+// window loads instead of 4: the data-dependent inner loop costs more than the loads it saves, 20k-read C5 decode 511 -> 504.)
 // (Tried: the Huffman stage as a __noinline__ function of its own, to take its registers out of the chunk loop's
 // allocation -- no spills, but 3 % slower overall on the B200: 483.7 vs 500.6 GB/s on the 20k-read C5 set.)
 #ifndef RNSC_NOINLINE
