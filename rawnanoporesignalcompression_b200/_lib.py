@@ -25,7 +25,7 @@ EXPORTS = [
     "rnsc_version", "rnsc_device_count", "rnsc_status_string", "rnsc_last_error", "rnsc_create", "rnsc_destroy",
     "rnsc_set_host_threads", "rnsc_max_compressed_size", "rnsc_max_stream_bytes", "rnsc_stream_count",
     "rnsc_compress_chunk", "rnsc_decompress_chunk", "rnsc_compress_batch", "rnsc_decompress_batch",
-    "rnsc_dev_decode", "rnsc_dev_svb_encode", "rnsc_dev_svb_decode", "rnsc_dev_rc_encode", "rnsc_dev_rc_decode",
+    "rnsc_dev_decode", "rnsc_dev_svb_encode", "rnsc_dev_svb_encode_slabs", "rnsc_svb_slab_bytes", "rnsc_dev_svb_decode", "rnsc_dev_rc_encode", "rnsc_dev_rc_decode",
     "rnsc_dev_exclusive_scan_u32", "rnsc_launch_count", "rnsc_decode_class_counts", "rnsc_set_profiling", "rnsc_get_phase_cycles", "rnsc_get_cta_spans",
     "rnsc_pod5_vbz_compressed_signal_max_size", "rnsc_pod5_vbz_compress_signal", "rnsc_pod5_pinanoraw_compress_signal",
     "rnsc_pod5_vbz_decompress_signal", "rnsc_pod5_pinanoraw_decompress_signal", "rnsc_set_pgnano_variant",
@@ -69,6 +69,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
         "rnsc_decompress_batch": (i32, [vp, i32, vp, vp, vp, sz, vp, vp, vp]),
         "rnsc_dev_decode": (i32, [vp, i32, vp, vp, vp, vp, sz, u32, vp, vp, vp]),
         "rnsc_dev_svb_encode": (i32, [vp, i32, vp, vp, vp, sz, vp, sz, vp, vp]),
+        "rnsc_dev_svb_encode_slabs": (i32, [vp, i32, vp, vp, vp, sz, sz, vp, sz, vp, vp, vp]),
+        "rnsc_svb_slab_bytes": (sz, [i32, u32]),
         "rnsc_dev_svb_decode": (i32, [vp, i32, vp, vp, vp, vp, sz, vp, vp, vp]),
         "rnsc_dev_rc_encode": (i32, [vp, vp, vp, vp, sz, u8, vp, vp, vp, vp, vp]),
         "rnsc_dev_rc_decode": (i32, [vp, vp, vp, vp, vp, sz, vp, vp, vp]),

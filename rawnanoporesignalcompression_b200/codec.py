@@ -204,6 +204,11 @@ class Codec:
         self._check(self.lib.rnsc_dev_svb_encode(self.ctx, codec_id(codec), self._dp(samples), self._dp(sample_off), self._dp(n), int(n.numel()),
                                                  self._dp(streams), int(streams.numel()), self._dp(stream_off), self._stream(stream)))
 
+    def dev_svb_encode_slabs(self, codec, samples, sample_off, n, total_samples: int, streams, stream_start, stream_size, stream=None):
+        """One-pass splitter: stream k of chunk i = stream_size[5i+k] bytes at streams[stream_start[5i+k]] (per-chunk slabs)."""
+        self._check(self.lib.rnsc_dev_svb_encode_slabs(self.ctx, codec_id(codec), self._dp(samples), self._dp(sample_off), self._dp(n), int(n.numel()), int(total_samples),
+                                                       self._dp(streams), int(streams.numel()), self._dp(stream_start), self._dp(stream_size), self._stream(stream)))
+
     def dev_svb_decode(self, codec, streams, stream_off, n, sample_off, samples, status, stream=None):
         self._check(self.lib.rnsc_dev_svb_decode(self.ctx, codec_id(codec), self._dp(streams), self._dp(stream_off), self._dp(n), self._dp(sample_off),
                                                  int(n.numel()), self._dp(samples), self._dp(status), self._stream(stream)))

@@ -510,6 +510,41 @@ int rnsc_dev_svb_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const 
     return launch_svb_encode(c, codec, d_samples, d_sample_off, d_n, nchunks, d_streams, streams_cap, d_stream_off, stream ? (cudaStream_t)stream : c->stream, true);
 }
 
+// One-pass splitter into per-chunk slabs (kernels.cuh: k_svb_pack_slab): slab sizes by formula, one scan, one kernel over the samples.
+static int launch_svb_encode_slabs(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks,
+                                   uint8_t* d_streams, uint64_t* d_stream_start, uint32_t* d_stream_size, cudaStream_t st)
+{
+    if (c->d_slab.reserve(nchunks * 4 + 16 + (nchunks + 1) * 8)) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(slab table) failed");
+    uint64_t* slab_off = (uint64_t*)c->d_slab.p; uint32_t* slab_sz = (uint32_t*)((uint8_t*)c->d_slab.p + (nchunks + 1) * 8);
+    RNSC_LAUNCH(k_slab_sizes, (int)((nchunks + 255) / 256), 256, 0, st, d_n, (uint32_t)nchunks, codec, slab_sz);
+    RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)slab_sz, (unsigned long long)nchunks, (unsigned long long*)slab_off);
+    const int grid = (int)std::min<size_t>((size_t)1 << 30, nchunks);
+#define RNSC_SLAB(C) case C: RNSC_LAUNCH(k_svb_pack_slab<C>, grid, P2_NT, (size_t)P2_STAGE_BYTES, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, d_streams, (const uint64_t*)slab_off, (unsigned long long*)d_stream_start, d_stream_size); break
+    switch (codec) { RNSC_SLAB(RNSC_VBZ); RNSC_SLAB(RNSC_VBZ0); RNSC_SLAB(RNSC_C1); RNSC_SLAB(RNSC_C2); RNSC_SLAB(RNSC_C3); RNSC_SLAB(RNSC_C4); default: RNSC_SLAB(RNSC_C5); }
+#undef RNSC_SLAB
+    c->launches += 3;
+    CUDA_OK(cudaGetLastError());
+    return RNSC_OK;
+}
+
+size_t rnsc_svb_slab_bytes(int codec, uint32_t n)
+{
+    if (!svb_codec_ok(codec)) return 0;
+    uint32_t rel[6]; slab_layout(codec, n, rel);
+    return rel[5];
+}
+
+int rnsc_dev_svb_encode_slabs(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks, size_t total_samples,
+                              uint8_t* d_streams, size_t streams_cap, uint64_t* d_stream_start, uint32_t* d_stream_size, void* stream)
+{
+    if (!c || !svb_codec_ok(codec) || (nchunks && (!d_samples || !d_sample_off || !d_n || !d_streams || !d_stream_start || !d_stream_size))) return fail(RNSC_ERR_BAD_ARG, "rnsc_dev_svb_encode_slabs: bad argument");
+    if (use_device(c)) return RNSC_ERR_NO_DEVICE;
+    if (!nchunks) return RNSC_OK;
+    // every slab is at most keys (<= n/4 + 1) + 3.5 n + 5 x 16 bytes of padding + 15 of rounding
+    if (streams_cap < 4 * total_samples + 128 * nchunks + 64) return fail(RNSC_ERR_DST_TOO_SMALL, "stream buffer too small: %zu bytes for the slabs of %zu samples in %zu chunks (need 4 x samples + 128 x chunks + 64)", streams_cap, total_samples, nchunks);
+    return launch_svb_encode_slabs(c, codec, d_samples, d_sample_off, d_n, nchunks, d_streams, d_stream_start, d_stream_size, stream ? (cudaStream_t)stream : c->stream);
+}
+
 // Whole-chunk encode on the device: splitter, then the GPU entropy stage (zstd_encode.cuh): valid zstd frames, decodable by
 // libzstd / the reference / this library, NOT byte-identical to libzstd's level-1 output.
 int rnsc_dev_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint64_t* d_sample_off, const uint32_t* d_n, size_t nchunks, size_t total_samples,
@@ -523,21 +558,12 @@ int rnsc_dev_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint
     const size_t streams_cap = 4 * total_samples + 128 * nchunks + 64;                                        // >= the sum of the chunks' slabs (slab_layout: keys + every stream at its upper bound)
     const size_t slots_cap = 2 * total_samples + total_samples / 4 + 1104 * nchunks + 64;                     // sum of the reference's output capacities, 16-byte rounded
     if (c->d_streams.reserve(streams_cap + 64) || c->d_stream_off.reserve((5 * nchunks + 1) * 8) || c->d_sizes.reserve(5 * nchunks * sizeof(uint32_t) + 16) ||
-        c->d_slab.reserve(nchunks * 4 + 16 + (nchunks + 1) * 8) || c->d_zhist.reserve(nchunks * nf * 256 * sizeof(uint32_t)) ||
+        c->d_zhist.reserve(nchunks * nf * 256 * sizeof(uint32_t)) ||
         c->d_zframes.reserve(nchunks * nf * sizeof(ZencFrame)) || c->d_zslots.reserve(slots_cap + 64) || c->d_zslot_sz.reserve(nchunks * 4 + 16) ||
         c->d_zslot_off.reserve((nchunks + 1) * 8) || c->d_zout_sz.reserve(nchunks * 4 + 16))
         return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(encoder scratch) failed");
     // splitter into per-chunk slabs: one pass over the samples (no size pass, no scan of the stream sizes)
-    uint64_t* slab_off = (uint64_t*)c->d_slab.p; uint32_t* slab_sz = (uint32_t*)((uint8_t*)c->d_slab.p + (nchunks + 1) * 8);
-    RNSC_LAUNCH(k_slab_sizes, (int)((nchunks + 255) / 256), 256, 0, st, d_n, (uint32_t)nchunks, codec, slab_sz);
-    RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)slab_sz, (unsigned long long)nchunks, (unsigned long long*)slab_off);
-    {
-        const int grid = (int)std::min<size_t>((size_t)1 << 30, nchunks);
-#define RNSC_SLAB(C) case C: RNSC_LAUNCH(k_svb_pack_slab<C>, grid, P2_NT, (size_t)P2_STAGE_BYTES, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, (uint8_t*)c->d_streams.p, (const uint64_t*)slab_off, (unsigned long long*)c->d_stream_off.p, (uint32_t*)c->d_sizes.p); break
-        switch (codec) { RNSC_SLAB(RNSC_VBZ); RNSC_SLAB(RNSC_VBZ0); RNSC_SLAB(RNSC_C1); RNSC_SLAB(RNSC_C2); RNSC_SLAB(RNSC_C3); RNSC_SLAB(RNSC_C4); default: RNSC_SLAB(RNSC_C5); }
-#undef RNSC_SLAB
-    }
-    c->launches += 3;
+    { const int r = launch_svb_encode_slabs(c, codec, d_samples, d_sample_off, d_n, nchunks, (uint8_t*)c->d_streams.p, (uint64_t*)c->d_stream_off.p, (uint32_t*)c->d_sizes.p, st); if (r) return r; }
     RNSC_LAUNCH(k_zenc_slot_sizes, (int)((nchunks + 255) / 256), 256, 0, st, d_n, (uint32_t)nchunks, codec, (uint32_t*)c->d_zslot_sz.p);
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zslot_sz.p, (unsigned long long)nchunks, (unsigned long long*)c->d_zslot_off.p);
     ZencParams zp;

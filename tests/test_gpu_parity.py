@@ -150,6 +150,20 @@ def test_device_resident_api(gpu_codec, oracle):
         gpu_codec.dev_svb_decode(codec, d_streams, d_soff, d_n, d_off, out, status)
         torch.cuda.synchronize()
         assert not status.any() and (out == sig).all(), NAMES[codec]
+        # the one-pass variant (per-chunk slabs): same stream bytes, start + size per stream
+        total = int(n.sum())
+        assert sum(gpu_codec.lib.rnsc_svb_slab_bytes(codec, int(k)) for k in n) <= 4 * total + 128 * nch + 64
+        d_slabs = torch.zeros(4 * total + 128 * nch + 64, dtype=torch.uint8, device=dev)
+        d_start = torch.empty(5 * nch, dtype=torch.int64, device=dev); d_size = torch.empty(5 * nch, dtype=torch.int32, device=dev)
+        gpu_codec.dev_svb_encode_slabs(codec, sig, d_off, d_n, total, d_slabs, d_start, d_size)
+        torch.cuda.synchronize()
+        start, size, sl_host = d_start.cpu().numpy(), d_size.cpu().numpy(), d_slabs.cpu().numpy()
+        for i in range(nch):
+            want = oracle.streams(codec, host[off[i] : off[i] + n[i]])
+            got = [sl_host[start[5 * i + k] : start[5 * i + k] + size[5 * i + k]].tobytes() for k in range(5)]
+            assert got == want, (NAMES[codec], i, "slabs")
+        with pytest.raises(Exception):
+            gpu_codec.dev_svb_encode_slabs(codec, sig, d_off, d_n, total, d_slabs[: total], d_start, d_size)
     # whole-chunk device decode of oracle-produced bytes at unaligned offsets
     for codec in (0, 6):
         comp = [oracle.encode(codec, host[o : o + c]) for o, c in zip(off, n)]
