@@ -78,10 +78,10 @@ def test_fast_path_routing_and_sequences(ecodec, oracle):
 def test_fuzz_corrupt_chunks_never_crash_and_agree_with_rfc_decoder(ecodec, oracle):
     """Random byte flips anywhere in a chunk (headers, Huffman tree, bitstreams, sequences): the decoder must return a
     status or the same samples as the oracle's RFC 8878 decoder -- never crash, hang or write out of bounds."""
-    rng = np.random.default_rng(1234)
     x = recipes.walk(6000, 31, 14.0)
     flat = x.copy(); flat[1000:1600] = flat[999]
-    for codec, src in ((6, x), (0, x), (6, flat), (0, flat), (1, x)):
+    for seed, (codec, src) in [(sd, cs) for sd in (1234, 1, 2, 3) for cs in ((6, x), (0, x), (6, flat), (0, flat), (1, x))]:
+        rng = np.random.default_rng(seed)
         good = oracle.encode(codec, src)
         trials = []
         for _ in range(24):
@@ -96,7 +96,12 @@ def test_fuzz_corrupt_chunks_never_crash_and_agree_with_rfc_decoder(ecodec, orac
         assert st[-1] == 0 and (outs[-1] == src).all()              # the intact chunk next to them is untouched
         for t, o, s in zip(trials, outs, st):
             ost, oy = oracle.decode_status(codec, t, src.size, own_zstd=True)
-            assert (s != 0) == (ost != 0), (codec, s, ost)
+            # DESIGN.md section 2, second deliberate difference: corrupted keys can make ONE stream over-read while the last
+            # one still ends where it should; librnsc bounds every stream (status 4, "Remaining data"), the reference checks
+            # only the final pointer and returns OK with garbage
+            if s == 4 and ost == 0:
+                continue
+            assert (s != 0) == (ost != 0), (seed, codec, s, ost)
             if ost == 0:
                 assert (o == oy).all()
 
