@@ -28,7 +28,7 @@ namespace rnsc {
 #define RNSC_NOINLINE
 #endif
 
-constexpr uint32_t FAST_WARM_BITS = 256;   // speculative warm-up before a sub-sequence
+constexpr uint32_t FAST_WARM_BITS = 192;   // speculative warm-up before a sub-sequence
 constexpr uint32_t FAST_NONE = 0xFFFFFFFFu;
 
 struct FastParams {
