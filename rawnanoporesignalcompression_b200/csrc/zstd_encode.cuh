@@ -213,15 +213,25 @@ __device__ inline uint32_t ze_fse_weights(const uint8_t* w, uint32_t n, uint32_t
 
 // Scratch of one frame's build, in shared memory: thread-private arrays of this size in LOCAL memory (the first version,
 // one thread per frame) made every access an L2 round trip -- 2.7 ms for the 110k frames of a 20k-read batch.
+// 2.6 KB per frame (4.5 KB with every array on its own: three instead of five CTAs per SM, and the kernel is bound by the
+// frames in flight: 2.35 -> 1.9 ms at four CTAs on the 20k-read batch). The internal nodes' weights are dead once the tree
+// stands, before the code lengths, the weight bytes and the FSE scratch of the tree description come to life: they share
+// their bytes. A symbol's zstd weight replaces its code length in place (a lane converts the eight symbols it has just
+// read). A parent index is below 256, and an internal node's depth replaces its parent index in place (root first).
 struct ZencBuildWs {
     uint32_t key[256];           // present symbols: count << 8 | symbol, sorted ascending
-    uint32_t wgt[256];           // weights of the internal nodes of the Huffman tree
-    uint16_t par[512];           // parent (index among the internal nodes) of leaf i / of internal node 256 + j
-    uint8_t depth[256], len[256], wts[256];
-    ZeFseWs fse;
+    union {
+        uint32_t wgt[256];       // stage B: weights of the internal nodes of the Huffman tree
+        struct {
+            union { uint8_t len[256]; uint8_t wts[256]; };   // stages C-E: code length per symbol; E-G: its zstd weight
+            ZeFseWs fse;         // stages E-G: scratch of the FSE-compressed tree description
+        };
+    };
+    uint8_t par[512];            // parent (index among the internal nodes) of leaf i; of internal node j at [256 + j], then (end of stage B) the depth of node j
     uint32_t m, maxs, L, kraft, nfull, maxw, dl, have, size, live;   // state of the frame between the stages
     unsigned long long bits;
 };
+static_assert(sizeof(ZeFseWs) + 256 <= 1024, "the tree description's scratch must fit behind the internal nodes' weights");
 constexpr int ZE_BUILD_WARPS = 4;        // warps per CTA
 constexpr int ZE_BUILD_SLOTS = 4;        // frames a warp builds at once: the serial stages run on ZE_BUILD_SLOTS lanes together
 constexpr size_t ZE_BUILD_SMEM = sizeof(ZencBuildWs) * ZE_BUILD_WARPS * ZE_BUILD_SLOTS;
@@ -312,15 +322,15 @@ __global__ void __launch_bounds__(32 * ZE_BUILD_WARPS) k_zenc_build(ZencParams P
                 uint32_t sum = 0;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    if (lw <= iw) { sum += lw; w.par[li++] = (uint16_t)qn; lw = li < m ? w.key[li] >> 8 : INF; }
-                    else { sum += iw; w.par[256 + qi++] = (uint16_t)qn; iw = qi < qn ? w.wgt[qi] : INF; }
+                    if (lw <= iw) { sum += lw; w.par[li++] = (uint8_t)qn; lw = li < m ? w.key[li] >> 8 : INF; }
+                    else { sum += iw; w.par[256 + qi++] = (uint8_t)qn; iw = qi < qn ? w.wgt[qi] : INF; }
                 }
                 w.wgt[qn] = sum;
                 if (iw == INF && qi == qn) iw = sum;                  // the internal queue was empty: the new node is its head
                 ++qn;
             }
-            w.depth[m - 2] = 0;                                       // the root is the last internal node
-            for (int j = (int)m - 3; j >= 0; --j) w.depth[j] = (uint8_t)(w.depth[w.par[256 + j]] + 1);
+            w.par[256 + m - 2] = 0;                                   // depths in place of the parent indices: the root is the last internal node,
+            for (int j = (int)m - 3; j >= 0; --j) w.par[256 + j] = (uint8_t)(w.par[256 + w.par[256 + j]] + 1);   // a parent has a higher index than its child and holds its depth already
         }
         __syncwarp();
         // ---- stage C (all lanes, slot by slot): code lengths per symbol, cut at ZE_LOG_MAX, Kraft sum ----
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(32 * ZE_BUILD_WARPS) k_zenc_build(ZencParams P
             __syncwarp();
             uint32_t kraft = 0, nfull = 0, maxlen = 0;
             for (uint32_t i = lane; i < m; i += 32) {
-                uint32_t l = w.depth[w.par[i]] + 1u;
+                uint32_t l = w.par[256 + w.par[i]] + 1u;
                 maxlen = max(maxlen, l);
                 if (l > ZE_LOG_MAX) l = ZE_LOG_MAX;
                 w.len[w.key[i] & 0xFF] = (uint8_t)l; kraft += 1u << (ZE_LOG_MAX - l); nfull += l == ZE_LOG_MAX;
