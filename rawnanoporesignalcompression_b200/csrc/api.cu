@@ -216,9 +216,13 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     pp.has_origin = (lz_heavy || c->pool_per_chunk[0] > 64 || c->d_origin.p) ? 1u : 0u;
     pp.seq_pool = (uint32_t*)c->d_seqpool.p; pp.pool_cap = (uint32_t)std::min<size_t>(pool_cap, 0xFFFFFFFFu); pp.pool_cursor = (unsigned long long*)(cnt + 4);   /* words 4-5, 8-byte aligned */
     RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
-    {   // the pool cursor (entries asked for) and the chunk count travel to the pinned mirror; nobody waits for them
-        RNSC_LAUNCH(k_pool_demand, 1, 1, 0, st, (const unsigned long long*)(cnt + 4), (unsigned long long)nchunks, (unsigned long long*)c->d_counter.p + 16);
-        CUDA_OK(cudaMemcpyAsync(c->h_pool_seen.p, (const unsigned long long*)c->d_counter.p + 16, 16, cudaMemcpyDeviceToHost, st));
+    {   // the pool cursor (entries asked for) and the chunk count travel to the pinned mirror; nobody waits for them. The kernel
+        // stores straight into the pinned host words (mapped under unified addressing): a D2H copy on this stream would queue
+        // behind whatever the copy engine is doing -- in rnsc_decompress_batch the 128 MiB D2H of the previous slice -- and hold
+        // the decode kernels behind it back with it (measured: a bubble of one decode, ~0.4 ms, per slice in the D2H stream)
+        unsigned long long* mirror = nullptr;
+        CUDA_OK(cudaHostGetDevicePointer((void**)&mirror, c->h_pool_seen.p, 0));
+        RNSC_LAUNCH(k_pool_demand, 1, 1, 0, st, (const unsigned long long*)(cnt + 4), (unsigned long long)nchunks, mirror);
     }
     // 2. fast kernel over the three size classes, 3. general decoder over what is left. Fork: class B (large chunks, one
     // CTA per SM) stays on the caller's stream and is enqueued first; the other classes and the general decoder go to side

@@ -304,10 +304,11 @@ __global__ void __launch_bounds__(NT, 1) k_exclusive_scan_u32(const uint32_t* in
     if (threadIdx.x == 0) out[count] = run;
 }
 
-// {sequence pool entries the planner asked for, chunks} of this decode -> the slot a D2H copy mirrors to the host (api.cu)
+// {sequence pool entries the planner asked for, chunks} of this decode -> the host's pinned mirror (api.cu), written directly
 __global__ void k_pool_demand(const unsigned long long* cursor, unsigned long long nchunks, unsigned long long* out)
 {
     out[0] = *cursor; out[1] = nchunks;
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ inline void __syncwarp(unsigned mask = 0xffffffffu) { unsigned long long all[32]
 inline long long clock64() { static long long t = 0; return ++t; }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
+inline void __threadfence_system() {}
 
 template <typename T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
     unsigned long long all[32], raw = 0; memcpy(&raw, &v, sizeof(T)); emul::warp_exchange(mask, raw, all);
@@ -112,6 +113,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? 0 : 2; }
 inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
