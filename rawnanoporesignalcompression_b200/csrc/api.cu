@@ -129,7 +129,9 @@ void host_default_tables(uint32_t* tab /* 160 */)
 struct Lane {
     DevBuf comp, samples, off_a, off_b, n, status;
     PinBuf h_off;
-    cudaEvent_t ev_in = nullptr, ev_dec = nullptr, ev_out = nullptr;
+    PinBuf h_status;                          // the slice's statuses land here (pinned: a D2H copy into the caller's pageable array would block the issuing thread until the slice's kernels are done)
+    size_t st_first = 0, st_count = 0;        // which chunks of the call they belong to (copied out by the host once the slice is through)
+    cudaEvent_t ev_in = nullptr, ev_dec = nullptr, ev_out = nullptr, ev_tab = nullptr;
     bool used = false;
 };
 static uint64_t slice_samples()                   // samples per pipeline slice (default 128 MiB of int16); RNSC_SLICE_SAMPLES overrides (tuning)
@@ -341,7 +343,8 @@ rnsc_ctx* rnsc_create(int device)
     }
     ok = ok && cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) ok = cudaEventCreateWithFlags(&c->lane[k].ev_in, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->lane[k].ev_dec, cudaEventDisableTiming) == cudaSuccess &&
-                                           cudaEventCreateWithFlags(&c->lane[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
+                                           cudaEventCreateWithFlags(&c->lane[k].ev_out, cudaEventDisableTiming) == cudaSuccess &&
+                                           cudaEventCreateWithFlags(&c->lane[k].ev_tab, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { rnsc_destroy(c); fail(RNSC_ERR_NO_DEVICE, "cudaStreamCreate/cudaEventCreate failed"); return nullptr; }
     cudaError_t e1 = cudaFuncSetAttribute(k_decode_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
     { cudaError_t e0 = cudaFuncSetAttribute(k_zenc_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZE_BUILD_SMEM); if (e1 == cudaSuccess) e1 = e0; }
@@ -387,8 +390,8 @@ void rnsc_destroy(rnsc_ctx* c)
     for (int k = 0; k < 2; ++k) {
         Lane& L = c->lane[k];
         for (DevBuf* b : {&L.comp, &L.samples, &L.off_a, &L.off_b, &L.n, &L.status}) b->release();
-        L.h_off.release();
-        for (cudaEvent_t e : {L.ev_in, L.ev_dec, L.ev_out}) if (e) cudaEventDestroy(e);
+        L.h_off.release(); L.h_status.release();
+        for (cudaEvent_t e : {L.ev_in, L.ev_dec, L.ev_out, L.ev_tab}) if (e) cudaEventDestroy(e);
     }
     if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
     if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
@@ -653,9 +656,12 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
         while (last < nchunks && (last == first || sb + n[last] <= slice_samples())) { cb += comp_off[last + 1] - comp_off[last]; sb += n[last]; if (n[last] > max_n) max_n = n[last]; ++last; }
         const size_t m = last - first;
         Lane& L = c->lane[slice & 1];
-        if (L.used) CUDA_OK(cudaEventSynchronize(L.ev_out));     // the lane's previous slice has left the device; its pinned tables are free
+        if (L.used) {                                             // the lane's previous slice has left the device: its pinned tables are free, its statuses go to the caller
+            CUDA_OK(cudaEventSynchronize(L.ev_out));
+            memcpy(status + L.st_first, L.h_status.p, L.st_count * 4); L.st_count = 0;
+        }
         if (L.comp.reserve(cb + 64) || L.samples.reserve(sb * 2 + 64) || L.off_a.reserve((m + 1) * 8) || L.off_b.reserve((m + 1) * 8) ||
-            L.n.reserve(m * 4 + 16) || L.status.reserve(m * 4 + 16) || L.h_off.reserve(2 * (m + 1) * 8))
+            L.n.reserve(m * 4 + 16) || L.status.reserve(m * 4 + 16) || L.h_off.reserve(2 * (m + 1) * 8) || L.h_status.reserve(m * 4 + 16))
             return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
         uint64_t* coff = (uint64_t*)L.h_off.p; uint64_t* soff = coff + (m + 1);
         bool contiguous = true, dense = true;
@@ -686,7 +692,8 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
         CUDA_OK(cudaEventRecord(L.ev_dec, st));
         // ---- D2H ----
         CUDA_OK(cudaStreamWaitEvent(c->d2h, L.ev_dec, 0));
-        CUDA_OK(cudaMemcpyAsync(status + first, L.status.p, m * 4, cudaMemcpyDeviceToHost, c->d2h));
+        CUDA_OK(cudaMemcpyAsync(L.h_status.p, L.status.p, m * 4, cudaMemcpyDeviceToHost, c->d2h));
+        L.st_first = first; L.st_count = m;
         if (dense) CUDA_OK(cudaMemcpyAsync(samples + sample_off[first], L.samples.p, sb * 2, cudaMemcpyDeviceToHost, c->d2h));
         else for (size_t i = 0; i < m; ++i) if (n[first + i]) CUDA_OK(cudaMemcpyAsync(samples + sample_off[first + i], (int16_t*)L.samples.p + soff[i], (size_t)n[first + i] * 2, cudaMemcpyDeviceToHost, c->d2h));
         CUDA_OK(cudaEventRecord(L.ev_out, c->d2h));
@@ -697,7 +704,11 @@ int rnsc_decompress_batch(rnsc_ctx* c, int codec, const uint8_t* comp, const uin
     };
     int rc = run();
     const cudaError_t e1 = cudaStreamSynchronize(c->h2d), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(c->d2h);
-    for (int k = 0; k < 2; ++k) c->lane[k].used = false;
+    for (int k = 0; k < 2; ++k) {
+        Lane& L = c->lane[k];
+        if (L.st_count && e3 == cudaSuccess) memcpy(status + L.st_first, L.h_status.p, L.st_count * 4);      // the last slices' statuses
+        L.st_count = 0; L.used = false;
+    }
     if (rc == RNSC_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
         rc = fail(RNSC_ERR_NO_DEVICE, "rnsc_decompress_batch: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return rc;
@@ -754,37 +765,76 @@ int rnsc_compress_batch(rnsc_ctx* c, int codec, const int16_t* samples, const ui
     }
 
     if (c->entropy_stage == 1) {
-        // ---- GPU entropy stage: samples in, finished chunks out; nothing but the two copies touches the host ----
-        size_t first = 0; uint64_t op = 0;
-        while (first < nchunks) {
-            size_t last = first; uint64_t sb = 0;
-            while (last < nchunks && (last == first || sb + n[last] <= slice_samples())) { sb += n[last]; ++last; }
-            const size_t m = last - first;
-            std::vector<uint64_t> soff(m + 1), coff(m + 1);
-            bool dense = true; uint64_t a = 0;
-            for (size_t i = 0; i < m; ++i) { soff[i] = a; if (sample_off[first + i] - sample_off[first] != a) dense = false; a += n[first + i]; }
-            soff[m] = a;
-            const size_t ccap = 2 * sb + sb / 4 + 1104 * m + 64;
-            if (c->d_samples.reserve(sb * 2 + 64) || c->d_off_b.reserve((m + 1) * 8) || c->d_n.reserve(m * 4 + 16) || c->d_comp.reserve(ccap + 64) || c->d_off_a.reserve((m + 1) * 8) || c->d_status.reserve(m * 4 + 16))
-                return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
-            if (dense) CUDA_OK(cudaMemcpyAsync(c->d_samples.p, samples + sample_off[first], sb * 2, cudaMemcpyHostToDevice, st));
-            else for (size_t i = 0; i < m; ++i) if (n[first + i]) CUDA_OK(cudaMemcpyAsync((int16_t*)c->d_samples.p + soff[i], samples + sample_off[first + i], (size_t)n[first + i] * 2, cudaMemcpyHostToDevice, st));
-            CUDA_OK(cudaMemcpyAsync(c->d_off_b.p, soff.data(), (m + 1) * 8, cudaMemcpyHostToDevice, st));
-            CUDA_OK(cudaMemcpyAsync(c->d_n.p, n + first, m * 4, cudaMemcpyHostToDevice, st));
-            int r = rnsc_dev_encode(c, codec, (const int16_t*)c->d_samples.p, (const uint64_t*)c->d_off_b.p, (const uint32_t*)c->d_n.p, m, sb, (uint8_t*)c->d_comp.p, ccap,
-                                    (uint64_t*)c->d_off_a.p, (int32_t*)c->d_status.p, st);
-            if (r) { cudaStreamSynchronize(st); return r; }
-            CUDA_OK(cudaMemcpyAsync(coff.data(), c->d_off_a.p, (m + 1) * 8, cudaMemcpyDeviceToHost, st));
-            CUDA_OK(cudaMemcpyAsync(status + first, c->d_status.p, m * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_OK(cudaStreamSynchronize(st));
-            if (op + coff[m] > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need %llu bytes, have %zu", (unsigned long long)(op + coff[m]), comp_cap);
-            CUDA_OK(cudaMemcpyAsync(comp + op, c->d_comp.p, coff[m], cudaMemcpyDeviceToHost, st));
-            for (size_t i = 0; i < m; ++i) comp_off[first + i] = op + coff[i];
-            CUDA_OK(cudaStreamSynchronize(st));
-            op += coff[m]; first = last;
-        }
-        comp_off[nchunks] = op;
-        return RNSC_OK;
+        // ---- GPU entropy stage: samples in, finished chunks out; nothing but the copies touches the host. Slices flow through
+        //      the two staging lanes like in rnsc_decompress_batch: H2D of slice k+1, encode of slice k and D2H of slice k-1
+        //      overlap on three streams. A slice's place in the caller's buffer is known once the sizes of the slices before
+        //      it are, so its offset table comes back first (a small copy), the host adds it up, and the payload copy follows.
+        struct Pending { size_t first = 0, m = 0; Lane* L = nullptr; };
+        Pending pend; bool have = false;
+        uint64_t op = 0;
+        int rc = RNSC_OK;
+        auto finish = [&](const Pending& q) -> int {      // slice q's table is on its way: place it, start its payload copy
+            CUDA_OK(cudaEventSynchronize(q.L->ev_tab));
+            memcpy(status + q.first, q.L->h_status.p, q.m * 4);
+            const uint64_t* coff = (const uint64_t*)q.L->h_off.p + (q.m + 1);
+            if (op + coff[q.m] > comp_cap) return fail(RNSC_ERR_DST_TOO_SMALL, "output buffer too small: need %llu bytes, have %zu", (unsigned long long)(op + coff[q.m]), comp_cap);
+            if (coff[q.m]) CUDA_OK(cudaMemcpyAsync(comp + op, q.L->comp.p, coff[q.m], cudaMemcpyDeviceToHost, c->d2h));
+            CUDA_OK(cudaEventRecord(q.L->ev_out, c->d2h));
+            for (size_t i = 0; i < q.m; ++i) comp_off[q.first + i] = op + coff[i];
+            op += coff[q.m];
+            return RNSC_OK;
+        };
+        auto run = [&]() -> int {
+            size_t first = 0; int slice = 0;
+            while (first < nchunks) {
+                size_t last = first; uint64_t sb = 0;
+                while (last < nchunks && (last == first || sb + n[last] <= slice_samples())) { sb += n[last]; ++last; }
+                const size_t m = last - first;
+                Lane& L = c->lane[slice & 1];
+                // the lane's previous slice (k-2) was finished in the previous iteration: its tables are free, its payload copy is queued
+                const size_t ccap = 2 * sb + sb / 4 + 1104 * m + 64;
+                if (L.samples.reserve(sb * 2 + 64) || L.off_b.reserve((m + 1) * 8) || L.n.reserve(m * 4 + 16) || L.comp.reserve(ccap + 64) || L.off_a.reserve((m + 1) * 8) ||
+                    L.status.reserve(m * 4 + 16) || L.h_off.reserve(2 * (m + 1) * 8) || L.h_status.reserve(m * 4 + 16))
+                    return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(staging) failed");
+                uint64_t* soff = (uint64_t*)L.h_off.p;          // [0, m]: sample offsets in the lane; [m+1, 2m+1]: the slice's chunk offsets, filled by the device
+                bool dense = true; uint64_t a = 0;
+                for (size_t i = 0; i < m; ++i) { soff[i] = a; if (sample_off[first + i] - sample_off[first] != a) dense = false; a += n[first + i]; }
+                soff[m] = a;
+                // ---- H2D (the lane's sample buffer is free once its previous encode has run) ----
+                if (L.used) CUDA_OK(cudaStreamWaitEvent(c->h2d, L.ev_dec, 0));
+                if (dense) CUDA_OK(cudaMemcpyAsync(L.samples.p, samples + sample_off[first], sb * 2, cudaMemcpyHostToDevice, c->h2d));
+                else for (size_t i = 0; i < m; ++i) if (n[first + i]) CUDA_OK(cudaMemcpyAsync((int16_t*)L.samples.p + soff[i], samples + sample_off[first + i], (size_t)n[first + i] * 2, cudaMemcpyHostToDevice, c->h2d));
+                CUDA_OK(cudaMemcpyAsync(L.off_b.p, soff, (m + 1) * 8, cudaMemcpyHostToDevice, c->h2d));
+                CUDA_OK(cudaMemcpyAsync(L.n.p, n + first, m * 4, cudaMemcpyHostToDevice, c->h2d));
+                CUDA_OK(cudaEventRecord(L.ev_in, c->h2d));
+                // ---- encode (the lane's output buffer is free once its previous payload has left) ----
+                CUDA_OK(cudaStreamWaitEvent(st, L.ev_in, 0));
+                if (L.used) CUDA_OK(cudaStreamWaitEvent(st, L.ev_out, 0));
+                const int r = rnsc_dev_encode(c, codec, (const int16_t*)L.samples.p, (const uint64_t*)L.off_b.p, (const uint32_t*)L.n.p, m, sb, (uint8_t*)L.comp.p, ccap,
+                                              (uint64_t*)L.off_a.p, (int32_t*)L.status.p, st);
+                if (r) return r;
+                CUDA_OK(cudaEventRecord(L.ev_dec, st));
+                // ---- the slice's offset table and statuses ----
+                CUDA_OK(cudaStreamWaitEvent(c->d2h, L.ev_dec, 0));
+                CUDA_OK(cudaMemcpyAsync(soff + (m + 1), L.off_a.p, (m + 1) * 8, cudaMemcpyDeviceToHost, c->d2h));
+                CUDA_OK(cudaMemcpyAsync(L.h_status.p, L.status.p, m * 4, cudaMemcpyDeviceToHost, c->d2h));
+                CUDA_OK(cudaEventRecord(L.ev_tab, c->d2h));
+                L.used = true;
+                // ---- the previous slice: place it, start its payload copy (this slice's H2D and encode are already queued) ----
+                if (have) { const int r2 = finish(pend); if (r2) return r2; }
+                pend.first = first; pend.m = m; pend.L = &L; have = true;
+                first = last; ++slice;
+            }
+            if (have) { const int r2 = finish(pend); if (r2) return r2; }
+            return RNSC_OK;
+        };
+        rc = run();
+        const cudaError_t e1 = cudaStreamSynchronize(c->h2d), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(c->d2h);
+        for (int k = 0; k < 2; ++k) c->lane[k].used = false;
+        if (rc == RNSC_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
+            rc = fail(RNSC_ERR_NO_DEVICE, "rnsc_compress_batch: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        if (rc == RNSC_OK) comp_off[nchunks] = op;
+        return rc;
     }
 
     // ---- sliced pipeline: while the host threads run the zstd frame stage of slice k, this thread stages slice k+1

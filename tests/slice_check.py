@@ -24,5 +24,20 @@ for codec in codecs:
     ok = [i for i in range(len(chunks)) if not st[i]]
     dec, st2 = cd.decompress_batch([comp[i] for i in ok], [len(chunks[i]) for i in ok], codec)
     assert not st2.any() and all((a == chunks[i]).all() for a, i in zip(dec, ok))
+# the same batch with the GPU entropy stage: other bytes, but every chunk must decode to its samples through the reference-side
+# decoder (the oracle) and through this library; chunk offsets must be consistent across the slices
+if len(sys.argv) > 3 and sys.argv[3] == "gpu_entropy":
+    cd.set_entropy_stage("gpu")
+    for codec in [c for c in codecs if c != 7]:
+        comp, st = cd.compress_batch(chunks, codec)
+        for got, s, c in zip(comp, st, chunks):
+            ws, _ = orc.encode_status(codec, c)
+            assert (s != 0) == (ws != 0), (codec, len(c), s, ws)
+            if not s:
+                assert (orc.decode(codec, got, len(c)) == c).all(), (codec, len(c))
+        ok = [i for i in range(len(chunks)) if not st[i]]
+        dec, st2 = cd.decompress_batch([comp[i] for i in ok], [len(chunks[i]) for i in ok], codec)
+        assert not st2.any() and all((a == chunks[i]).all() for a, i in zip(dec, ok))
+    cd.set_entropy_stage("libzstd")
 cd.close()
 print("slices ok")

@@ -132,7 +132,7 @@ def test_encode_pipeline_many_slices(emul_lib):
     """rnsc_compress_batch stages slice k+1 while host threads compress slice k: force ~10 slices on a small batch."""
     import os, subprocess, sys
     env = dict(os.environ, RNSC_SLICE_SAMPLES="6000")
-    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "slice_check.py"), emul_lib, "6,0,2,7"], env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "slice_check.py"), emul_lib, "6,0,2,7", "gpu_entropy"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "slices ok" in r.stdout, r.stdout + r.stderr
 
 

@@ -231,7 +231,7 @@ def test_encode_pipeline_many_slices(gpu_codec):
     """Host-buffer encode across many pipeline slices (RNSC_SLICE_SAMPLES is read once per process -> subprocess)."""
     import os, subprocess, sys
     env = dict(os.environ, RNSC_SLICE_SAMPLES="6000")
-    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "slice_check.py"), "gpu", "0,1,2,3,4,5,6,7"], env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "slice_check.py"), "gpu", "0,1,2,3,4,5,6,7", "gpu_entropy"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "slices ok" in r.stdout, r.stdout + r.stderr
 
 
