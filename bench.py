@@ -500,7 +500,44 @@ def run_rnsc(args):
         e2e = {"value": round(e_val, 3), "unit": UNIT, "h2d_bytes_per_step": int(e_cb + 20 * e_ch + 16),
                "d2h_bytes_per_step": int(2 * e_samples + 4 * e_ch), "steps": e_steps, "reads_per_rank": e_reads, "bit_exact": e_ok, "pcie_link": pcie,
                "call": "rnsc_decompress_batch (pinned host buffers in and out)"}
-        del h_comp, h_out
+        # The other direction: whole-chunk ENCODE end to end through rnsc_compress_batch with the GPU entropy stage (pinned host
+        # buffers: H2D of the samples, splitter + entropy stage on the device, D2H of the finished chunks). The decode leg's
+        # output buffer holds the samples; the result is checked by decoding it on the device.
+        try:
+            del h_comp
+            enc_cap = int(e_cb * 1.03) + 1104 * 64 + 65536
+            h_enc = torch.empty(enc_cap, dtype=torch.uint8).pin_memory(); he = h_enc.numpy()
+            coff2 = np.zeros(e_ch + 1, np.uint64); status2 = np.zeros(e_ch, np.int32)
+            cd.set_entropy_stage("gpu")
+
+            def e2e_enc_step():
+                r = cd.lib.rnsc_compress_batch(cd.ctx, codec, _ptr(ho), _ptr(e_soff), _ptr(e_n), e_ch, _ptr(he), enc_cap, _ptr(coff2), _ptr(status2))
+                if r or status2.any():
+                    raise RuntimeError("rnsc_compress_batch (GPU entropy stage) failed in the e2e leg")
+
+            for _ in range(2):
+                e2e_enc_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                e2e_enc_step()
+            barrier()
+            dt2 = allreduce(time.perf_counter() - t0, "max")
+            cd.set_entropy_stage("libzstd")
+            g_b = int(coff2[-1])
+            d_enc = torch.from_numpy(he[: g_b + 64].copy()).to(dev); d_c2 = torch.from_numpy(coff2.astype(np.int64)).to(dev)
+            d_o2 = torch.empty(e_samples, dtype=torch.int16, device=dev); d_s2 = torch.empty(e_ch, dtype=torch.int32, device=dev)
+            cd.dev_decode(codec, d_enc, d_c2, d_n[:e_ch], d_off[:e_ch], max_n, d_o2, d_s2)
+            torch.cuda.synchronize()
+            enc_ok = bool(torch.equal(d_o2, wl["d_sig"][:e_samples])) and not bool(d_s2.any().item())
+            e2e["encode_gpu_entropy"] = {"value": round(2.0 * es * e_steps / dt2 / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": int(2 * e_samples + 12 * e_ch + 8),
+                                         "d2h_bytes_per_step": int(g_b + 12 * e_ch + 8), "bits_per_sample": round(8.0 * g_b / e_samples, 4),
+                                         "roundtrip_bit_exact": enc_ok, "call": "rnsc_compress_batch, RNSC_ENTROPY_GPU (pinned host buffers in and out)"}
+            del h_enc, d_enc, d_o2
+        except Exception as ex:  # noqa: BLE001
+            cd.set_entropy_stage("libzstd")
+            e2e["encode_gpu_entropy"] = {"error": str(ex)}
+        del h_out
 
     # ---- other legs of the path (not the headline) -------------------------------------------------------------
     extra = {}
