@@ -1,5 +1,5 @@
 import sys, time, os, numpy as np, torch
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,ROOT); sys.path.insert(0,os.path.join(ROOT,'tests'))
 from rawnanoporesignalcompression_b200 import synth
 from rawnanoporesignalcompression_b200.codec import Codec, _ptr
 R=int(sys.argv[1]) if len(sys.argv)>1 else 30000

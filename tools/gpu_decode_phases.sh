@@ -1,5 +1,5 @@
 #!/bin/bash
-# decode timing of the current tree: tools/run_dec.sh TAG [ncu]  (20k-read C5 R10.4.1 + VBZ R9.4.1; optional ncu --set full of the decode kernels)
+# decode timing of the current tree: tools/gpu_decode_phases.sh TAG [ncu]  (20k-read C5 R10.4.1 + VBZ R9.4.1; optional ncu --set full of the decode kernels)
 set -u
 mkdir -p gpurun_out
 TAG=${1:-dec}

@@ -1,5 +1,5 @@
 #!/bin/bash
-# device encode (GPU entropy stage): timing + launch list of one step (20k reads): tools/run_enc.sh TAG [codec]
+# device encode (GPU entropy stage): timing + launch list of one step (20k reads): tools/gpu_encode_launches.sh TAG [codec]
 set -u
 mkdir -p gpurun_out
 TAG=${1:-enc}; CODEC=${2:-6}
