@@ -94,7 +94,11 @@ int rnsc_decompress_chunk(rnsc_ctx* ctx, int codec, const uint8_t* in, size_t in
 /* ---- batch, host buffers (the POD5 hooks a batched codec sits behind: pod5_add_reads_data_pre_compressed
  *      c_api.h:665-673 on write, SignalTableReader::extract_samples_inplace signal_table_reader.cpp:320-340
  *      on read). Chunk i covers samples[sample_off[i] .. +n[i]) and comp[comp_off[i] .. comp_off[i+1]).
- *      status[i] receives the per-chunk rnsc_status. Returns RNSC_OK if the call itself succeeded. ------ */
+ *      status[i] receives the per-chunk rnsc_status. Returns RNSC_OK if the call itself succeeded.
+ *      Both calls cut the batch into slices (~128 MiB of int16) that flow through two lanes of device staging on three
+ *      streams: H2D of slice k+1, kernels of slice k and D2H of slice k-1 overlap when the caller's buffers are pinned
+ *      (cudaHostAlloc / cudaHostRegister) -- decode, and encode with RNSC_ENTROPY_GPU, then run at the PCIe rate; with
+ *      RNSC_ENTROPY_LIBZSTD the host threads compress slice k while slice k+1 is staged. ------ */
 int rnsc_compress_batch(rnsc_ctx* ctx, int codec, const int16_t* samples, const uint64_t* sample_off,
                         const uint32_t* n, size_t nchunks, uint8_t* comp, size_t comp_cap,
                         uint64_t* comp_off /* nchunks+1 */, int32_t* status);
