@@ -232,6 +232,12 @@ struct ZencBuildWs {
     unsigned long long bits;
 };
 static_assert(sizeof(ZeFseWs) + 256 <= 1024, "the tree description's scratch must fit behind the internal nodes' weights");
+// (Tried on the serial stages: the first two elements of either Huffman queue in registers so that the refill load is issued a
+// pick ahead, node depths by pointer jumping with all lanes instead of the serial walk, the next pair's weights and table
+// rows fetched while the FSE states make their round trip. Fewer dependent shared-memory round trips, but 966 M -> 1.05 G
+// warp instructions, and with five CTAs per SM the kernel is bound by issue slots -- a serial stage costs a full warp
+// instruction for four active lanes -- not by the chains' latency: 1.84 -> 1.92 ms on the C5 set; VBZ, with a fifth of
+// the frames, gained 3 %.)
 constexpr int ZE_BUILD_WARPS = 4;        // warps per CTA
 constexpr int ZE_BUILD_SLOTS = 4;        // frames a warp builds at once: the serial stages run on ZE_BUILD_SLOTS lanes together
 constexpr size_t ZE_BUILD_SMEM = sizeof(ZencBuildWs) * ZE_BUILD_WARPS * ZE_BUILD_SLOTS;
