@@ -1,8 +1,8 @@
 #!/bin/bash
-# N=2 validation of bench.py (reduced reads) -- run with gpurun --gpus 2
+# N-rank validation of bench.py (reduced reads): NP=4 gpurun --gpus 4 -- bash tools/gpu_bench_n2.sh (default 2 ranks)
 set -u
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --reads 8000 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NP:-2} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${NP:-2} --steps 3 --warmup 3 --reads 8000 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?"
 tail -5 gpurun_out/bench_n2.err | cut -c1-600
 python - <<'PY'
 import json
