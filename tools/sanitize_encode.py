@@ -2,7 +2,9 @@
 at every 16-byte phase, all seven splitter codecs, checked against the oracle."""
 import sys
 import numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import recipes
 from oracle_binding import Oracle
 from rawnanoporesignalcompression_b200.codec import Codec
