@@ -154,7 +154,7 @@ struct rnsc_ctx {
     int entropy_stage = 0;                    // rnsc_compress_batch: 0 = host libzstd level 1 (byte-identical to the reference), 1 = GPU entropy stage
     bool profiling = false;
     uint32_t prof_warp = 0;                   // RNSC_PROF_WARP (tuning): which warp, counted from the end, times the phases
-    uint32_t cost_bit = 1, cost_sym = 12;   // planner's cost model of the Huffman stage (plan.cuh); RNSC_COST_BIT / RNSC_COST_SYM override (tuning)
+    uint32_t cost_bit = 1, cost_sym = 12, cost_run = 2000;   // planner's cost model of the Huffman stage (plan.cuh); RNSC_COST_BIT / RNSC_COST_SYM / RNSC_COST_RUN override (tuning)
     Lane lane[2];
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
@@ -214,7 +214,7 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
     pp.plans = (ChunkPlan*)c->d_plans.p; pp.status = d_status; pp.lists = (uint32_t*)c->d_lists.p; pp.counts = cnt;
     for (int k = 0; k < 3; ++k) pp.region[k] = (uint32_t)(kFastSmem[k] - kFastWs[k] - unpack2_lut_bytes(codec));
     pp.deftab = (const uint32_t*)c->d_deftab.p;
-    pp.cost_bit = c->cost_bit; pp.cost_sym = c->cost_sym;
+    pp.cost_bit = c->cost_bit; pp.cost_sym = c->cost_sym; pp.cost_run = c->cost_run;
     pp.has_origin = (lz_heavy || c->pool_per_chunk[0] > 64 || c->d_origin.p) ? 1u : 0u;
     pp.seq_pool = (uint32_t*)c->d_seqpool.p; pp.pool_cap = (uint32_t)std::min<size_t>(pool_cap, 0xFFFFFFFFu); pp.pool_cursor = (unsigned long long*)(cnt + 4);   /* words 4-5, 8-byte aligned */
     RNSC_LAUNCH(k_plan_chunks, (int)((nchunks + PLAN_THREADS - 1) / PLAN_THREADS), PLAN_THREADS, 0, st, pp);
@@ -372,6 +372,7 @@ rnsc_ctx* rnsc_create(int device)
     if (const char* e = getenv("RNSC_PROF_WARP")) c->prof_warp = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("RNSC_COST_BIT")) c->cost_bit = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("RNSC_COST_SYM")) c->cost_sym = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("RNSC_COST_RUN")) c->cost_run = (uint32_t)strtoul(e, nullptr, 10);
     if (c->cost_bit + c->cost_sym == 0) c->cost_bit = 1;
     return c;
 }

@@ -45,6 +45,7 @@ struct FramePlan {               // planner-internal description of one frame
     uint32_t nruns;              // number of non-empty literal runs (the tail after the last match included)
     uint32_t hz_off, hz_len;     // chunk offset / size of the Huffman bitstream area (dead once the literals are decoded)
     uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
+    uint32_t s_runs[4];              // non-empty literal runs that start inside each stream's literals (frames with sequences)
 };
 struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decoding table
     uint32_t log;                // table log (max code length), <= 12
@@ -102,6 +103,7 @@ struct PlanParams {
     const uint32_t* deftab;      // predefined FSE decoding tables: LL[64] OF[32] ML[64]
     uint32_t has_origin;         // the fast kernel has global scratch for the match resolver's origin words (else: chunks that need it go to the general decoder)
     uint32_t cost_bit, cost_sym; // Huffman stage cost model: a sub-sequence of b bits holding s symbols costs cost_bit * b + cost_sym * s
+    uint32_t cost_run;           // ... + cost_run per literal run that starts in it (the second pass changes its output position at every run)
     uint32_t* seq_pool; uint32_t pool_cap; unsigned long long* pool_cursor;   // 64-bit cursor: a hostile batch can ask for more than 2^32 entries; bump-allocated sequence storage (SEQ_WORDS words per entry)
 };
 
@@ -252,8 +254,9 @@ __device__ inline uint32_t plan_read_weights(PlanScratch* sc, const uint8_t* src
 // Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
 // an FSE description). Returns 0 on success. Single exit (the planner runs one chunk per lane).
 __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, const uint32_t* tll, int ll_log, const uint32_t* tof, int of_log,
-                                     const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out, uint32_t* nruns)
+                                     const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out, uint32_t* nruns, uint32_t lit_per_stream, uint32_t* runs4)
 {
+    unsigned long long rc = 0;                  // runs per Huffman stream of the literals, four 16-bit counters (saturating use: a cost estimate)
     BwdBits b;
     bool bad = bwd_init(b, bs, bs_size) != 0;
     uint32_t sl = 0, so = 0, sm = 0;
@@ -285,13 +288,18 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
         }
         if (b.overflow || lp + ll > regen || op + ll + ml > fcs || offset > op + ll) { bad = true; break; }
         out[SEQ_WORDS * i] = ll; out[SEQ_WORDS * i + 1] = ml; out[SEQ_WORDS * i + 2] = offset; out[SEQ_WORDS * i + 3] = lp; out[SEQ_WORDS * i + 4] = op; out[SEQ_WORDS * i + 5] = op - lp;
-        if (ll) { out[SEQ_WORDS * nr + 6] = lp; out[SEQ_WORDS * nr + 7] = op - lp; ++nr; }      // compact list of the non-empty literal runs (nr <= i)
+        if (ll) {      // compact list of the non-empty literal runs (nr <= i)
+            out[SEQ_WORDS * nr + 6] = lp; out[SEQ_WORDS * nr + 7] = op - lp; ++nr;
+            const uint32_t sidx = (lp >= lit_per_stream) + (lp >= 2 * lit_per_stream) + (lp >= 3 * lit_per_stream);
+            rc += 1ull << (16 * sidx);
+        }
         op += ll + ml; lp += ll;
     }
     if (!bad && (b.bitpos != 0 || op + (regen - lp) != fcs)) bad = true;
     if (!bad) {
         if (regen > lp) { out[SEQ_WORDS * nr + 6] = lp; out[SEQ_WORDS * nr + 7] = op - lp; ++nr; }   // the tail (the allocation has nseq + 1 entries)
         *nruns = nr;
+        for (int j = 0; j < 4; ++j) runs4[j] = (uint32_t)(rc >> (16 * j)) & 0xFFFFu;
     }
     return bad ? 1 : 0;
 }
@@ -438,7 +446,8 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
             } else { bad = true; break; }
         }
         if (!bad && p >= size) bad = true;
-        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, P.seq_pool + (size_t)SEQ_WORDS * base, &fp.nruns)) bad = true;
+        if (!bad && plan_sequences(src + p, size - p, nseq, tab[0], tlog[0], tab[1], tlog[1], tab[2], tlog[2], regen, fp.fcs, P.seq_pool + (size_t)SEQ_WORDS * base, &fp.nruns,
+                                    nstreams == 4 ? (regen + 3) / 4 : (regen ? regen : 1u), fp.s_runs)) bad = true;
         if (!bad) nseq_tot += nseq;
     }
     return bad ? 1 : 0;
@@ -488,7 +497,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         FramePlan fp;
         fp.kind = FK_RAW; fp.fcs = (uint32_t)fcs; fp.data_off = 0; fp.dst_off = 0; fp.ltype = 0; fp.regen = 0; fp.lit_off = 0;
         fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0; fp.nruns = 0; fp.hz_off = 0; fp.hz_len = 0;
-        for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; }
+        for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; fp.s_runs[j] = 0; }
         bool comp_block = false; uint32_t bsz = 0;
         if (live) {
             if (hdr + 3 > fl) slow = true;
@@ -537,6 +546,8 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     }
     // ---- the kernel's program: Huffman streams, fills, sequence ops, views ----
     uint32_t nst = 0, ttot = 0, nfill = 0, nsop = 0, zone_off = 0, zone_len = 0;
+    uint32_t sruns[PLAN_MAX_STREAMS];                  // literal runs per Huffman stream (0 without sequences)
+    for (int s = 0; s < PLAN_MAX_STREAMS; ++s) sruns[s] = 0;
     int vst = RNSC_OK;
     const uint32_t kl = key_len(P.codec, n);
     uint32_t tot_fcs = 0;
@@ -560,6 +571,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                 sp.tab_off = pl->h[fp.huf].tab_off; sp.skip_off = pl->h[fp.huf].skip_off; sp.log = pl->h[fp.huf].log;
                 sp.sop = my_sop; sp.regen = fp.regen; sp.pitch = 2; sp.sub = 0;
                 if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
+                sruns[nst] = fp.nseq ? fp.s_runs[j] : 0u;
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }
         }
@@ -592,16 +604,16 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     // (many symbols per bit: long second pass) do not hold up the others. Warps are dealt out in proportion to each
     // frame's estimated cost, cost_bit per payload bit (first pass) + cost_sym per symbol (second pass); the warm-up is the
     // same for every thread and drops out.
-    uint32_t gw[PLAN_MAX_HUF] = {0, 0, 0}, gt[PLAN_MAX_HUF] = {0, 0, 0}, gc[PLAN_MAX_HUF] = {0, 0, 0}, gn[PLAN_MAX_HUF] = {0, 0, 0}, gs0[PLAN_MAX_HUF] = {0, 0, 0};
+    uint32_t gw[PLAN_MAX_HUF] = {0, 0, 0}, gt[PLAN_MAX_HUF] = {0, 0, 0}, gc[PLAN_MAX_HUF] = {0, 0, 0}, gn[PLAN_MAX_HUF] = {0, 0, 0}, gs0[PLAN_MAX_HUF] = {0, 0, 0}, gr[PLAN_MAX_HUF] = {0, 0, 0};
     uint32_t ngrp = 0;
     for (uint32_t s = 0; s < nst; ++s) {
         if (s == 0 || hd->st[s].tab_off != hd->st[s - 1].tab_off) { gs0[ngrp] = s; ++ngrp; }
-        gt[ngrp - 1] += hd->st[s].tbits; gc[ngrp - 1] += hd->st[s].count; gn[ngrp - 1] += 1;
+        gt[ngrp - 1] += hd->st[s].tbits; gc[ngrp - 1] += hd->st[s].count; gn[ngrp - 1] += 1; gr[ngrp - 1] += sruns[s];
     }
     {
         const uint32_t nw = nth_h / 32;
         unsigned long long wsum = 0, wg[PLAN_MAX_HUF];
-        for (uint32_t g = 0; g < ngrp; ++g) { wg[g] = (unsigned long long)P.cost_bit * gt[g] + (unsigned long long)P.cost_sym * gc[g] + 1; wsum += wg[g]; }
+        for (uint32_t g = 0; g < ngrp; ++g) { wg[g] = (unsigned long long)P.cost_bit * gt[g] + (unsigned long long)P.cost_sym * gc[g] + (unsigned long long)P.cost_run * gr[g] + 1; wsum += wg[g]; }
         uint32_t used = 0, big = 0;
         for (uint32_t g = 0; g < ngrp; ++g) { gw[g] = (uint32_t)((wg[g] * nw + wsum / 2) / wsum); if (gw[g] < 1) gw[g] = 1; used += gw[g]; if (wg[g] > wg[big]) big = g; }
         while (used > nw) { uint32_t m = 0; for (uint32_t g = 1; g < ngrp; ++g) if (gw[g] > gw[m]) m = g; --gw[m]; --used; }     // nw >= 7 > ngrp: never below one warp
@@ -618,7 +630,23 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                                                                 // bitstream (worth its rounding loss only where one CTA has the SM to itself)
         if (sub > sub_max) sub_max = sub;
         uint32_t t = first;
-        for (uint32_t s = gs0[g]; s < gs0[g] + gn[g]; ++s) { hd->st[s].sub = sub; hd->st_first[s] = t; t += (hd->st[s].tbits + sub - 1) / sub; }
+        if (gr[g] && gn[g] > 1 && nt > gn[g]) {
+            // a frame with LZ sequences: the streams whose literals are cut into many runs (VBZ: the key region, at the start of
+            // the first stream) decode slower in the second pass; threads are dealt out to the streams by cost, not by bits
+            unsigned long long wsm = 0, wst[4] = {0, 0, 0, 0};
+            for (uint32_t k = 0; k < gn[g] && k < 4; ++k) { const StreamPlan& sp = hd->st[gs0[g] + k];
+                wst[k] = (unsigned long long)P.cost_bit * sp.tbits + (unsigned long long)P.cost_sym * sp.count + (unsigned long long)P.cost_run * sruns[gs0[g] + k] + 1; wsm += wst[k]; }
+            for (uint32_t k = 0; k < gn[g] && k < 4; ++k) {
+                const uint32_t s = gs0[g] + k;
+                uint32_t ts = (uint32_t)((wst[k] * nt) / wsm); if (ts < 1) ts = 1;
+                uint32_t ss = (hd->st[s].tbits + ts - 1) / ts;
+                if (ss < PLAN_SUB_MIN) ss = PLAN_SUB_MIN;
+                if (cls == CLS_B) ss = ((ss + 31u) >> 5 | 1u) << 5;
+                if (ss > sub_max) sub_max = ss;
+                hd->st[s].sub = ss; hd->st_first[s] = t; t += (hd->st[s].tbits + ss - 1) / ss;
+            }
+        } else
+            for (uint32_t s = gs0[g]; s < gs0[g] + gn[g]; ++s) { hd->st[s].sub = sub; hd->st_first[s] = t; t += (hd->st[s].tbits + sub - 1) / sub; }
         first += nt;
     }
     hd->grp_first[PLAN_MAX_HUF] = first;
