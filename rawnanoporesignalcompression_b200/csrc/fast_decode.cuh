@@ -481,7 +481,10 @@ __device__ RNSC_NOINLINE int fast_huffman(FastWs<NTH>* ws, uint8_t* region, cons
             }
         } else {
             // runs can be a few literals long (the key region of a VBZ frame): one symbol at a time from a buffered
-            // 64-bit window, switching the output position whenever a run ends (the next run is fetched ahead)
+            // 64-bit window, switching the output position whenever a run ends (the next run is fetched ahead).
+            // (Tried: pieces of 16 and more literals through the four-symbols-per-window loop with word stores, the short ones
+            // as here -- the lanes of a warp sit in different kinds of piece at any time and the warp pays for both bodies:
+            // second pass of a large VBZ chunk 38 k -> 76 k cycles.)
             uint8_t* o = region + sp.out + li + shift;
             uint2 nxt = seg + 1 < nruns ? run[seg + 1] : make_uint2(sp.regen, 0u);
             int avail = 0;
