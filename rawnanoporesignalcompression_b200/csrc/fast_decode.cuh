@@ -68,7 +68,11 @@ struct FastWs {
     Unpack2Ws<NTH> u2;
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
-    uint32_t nlong, longq[128], long_k[128], long_ms[128], long_ml[128], long_of[128], long_mb[128];   // long matches of the frame being resolved (a warp each)
+    // Long matches of the frames being resolved (a warp each): six arrays of FAST_LONG_CAP words. The one-CTA-per-SM class, whose
+    // largest chunks need every byte of shared memory, keeps them in the part of the sub-sequence arrays that is idle during
+    // the sequence stage (behind the ST_WORDS <= 512 words of the parked plan); the smaller CTAs have no such room.
+    uint32_t nlong, long_own[NTH >= 1024 ? 1 : 6 * 128];
+    __device__ __forceinline__ uint32_t* long_arr(int k) { return (NTH >= 1024 ? sub_end + 512 : long_own) + 128 * k; }
     int status; uint32_t next;
     uint32_t n; unsigned long long sample_off;   // the chunk's sample count and offset in the output
     alignas(8) unsigned long long mbar;
@@ -632,7 +636,7 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const PlanHead& hd, 
         if (j < 2) { k = m_k[j & 1]; ms = m_ms[j & 1]; ml = m_ml[j & 1]; of = m_of[j & 1]; mb = m_mb[j & 1]; } else fetch(idx, k, ms, ml, of, mb);
         if (ml > LONG) {
             const uint32_t q = atomicAdd(&ws->nlong, 1u);
-            if (q < QCAP) { ws->longq[q] = idx; ws->long_k[q] = k; ws->long_ms[q] = ms; ws->long_ml[q] = ml; ws->long_of[q] = of; ws->long_mb[q] = mb; continue; }
+            if (q < QCAP) { ws->long_arr(0)[q] = idx; ws->long_arr(1)[q] = k; ws->long_arr(2)[q] = ms; ws->long_arr(3)[q] = ml; ws->long_arr(4)[q] = of; ws->long_arr(5)[q] = mb; continue; }
         }
         const SeqOp& op = hd.sop[k];
         emit_origins((const uint2*)(region + op.meta_off), op.nruns, op.regen, origin, obase[k], ms, ml, of, mb, 0, ml);
@@ -640,7 +644,7 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const PlanHead& hd, 
     __syncthreads();
     const uint32_t nl = min(ws->nlong, QCAP), lane = tid & 31u;
     for (uint32_t w = tid >> 5; w < nl; w += NTH / 32) {
-        const uint32_t k = ws->long_k[w], ms = ws->long_ms[w], ml = ws->long_ml[w], of = ws->long_of[w], mb = ws->long_mb[w];
+        const uint32_t k = ws->long_arr(1)[w], ms = ws->long_arr(2)[w], ml = ws->long_arr(3)[w], of = ws->long_arr(4)[w], mb = ws->long_arr(5)[w];
         const SeqOp& op = hd.sop[k];
         const uint32_t c = (ml + 31) / 32;                                  // a contiguous piece per lane
         emit_origins((const uint2*)(region + op.meta_off), op.nruns, op.regen, origin, obase[k], ms, ml, of, mb, min(ml, lane * c), min(ml, (lane + 1) * c));
@@ -659,13 +663,13 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const PlanHead& hd, 
     for (uint32_t idx = tid, j = 0; idx < total_seq; idx += NTH, ++j) {
         uint32_t k, ms, ml, of, mb;
         if (j < 2) { k = m_k[j & 1]; ms = m_ms[j & 1]; ml = m_ml[j & 1]; mb = m_mb[j & 1]; } else fetch(idx, k, ms, ml, of, mb);
-        if (ml > LONG) { bool queued = false; for (uint32_t q = 0; q < nl; ++q) queued |= ws->longq[q] == idx; if (queued) continue; }
+        if (ml > LONG) { bool queued = false; for (uint32_t q = 0; q < nl; ++q) queued |= ws->long_arr(0)[q] == idx; if (queued) continue; }
         uint8_t* dst = region + hd.sop[k].dst_off;
         const uint32_t* o = origin + obase[k] + mb;
         for (uint32_t q = 0; q < ml; ++q) dst[ms + q] = dst[o[q] & ~ORIGIN_LIT];
     }
     for (uint32_t w = tid >> 5; w < nl; w += NTH / 32) {
-        const uint32_t k = ws->long_k[w], ms = ws->long_ms[w], ml = ws->long_ml[w], mb = ws->long_mb[w];
+        const uint32_t k = ws->long_arr(1)[w], ms = ws->long_arr(2)[w], ml = ws->long_arr(3)[w], mb = ws->long_arr(5)[w];
         uint8_t* dst = region + hd.sop[k].dst_off;
         const uint32_t* o = origin + obase[k] + mb;
         for (uint32_t q = lane; q < ml; q += 32) dst[ms + q] = dst[o[q] & ~ORIGIN_LIT];
