@@ -68,11 +68,13 @@ struct FastWs {
     Unpack2Ws<NTH> u2;
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
-    // Long matches of the frames being resolved (a warp each): six arrays of FAST_LONG_CAP words. The one-CTA-per-SM class, whose
-    // largest chunks need every byte of shared memory, keeps them in the part of the sub-sequence arrays that is idle during
-    // the sequence stage (behind the ST_WORDS <= 512 words of the parked plan); the smaller CTAs have no such room.
-    uint32_t nlong, long_own[NTH >= 1024 ? 1 : 6 * 128];
-    __device__ __forceinline__ uint32_t* long_arr(int k) { return (NTH >= 1024 ? sub_end + 512 : long_own) + 128 * k; }
+    // Long matches of the frames being resolved (a warp each): six arrays of LONG_CAP words. The classes with 512 and 1024
+    // threads keep them in the part of the sub-sequence arrays that is idle during the sequence stage (behind the
+    // ST_WORDS <= 512 words of the parked plan) -- the largest chunks of the one-CTA-per-SM class need every byte of shared
+    // memory; the 256-thread class has no such room and a short queue of its own (its chunks are small).
+    static constexpr uint32_t LONG_CAP = NTH >= 1024 ? 128u : (NTH >= 512 ? 64u : 32u);
+    uint32_t nlong, long_own[NTH >= 512 ? 1 : 6 * LONG_CAP];
+    __device__ __forceinline__ uint32_t* long_arr(int k) { return (NTH >= 512 ? sub_end + 512 : long_own) + LONG_CAP * k; }
     int status; uint32_t next;
     uint32_t n; unsigned long long sample_off;   // the chunk's sample count and offset in the output
     alignas(8) unsigned long long mbar;
@@ -338,6 +340,7 @@ __device__ __forceinline__ void put_kept(uint8_t* o, const uint32_t* slot, uint3
 constexpr uint32_t ST_HEAD_W = sizeof(PlanHead) / 4, ST_HUF_W = PLAN_MAX_HUF * sizeof(HufPlan) / 4;
 constexpr uint32_t ST_COFF = ST_HEAD_W + ST_HUF_W, ST_SOFF = ST_COFF + 2, ST_N = ST_SOFF + 2, ST_WORDS = ST_N + 1;   // + compressed offset, sample offset, sample count
 static_assert(ST_WORDS <= 2 * 256, "the stash must fit the smallest CTA's sub-sequence arrays");
+static_assert(512 + 6 * 64 <= 2 * 512 && 512 + 6 * 128 <= 2 * 1024, "the long-match queue must fit behind the stash (FastWs::long_arr)");
 __device__ __forceinline__ uint32_t stash_fetch(const FastParams& P, uint32_t c, uint32_t idx)
 {
     if (idx < ST_HEAD_W) return ((const uint32_t*)&P.plans[c].head)[idx];
@@ -616,7 +619,7 @@ __device__ inline void fast_exec_sequences(FastWs<NTH>* ws, const PlanHead& hd, 
             else { const uint8_t* s = region + op.lit + lp; for (uint32_t q = tid; q < len; q += NTH) d[q] = s[q]; }
         }
     }
-    constexpr uint32_t LONG = 48, QCAP = 128;
+    constexpr uint32_t LONG = 48, QCAP = FastWs<NTH>::LONG_CAP;
     if (tid == 0) ws->nlong = 0;
     // my (up to two) sequences, fetched once from the global pool: frame, match start, length, offset, matched-byte index
     uint32_t m_k[2] = {0, 0}, m_ms[2] = {0, 0}, m_ml[2] = {0, 0}, m_of[2] = {1, 1}, m_mb[2] = {0, 0};
