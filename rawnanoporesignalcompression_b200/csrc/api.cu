@@ -579,10 +579,16 @@ int rnsc_dev_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint
     zp.stream_size = (const uint32_t*)c->d_sizes.p;
     zp.hist = (uint32_t*)c->d_zhist.p; zp.frames = (ZencFrame*)c->d_zframes.p; zp.slots = (uint8_t*)c->d_zslots.p; zp.slot_off = (const uint64_t*)c->d_zslot_off.p;
     zp.out_size = (uint32_t*)c->d_zout_sz.p; zp.status = d_status;
-    const int wide = (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 8);
+    // one CTA per chunk for the per-chunk kernels: the chunks are ragged (1 .. 102400 samples) and a fixed stride over a
+    // persistent grid left the CTAs with the most samples running alone at the end (emit: 50 % warps active of 75 % possible)
+#ifdef RNSC_ZE_STATIC_GRID
+    const int wide = (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 8), emit_grid = (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 6);
+#else
+    const int wide = (int)nchunks, emit_grid = (int)nchunks;
+#endif
     RNSC_LAUNCH(k_zenc_histogram, wide, ZE_NT, 0, st, zp);
     RNSC_LAUNCH(k_zenc_build, (int)std::min<size_t>((nchunks * nf + ZE_BUILD_WARPS * ZE_BUILD_SLOTS - 1) / (ZE_BUILD_WARPS * ZE_BUILD_SLOTS), (size_t)c->sm_count * 16), 32 * ZE_BUILD_WARPS, ZE_BUILD_SMEM, st, zp);
-    RNSC_LAUNCH(k_zenc_emit, (int)std::min<size_t>(nchunks, (size_t)c->sm_count * 6), ZE_NT, 0, st, zp);
+    RNSC_LAUNCH(k_zenc_emit, emit_grid, ZE_NT, 0, st, zp);
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zout_sz.p, (unsigned long long)nchunks, (unsigned long long*)d_comp_off);
     RNSC_LAUNCH(k_zenc_gather, wide, ZE_NT, 0, st, (const uint8_t*)c->d_zslots.p, (const uint64_t*)c->d_zslot_off.p, (const uint64_t*)d_comp_off, (uint32_t)nchunks, d_comp,
                 (unsigned long long)comp_cap, d_status);
@@ -598,7 +604,7 @@ int rnsc_dev_svb_decode(rnsc_ctx* c, int codec, const uint8_t* d_streams, const 
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     if (!nchunks) return RNSC_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    const int grid = (int)std::min<size_t>((size_t)c->sm_count * 8, nchunks);
+    const int grid = (int)nchunks;                                        // one CTA per chunk: ragged sizes, balanced by the block scheduler
     RNSC_LAUNCH(k_svb_unpack, grid, NT, 0, st, codec, d_streams, d_stream_off, d_n, d_sample_off, (uint32_t)nchunks, d_samples, d_status);
     c->launches += 1;
     CUDA_OK(cudaGetLastError());
@@ -612,7 +618,7 @@ int rnsc_dev_rc_encode(rnsc_ctx* c, const int16_t* d_samples, const uint64_t* d_
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     if (!nchunks) return RNSC_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    const int grid = (int)std::min<size_t>((size_t)c->sm_count * 8, (nchunks + RC_WARPS - 1) / RC_WARPS);
+    const int grid = (int)((nchunks + RC_WARPS - 1) / RC_WARPS);      // one warp per chunk, the block scheduler deals the ragged chunks out
     RNSC_LAUNCH(k_rc_encode, grid, 32 * RC_WARPS, 0, st, d_samples, d_sample_off, d_n, (uint32_t)nchunks, pore_type, d_comp, d_slot_off, d_comp_size, d_status);
     c->launches += 1;
     CUDA_OK(cudaGetLastError());
@@ -626,7 +632,7 @@ int rnsc_dev_rc_decode(rnsc_ctx* c, const uint8_t* d_comp, const uint64_t* d_com
     if (use_device(c)) return RNSC_ERR_NO_DEVICE;
     if (!nchunks) return RNSC_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    const int grid = (int)std::min<size_t>((size_t)c->sm_count * 8, (nchunks + RC_WARPS - 1) / RC_WARPS);
+    const int grid = (int)((nchunks + RC_WARPS - 1) / RC_WARPS);      // one warp per chunk, the block scheduler deals the ragged chunks out
     RNSC_LAUNCH(k_rc_decode, grid, 32 * RC_WARPS, 0, st, d_comp, d_comp_off, d_n, d_sample_off, (uint32_t)nchunks, d_samples, d_status);
     c->launches += 1;
     CUDA_OK(cudaGetLastError());

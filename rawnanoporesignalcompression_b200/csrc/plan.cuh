@@ -107,17 +107,34 @@ struct PlanParams {
     uint32_t* seq_pool; uint32_t pool_cap; unsigned long long* pool_cursor;   // 64-bit cursor: a hostile batch can ask for more than 2^32 entries; bump-allocated sequence storage (SEQ_WORDS words per entry)
 };
 
-// Per planner thread scratch in shared memory. 161 words: an odd stride, so the same field of the 32 threads of a
+// Per planner thread scratch in shared memory. An odd number of words, so the same field of the 32 threads of a
 // warp falls into 32 different banks. The FSE build temporaries (norm, next16) are dead before the first weight is
 // written, so they share the weights' bytes: a smaller scratch = more planner CTAs per SM.
+// -DRNSC_PLAN_HYBRID: the weights (written once, read once by the sort) and the temporaries of the sequence tables' FSE
+// descriptions live in thread-private local memory instead; the shared scratch keeps the small arrays the serial chains
+// read (the weights' FSE table and its 13-symbol temporaries, the staged description): 460 instead of 652 bytes per thread.
+struct PlanBig { union { uint8_t weights[256]; struct { int16_t norm[64]; uint16_t next16[64]; }; }; };
 struct PlanScratch {
-    union { uint8_t weights[256]; struct { int16_t norm[64]; uint16_t next16[64]; }; };
+#ifndef RNSC_PLAN_HYBRID
+    PlanBig big;
+#endif
     uint32_t fse_w[64];
     // stage: the bytes of a Huffman tree description (<= 127) as words, word 0 = a zero word below them, two more behind them
     // (plan_read_weights); dead before the weight counts are written
     union { struct { uint32_t rank_start[16]; uint32_t rank_cnt[16]; int huf_log; }; uint32_t stage[35]; };
+#ifdef RNSC_PLAN_HYBRID
+    int16_t wnorm[16]; uint16_t wnext[16];      // normalised counts / build temporaries of the weights' FSE table (<= 13 symbols)
+#endif
 };
+#ifdef RNSC_PLAN_HYBRID
+static_assert(sizeof(PlanScratch) == 460, "PlanScratch layout");      // 115 words: odd
+#define RNSC_PLAN_WNORM(sc, bg) ((sc)->wnorm)
+#define RNSC_PLAN_WNEXT(sc, bg) ((sc)->wnext)
+#else
 static_assert(sizeof(PlanScratch) == 652, "PlanScratch layout");      // 163 words: odd
+#define RNSC_PLAN_WNORM(sc, bg) ((bg)->norm)
+#define RNSC_PLAN_WNEXT(sc, bg) ((bg)->next16)
+#endif
 
 __host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 __host__ __device__ inline uint32_t huf_tab_bytes(uint32_t log) { return align16(2u << log); }
@@ -135,9 +152,9 @@ __device__ __forceinline__ uint32_t stage_bits(const uint32_t* stage, uint32_t b
     const uint32_t wi = 1u + (bit >> 5);
     return __funnelshift_r(stage[wi], stage[wi + 1], bit);
 }
-__device__ inline uint32_t plan_read_weights(PlanScratch* sc, const uint8_t* src, uint32_t size, int* nw_out)
+__device__ inline uint32_t plan_read_weights(PlanScratch* sc, PlanBig* bg, const uint8_t* src, uint32_t size, int* nw_out)
 {
-    uint8_t* w = sc->weights; uint32_t nw = 0;
+    uint8_t* w = bg->weights; int16_t* const wnorm = RNSC_PLAN_WNORM(sc, bg); uint16_t* const wnext = RNSC_PLAN_WNEXT(sc, bg); uint32_t nw = 0;
     bool ok = size >= 1;
     const uint32_t hb = ok ? ldg8(src) : 0;
     const bool direct = hb >= 128;
@@ -180,7 +197,7 @@ __device__ inline uint32_t plan_read_weights(PlanScratch* sc, const uint8_t* src
                 int n0 = sym;
                 for (;;) { const uint32_t r = bp < tbits ? stage_bits(sc->stage, bp) & 3u : 0u; bp += 2; n0 += (int)r; if (r != 3 || n0 > 13) break; }
                 if (n0 > 13) { bad = true; break; }
-                while (sym < n0) sc->norm[sym++] = 0;
+                while (sym < n0) wnorm[sym++] = 0;
                 if (sym > 12) break;
             }
             const int mx = (2 * threshold - 1) - remaining;
@@ -190,7 +207,7 @@ __device__ inline uint32_t plan_read_weights(PlanScratch* sc, const uint8_t* src
             else { count = (int)(v & ((1u << nb) - 1u)); if (count >= threshold) count -= mx; bp += nb; }
             count--;
             remaining -= count < 0 ? -count : count;
-            sc->norm[sym++] = (int16_t)count;
+            wnorm[sym++] = (int16_t)count;
             prev0 = count == 0;
             while (remaining < threshold) { nb--; threshold >>= 1; }
         }
@@ -199,7 +216,7 @@ __device__ inline uint32_t plan_read_weights(PlanScratch* sc, const uint8_t* src
         ns = sym;
     }
     warp_converge<true>();
-    if (ok && !direct) fse_build(sc->fse_w, sc->norm, ns, tl, sc->next16);
+    if (ok && !direct) fse_build(sc->fse_w, wnorm, ns, tl, wnext);
     warp_converge<true>();
     // ---- two interleaved FSE states over the backward bitstream, bytes [h, hb) of the description ----
     if (ok && !direct) {
@@ -308,7 +325,7 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
 // `enable` false). Every lane of the warp calls it for every frame (enable = false when the lane has nothing to plan):
 // the body is single-exit so that the warp can reconverge in front of each long loop.
 __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t boff, uint32_t size, FramePlan& fp, ChunkPlan* pl, uint32_t& nhuf, uint32_t& nseq_tot,
-                                 PlanScratch* sc, const uint32_t* deftab, const PlanParams& P)
+                                 PlanScratch* sc, PlanBig* bg, const uint32_t* deftab, const PlanParams& P)
 {
     const uint8_t* src = chunk + boff;
     bool bad = !enable || size < 1;
@@ -354,7 +371,7 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     bool huf = !bad && ltype == 2;
     if (huf && nhuf >= PLAN_MAX_HUF) { bad = true; huf = false; }
     int nw = 0;
-    const uint32_t u = plan_read_weights(sc, src + lhs, huf ? comp : 0u, &nw);
+    const uint32_t u = plan_read_weights(sc, bg, src + lhs, huf ? comp : 0u, &nw);
     if (huf && !u) { bad = true; huf = false; }
     if (huf) {
         uint32_t p = lhs + u, left = comp - u;
@@ -401,9 +418,9 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
         const int lim = huf ? nw : 0;
         // a position is at most 255 when it is used; the increment past the last symbol of the heaviest class may carry
         // into the (unused) field above it
-        // weights are read a word at a time (PlanScratch is 4-byte aligned, weights[] sits at its start and holds 256 bytes)
+        // weights are read a word at a time (PlanBig is 4-byte aligned, weights[] sits at its start and holds 256 bytes)
         for (int i0 = 0; i0 < lim; i0 += 4) {
-            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(sc->weights + i0);
+            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(bg->weights + i0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t w = (w4 >> (8 * j)) & 0xFFu;
@@ -438,10 +455,10 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
                 rle[t] = sym; tab[t] = &rle[t]; tlog[t] = 0;
             } else if (mode == 2) {
                 int tl = 0, ns = 0;
-                const uint32_t h = fse_read_ncount(src + p, size - p, sc->norm, (int)max_sym, t == 1 ? 8 : 9, &tl, &ns);
+                const uint32_t h = fse_read_ncount(src + p, size - p, bg->norm, (int)max_sym, t == 1 ? 8 : 9, &tl, &ns);
                 if (!h) { bad = true; break; }
                 uint32_t* tt = pl->fse + (t == 0 ? 0 : (t == 1 ? 512 : 768));
-                fse_build(tt, sc->norm, ns, tl, sc->next16);
+                fse_build(tt, bg->norm, ns, tl, bg->next16);
                 tab[t] = tt; tlog[t] = tl; p += h;
             } else { bad = true; break; }
         }
@@ -459,7 +476,7 @@ __device__ inline void plan_emit(const PlanParams& P, uint32_t c, uint32_t cls)
     if (cls <= CLS_SLOW) { const uint32_t i = atomicAdd(P.counts + cls, 1u); P.lists[(size_t)cls * P.nchunks + i] = c; }
 }
 
-__device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* sc, const uint32_t* deftab)
+__device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* sc, PlanBig* bg, const uint32_t* deftab)
 {
     ChunkPlan* pl = P.plans + c;
     PlanHead* hd = &pl->head;
@@ -513,7 +530,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
             }
         }
         comp_block = comp_block && !slow;
-        const int pb = plan_block(comp_block, src, pos + hdr + 3, bsz, fp, pl, nhuf, nseq_tot, sc, deftab, P);
+        const int pb = plan_block(comp_block, src, pos + hdr + 3, bsz, fp, pl, nhuf, nseq_tot, sc, bg, deftab, P);
         if (comp_block && pb) slow = true;
         if (st == RNSC_OK && !slow) {
             // placement of the decoded output in the CTA's dynamic region (raw data is used in place; the literals of a
@@ -671,18 +688,22 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_chunks(PlanParams P)
 {
 #ifdef RNSC_PLAN_LOCAL
     PlanScratch local_scratch;                       // thread-private (local memory, L1): occupancy is no longer bound by shared memory
+    PlanScratch* const sc = &local_scratch;
 #else
     __shared__ PlanScratch scratch[PLAN_THREADS];
+    PlanScratch* const sc = &scratch[threadIdx.x];
+#endif
+#ifdef RNSC_PLAN_HYBRID
+    PlanBig big;
+    PlanBig* const bg = &big;
+#else
+    PlanBig* const bg = &sc->big;
 #endif
     __shared__ uint32_t deftab[160];
     for (int i = threadIdx.x; i < 160; i += PLAN_THREADS) deftab[i] = P.deftab[i];
     __syncthreads();
     const uint32_t c = blockIdx.x * PLAN_THREADS + threadIdx.x;
-#ifdef RNSC_PLAN_LOCAL
-    if (c < P.nchunks) plan_chunk(P, c, &local_scratch, deftab);
-#else
-    if (c < P.nchunks) plan_chunk(P, c, &scratch[threadIdx.x], deftab);
-#endif
+    if (c < P.nchunks) plan_chunk(P, c, sc, bg, deftab);
 }
 
 }  // namespace rnsc
