@@ -820,7 +820,7 @@ def main():
     ap.add_argument("--model", default="R10.4.1", choices=["R10.4.1", "R9.4.1"])
     ap.add_argument("--cpu-reads", type=int, default=1000, help="reads in the bounded CPU sample (>= 1000 chunks: also the encode byte-parity sample)")
     ap.add_argument("--vbz-reads", type=int, default=0, help="reads per GPU of the R9.4.1 VBZ leg (0 = --reads)")
-    ap.add_argument("--rc-reads", type=int, default=2000, help="reads per GPU of the range coder leg")
+    ap.add_argument("--rc-reads", type=int, default=16000, help="reads per GPU of the range coder leg")
     ap.add_argument("--seam-reads", type=int, default=200, help="reads of the per-chunk seam leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-reads", type=int, default=0)

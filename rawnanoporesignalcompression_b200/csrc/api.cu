@@ -587,7 +587,10 @@ int rnsc_dev_encode(rnsc_ctx* c, int codec, const int16_t* d_samples, const uint
     const int wide = (int)nchunks, emit_grid = (int)nchunks;
 #endif
     RNSC_LAUNCH(k_zenc_histogram, wide, ZE_NT, 0, st, zp);
-    RNSC_LAUNCH(k_zenc_build, (int)std::min<size_t>((nchunks * nf + ZE_BUILD_WARPS * ZE_BUILD_SLOTS - 1) / (ZE_BUILD_WARPS * ZE_BUILD_SLOTS), (size_t)c->sm_count * 16), 32 * ZE_BUILD_WARPS, ZE_BUILD_SMEM, st, zp);
+    // one round (ZE_BUILD_SLOTS consecutive frames) per warp, dealt out by the block scheduler: a round costs anything between
+    // nothing (raw frames) and four 256-symbol trees (a persistent grid with a fixed stride: 2.5 % slower on the 20k-read C5 set.
+    // Tried: rounds of one frame KIND, so that the four serial lanes are all busy with trees of one size -- no gain)
+    RNSC_LAUNCH(k_zenc_build, (int)((nchunks * nf + ZE_BUILD_WARPS * ZE_BUILD_SLOTS - 1) / (ZE_BUILD_WARPS * ZE_BUILD_SLOTS)), 32 * ZE_BUILD_WARPS, ZE_BUILD_SMEM, st, zp);
     RNSC_LAUNCH(k_zenc_emit, emit_grid, ZE_NT, 0, st, zp);
     RNSC_LAUNCH(k_exclusive_scan_u32, 1, NT, 0, st, (const uint32_t*)c->d_zout_sz.p, (unsigned long long)nchunks, (unsigned long long*)d_comp_off);
     RNSC_LAUNCH(k_zenc_gather, wide, ZE_NT, 0, st, (const uint8_t*)c->d_zslots.p, (const uint64_t*)c->d_zslot_off.p, (const uint64_t*)d_comp_off, (uint32_t)nchunks, d_comp,
