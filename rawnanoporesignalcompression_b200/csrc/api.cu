@@ -198,7 +198,10 @@ int launch_decode(rnsc_ctx* c, int codec, const uint8_t* d_comp, const uint64_t*
         if (seen[1]) { const size_t d = (size_t)((seen[0] + seen[1] - 1) / seen[1]); c->pool_per_chunk[lz_heavy] = std::max(c->pool_per_chunk[lz_heavy], d + d / 4 + 1); }
     }
     per_chunk = std::max(per_chunk, c->pool_per_chunk[lz_heavy]);
-    size_t pool_cap = nchunks * per_chunk + 4096;
+    // A floor of 2^20 entries (32 MiB) whatever the estimate says: the first call of a context on frames of another writer
+    // (zstd level 9: thousands of sequences in a C5 frame that level 1 writes without any) has no learned demand yet, and a
+    // small batch should not fall to the general decoder for a few KB of pool.
+    size_t pool_cap = std::max<size_t>(nchunks * per_chunk, (size_t)1 << 20) + 4096;
     if (comp_bytes_hint) pool_cap = std::min(pool_cap, std::max<size_t>(comp_bytes_hint / 8, nchunks * 16) + 4096);   // a sequence costs more than a byte in any real frame
     if (c->d_seqpool.reserve(pool_cap * SEQ_WORDS * sizeof(uint32_t))) return fail(RNSC_ERR_NO_DEVICE, "cudaMalloc(sequence pool) failed");
     if (!c->h_pool_seen.p) { if (c->h_pool_seen.reserve(64)) return fail(RNSC_ERR_NO_DEVICE, "cudaMallocHost(pool demand) failed"); memset(c->h_pool_seen.p, 0, 64); }

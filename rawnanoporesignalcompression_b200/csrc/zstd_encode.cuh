@@ -31,6 +31,10 @@
 namespace rnsc {
 
 constexpr int ZE_NT = 256;                       // threads per CTA of the histogram / emit kernels
+#ifndef RNSC_ZE_EMIT_CTAS
+#define RNSC_ZE_EMIT_CTAS 6
+#endif
+constexpr int ZE_EMIT_CTAS = RNSC_ZE_EMIT_CTAS;   // resident emit CTAs per SM the register allocation aims at
 constexpr uint32_t ZE_BLOCK_MAX = 128u << 10;    // Block_Maximum_Size
 constexpr uint32_t ZE_HUF_MIN = 64;              // shorter frames are not worth a tree description: raw
 constexpr uint32_t ZE_LOG_MAX = 11;              // HUF_TABLELOG_DEFAULT of the literals' Huffman codes
@@ -552,7 +556,7 @@ struct ZencWs {
     uint16_t code[256];
 };
 
-__global__ void __launch_bounds__(ZE_NT) k_zenc_emit(ZencParams P)
+__global__ void __launch_bounds__(ZE_NT, ZE_EMIT_CTAS) k_zenc_emit(ZencParams P)
 {
     __shared__ ZencWs ws;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

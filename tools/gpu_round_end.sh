@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 TAG=${1:-r2_final}
 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/${TAG}_tests.log
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python tools/foreign_routing.py > gpurun_out/${TAG}_foreign_routing.txt 2>&1; echo "foreign routing rc=$?"
 SECONDS=0
 python bench.py > gpurun_out/${TAG}_n1.json 2> gpurun_out/${TAG}_n1.err; echo "bench rc=$? ${SECONDS}s"
 head -c 400 gpurun_out/${TAG}_n1.json; echo
