@@ -489,6 +489,8 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     const uint32_t stage = align16(phase + clen);
     const uint32_t cbase = REGION_HEAD + phase;                    // region offset of chunk byte 0
     uint32_t region = REGION_HEAD + stage + 16, pos = 0, nhuf = 0, nseq_tot = 0;
+    uint32_t meta_bytes = 0;                                       // run tables of the frames with sequences
+    uint32_t hlog[PLAN_MAX_HUF] = {0, 0, 0};                       // table logs: kept here, not read back from the plan in global memory
     int st = RNSC_OK; bool slow = false;
     // Uniform frame loop: every lane runs all nf iterations (a lane whose chunk already failed just idles through
     // them), so that the warp can reconverge at the marked points.
@@ -537,6 +539,11 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
             // frame with sequences are written straight to their final positions)
             const bool zero_copy = fp.kind == FK_RAW || (fp.kind == FK_COMP && fp.ltype == 0 && fp.nseq == 0);
             if (!zero_copy) { fp.dst_off = region; region += align16(fp.fcs) + 16; }
+            if (fp.kind == FK_COMP && fp.nseq) meta_bytes += seq_meta_bytes(fp.nseq);
+            if (fp.kind == FK_COMP && fp.ltype == 2) {
+#pragma unroll
+                for (int h = 0; h < PLAN_MAX_HUF; ++h) if ((uint32_t)h == fp.huf) hlog[h] = (uint32_t)sc->huf_log;      // plan_read_weights left it there
+            }
             pl->f[f] = fp;
         }
         if (st == RNSC_OK) pos += fl;
@@ -544,16 +551,20 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     if (st != RNSC_OK) { P.status[c] = st; plan_emit(P, c, CLS_DONE); return; }
     if (slow) { plan_emit(P, c, CLS_SLOW); return; }
     // ---- Huffman tables live in the region too ----
-    for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].tab_off = region; pl->h[h].skip_off = 0; region += huf_tab_bytes(pl->h[h].log); }
+    uint32_t htab[PLAN_MAX_HUF] = {0, 0, 0}, hskip[PLAN_MAX_HUF] = {0, 0, 0};
+#pragma unroll
+    for (int h = 0; h < PLAN_MAX_HUF; ++h) if ((uint32_t)h < nhuf) { htab[h] = region; pl->h[h].tab_off = region; region += huf_tab_bytes(hlog[h]); }
     uint32_t meta = region;                                      // run tables of the frames with sequences
-    for (int f = 0; f < nf; ++f) { const FramePlan& q = pl->f[f]; if (q.kind == FK_COMP && q.nseq) region += seq_meta_bytes(q.nseq); }
-    if (slow) { plan_emit(P, c, CLS_SLOW); return; }
+    region += meta_bytes;
     const uint32_t cls = region <= P.region[0] ? CLS_S : (region <= P.region[1] ? CLS_A : (region <= P.region[2] ? CLS_B : CLS_SLOW));
     if (cls == CLS_SLOW) { plan_emit(P, c, CLS_SLOW); return; }
     {   // skip tables (pass 1 strides over several symbols per access) go behind everything else, if the class has room for them
         uint32_t r2 = region;
-        for (uint32_t h = 0; h < nhuf; ++h) r2 += huf_skip_bytes(pl->h[h].log);
-        if (r2 <= P.region[cls]) for (uint32_t h = 0; h < nhuf; ++h) { pl->h[h].skip_off = region; region += huf_skip_bytes(pl->h[h].log); }
+#pragma unroll
+        for (int h = 0; h < PLAN_MAX_HUF; ++h) if ((uint32_t)h < nhuf) r2 += huf_skip_bytes(hlog[h]);
+        const bool room = r2 <= P.region[cls];
+#pragma unroll
+        for (int h = 0; h < PLAN_MAX_HUF; ++h) if ((uint32_t)h < nhuf) { if (room) { hskip[h] = region; region += huf_skip_bytes(hlog[h]); } pl->h[h].skip_off = hskip[h]; }
     }
     const uint32_t nth = class_threads(cls);
     hd->lut_off = 0;
@@ -564,7 +575,11 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     // ---- the kernel's program: Huffman streams, fills, sequence ops, views ----
     uint32_t nst = 0, ttot = 0, nfill = 0, nsop = 0, zone_off = 0, zone_len = 0;
     uint32_t sruns[PLAN_MAX_STREAMS];                  // literal runs per Huffman stream (0 without sequences)
-    for (int s = 0; s < PLAN_MAX_STREAMS; ++s) sruns[s] = 0;
+    uint32_t stb[PLAN_MAX_STREAMS], stc[PLAN_MAX_STREAMS];   // payload bits / symbols per stream (thread-private copies: hd->st lives in global memory)
+    for (int s = 0; s < PLAN_MAX_STREAMS; ++s) { sruns[s] = 0; stb[s] = 0; stc[s] = 0; }
+    // thread groups of the Huffman stage = the Huffman-coded frames in order (fp.huf counts them): bits, symbols, streams, first stream, runs
+    uint32_t gt[PLAN_MAX_HUF] = {0, 0, 0}, gc[PLAN_MAX_HUF] = {0, 0, 0}, gn[PLAN_MAX_HUF] = {0, 0, 0}, gs0[PLAN_MAX_HUF] = {0, 0, 0}, gr[PLAN_MAX_HUF] = {0, 0, 0};
+    uint32_t ngrp = 0;
     int vst = RNSC_OK;
     const uint32_t kl = key_len(P.codec, n);
     uint32_t tot_fcs = 0;
@@ -580,15 +595,22 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         if (fp.kind == FK_COMP && fp.ltype == 2) {
             if (fp.hz_len > zone_len + 16) { const uint32_t z0 = align16(cbase + fp.hz_off); zone_off = z0; zone_len = cbase + fp.hz_off + fp.hz_len - z0; }
             const uint32_t q = (fp.regen + 3) / 4;
+            uint32_t f_tab = 0, f_skip = 0, f_log = 0;
+#pragma unroll
+            for (int h = 0; h < PLAN_MAX_HUF; ++h) if ((uint32_t)h == fp.huf) { f_tab = htab[h]; f_skip = hskip[h]; f_log = hlog[h]; }
+            const uint32_t g = ngrp++;                            // == fp.huf
+            gs0[g] = nst;
             for (uint32_t j = 0; j < fp.nstreams; ++j) {
                 StreamPlan sp;
                 sp.tbits = fp.s_tbits[j]; sp.abit = 8 * (cbase + fp.s_beg[j]) + fp.s_tbits[j];
                 sp.count = fp.nstreams == 1 ? fp.regen : (j < 3 ? q : fp.regen - 3 * q);
                 sp.out = fp.dst_off; sp.lit0 = fp.nstreams == 1 ? 0 : j * q;
-                sp.tab_off = pl->h[fp.huf].tab_off; sp.skip_off = pl->h[fp.huf].skip_off; sp.log = pl->h[fp.huf].log;
+                sp.tab_off = f_tab; sp.skip_off = f_skip; sp.log = f_log;
                 sp.sop = my_sop; sp.regen = fp.regen; sp.pitch = 2; sp.sub = 0;
                 if (sp.tbits == 0 && sp.count != 0) slow = true;   // nothing to decode from: the general decoder reports it
                 sruns[nst] = fp.nseq ? fp.s_runs[j] : 0u;
+                stb[nst] = sp.tbits; stc[nst] = sp.count;
+                gt[g] += sp.tbits; gc[g] += sp.count; gn[g] += 1; gr[g] += sruns[nst];
                 hd->st[nst++] = sp; ttot += sp.tbits;
             }
         }
@@ -621,12 +643,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     // (many symbols per bit: long second pass) do not hold up the others. Warps are dealt out in proportion to each
     // frame's estimated cost, cost_bit per payload bit (first pass) + cost_sym per symbol (second pass); the warm-up is the
     // same for every thread and drops out.
-    uint32_t gw[PLAN_MAX_HUF] = {0, 0, 0}, gt[PLAN_MAX_HUF] = {0, 0, 0}, gc[PLAN_MAX_HUF] = {0, 0, 0}, gn[PLAN_MAX_HUF] = {0, 0, 0}, gs0[PLAN_MAX_HUF] = {0, 0, 0}, gr[PLAN_MAX_HUF] = {0, 0, 0};
-    uint32_t ngrp = 0;
-    for (uint32_t s = 0; s < nst; ++s) {
-        if (s == 0 || hd->st[s].tab_off != hd->st[s - 1].tab_off) { gs0[ngrp] = s; ++ngrp; }
-        gt[ngrp - 1] += hd->st[s].tbits; gc[ngrp - 1] += hd->st[s].count; gn[ngrp - 1] += 1; gr[ngrp - 1] += sruns[s];
-    }
+    uint32_t gw[PLAN_MAX_HUF] = {0, 0, 0};
     {
         const uint32_t nw = nth_h / 32;
         unsigned long long wsum = 0, wg[PLAN_MAX_HUF];
@@ -651,19 +668,19 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
             // a frame with LZ sequences: the streams whose literals are cut into many runs (VBZ: the key region, at the start of
             // the first stream) decode slower in the second pass; threads are dealt out to the streams by cost, not by bits
             unsigned long long wsm = 0, wst[4] = {0, 0, 0, 0};
-            for (uint32_t k = 0; k < gn[g] && k < 4; ++k) { const StreamPlan& sp = hd->st[gs0[g] + k];
-                wst[k] = (unsigned long long)P.cost_bit * sp.tbits + (unsigned long long)P.cost_sym * sp.count + (unsigned long long)P.cost_run * sruns[gs0[g] + k] + 1; wsm += wst[k]; }
+            for (uint32_t k = 0; k < gn[g] && k < 4; ++k) { const uint32_t s = gs0[g] + k;
+                wst[k] = (unsigned long long)P.cost_bit * stb[s] + (unsigned long long)P.cost_sym * stc[s] + (unsigned long long)P.cost_run * sruns[s] + 1; wsm += wst[k]; }
             for (uint32_t k = 0; k < gn[g] && k < 4; ++k) {
                 const uint32_t s = gs0[g] + k;
                 uint32_t ts = (uint32_t)((wst[k] * nt) / wsm); if (ts < 1) ts = 1;
-                uint32_t ss = (hd->st[s].tbits + ts - 1) / ts;
+                uint32_t ss = (stb[s] + ts - 1) / ts;
                 if (ss < PLAN_SUB_MIN) ss = PLAN_SUB_MIN;
                 if (cls == CLS_B) ss = ((ss + 31u) >> 5 | 1u) << 5;
                 if (ss > sub_max) sub_max = ss;
-                hd->st[s].sub = ss; hd->st_first[s] = t; t += (hd->st[s].tbits + ss - 1) / ss;
+                hd->st[s].sub = ss; hd->st_first[s] = t; t += (stb[s] + ss - 1) / ss;
             }
         } else
-            for (uint32_t s = gs0[g]; s < gs0[g] + gn[g]; ++s) { hd->st[s].sub = sub; hd->st_first[s] = t; t += (hd->st[s].tbits + sub - 1) / sub; }
+            for (uint32_t s = gs0[g]; s < gs0[g] + gn[g]; ++s) { hd->st[s].sub = sub; hd->st_first[s] = t; t += (stb[s] + sub - 1) / sub; }
         first += nt;
     }
     hd->grp_first[PLAN_MAX_HUF] = first;
