@@ -11,6 +11,7 @@
 // owns the exact error semantics. Replaces, with the fast kernel, the reference's ZSTD_getFrameContentSize +
 // ZSTD_decompress calls (signal_compression.cpp:103,117; C5.hpp:494-565,588-655).
 #pragma once
+#include <cstddef>
 #include "zstd_decode.cuh"
 
 namespace rnsc {
@@ -47,6 +48,33 @@ struct FramePlan {               // planner-internal description of one frame
     uint32_t s_beg[4], s_tbits[4];   // Huffman streams: chunk offset of the first byte; payload bits below the end mark
     uint32_t s_runs[4];              // non-empty literal runs that start inside each stream's literals (frames with sequences)
 };
+// A FramePlan travels through the plan's global scratch between the two frame loops of plan_chunk: only the fields its kind
+// of frame uses are stored and read back (raw / RLE frames: 4 words; Huffman literals: + the stream geometry; + the runs per
+// stream when LZ sequences follow) -- every word is a 32-sector access for the warp.
+__device__ __forceinline__ void frame_store(FramePlan* g, const FramePlan& fp)
+{
+    g->kind = fp.kind; g->fcs = fp.fcs; g->data_off = fp.data_off; g->dst_off = fp.dst_off;
+    if (fp.kind != FK_COMP) return;
+    g->ltype = fp.ltype; g->regen = fp.regen; g->lit_off = fp.lit_off; g->nstreams = fp.nstreams; g->huf = fp.huf;
+    g->nseq = fp.nseq; g->seq_base = fp.seq_base; g->nruns = fp.nruns;
+    if (fp.ltype != 2) return;
+    g->hz_off = fp.hz_off; g->hz_len = fp.hz_len;
+    for (int j = 0; j < 4; ++j) { g->s_beg[j] = fp.s_beg[j]; g->s_tbits[j] = fp.s_tbits[j]; }
+    if (fp.nseq) for (int j = 0; j < 4; ++j) g->s_runs[j] = fp.s_runs[j];
+}
+__device__ __forceinline__ void frame_load(FramePlan& fp, const FramePlan* g)
+{
+    fp.kind = g->kind; fp.fcs = g->fcs; fp.data_off = g->data_off; fp.dst_off = g->dst_off;
+    fp.ltype = 0; fp.regen = 0; fp.lit_off = 0; fp.nstreams = 0; fp.huf = 0; fp.nseq = 0; fp.seq_base = 0; fp.nruns = 0; fp.hz_off = 0; fp.hz_len = 0;
+    for (int j = 0; j < 4; ++j) { fp.s_beg[j] = 0; fp.s_tbits[j] = 0; fp.s_runs[j] = 0; }
+    if (fp.kind != FK_COMP) return;
+    fp.ltype = g->ltype; fp.regen = g->regen; fp.lit_off = g->lit_off; fp.nstreams = g->nstreams; fp.huf = g->huf;
+    fp.nseq = g->nseq; fp.seq_base = g->seq_base; fp.nruns = g->nruns;
+    if (fp.ltype != 2) return;
+    fp.hz_off = g->hz_off; fp.hz_len = g->hz_len;
+    for (int j = 0; j < 4; ++j) { fp.s_beg[j] = g->s_beg[j]; fp.s_tbits[j] = g->s_tbits[j]; }
+    if (fp.nseq) for (int j = 0; j < 4; ++j) fp.s_runs[j] = g->s_runs[j];
+}
 struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decoding table
     uint32_t log;                // table log (max code length), <= 12
     uint32_t tab_off;            // region offset of the table (2^log entries of 2 bytes)
@@ -56,6 +84,8 @@ struct HufPlan {                 // recipe of a HUF_readDTableX1-ordered decodin
     uint16_t cls_sym[14];        // index into sorted[] of the first symbol of class w
     uint8_t sorted[256];         // symbols of weight > 0 ordered by (weight, symbol)
 };
+static_assert(offsetof(HufPlan, cls_start) % 4 == 0 && offsetof(HufPlan, cls_sym) % 4 == 0 && offsetof(HufPlan, sorted) % 4 == 0 && sizeof(HufPlan) % 4 == 0,
+              "the planner stores these arrays as 32-bit words");
 // One Huffman bitstream: payload bits, absolute bit address of the end mark in the region, symbols, region offset of
 // the frame's output, literal index of its first symbol, its table; and, when LZ sequences follow, where they are in
 // ChunkPlan::seq, so that every literal is written straight to its final place between the matches.
@@ -399,21 +429,33 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
     // table recipe: weight classes in ascending weight (= descending code length), symbols in natural order
     HufPlan* hp = &pl->h[huf ? nhuf : 0];
     unsigned long long p_lo = 0, p_hi = 0;           // running insert position of every class, 8-bit fields (weights 0-7, 8-15)
+    uint32_t nsym = 0;                               // symbols of weight > 0
     if (huf) {
         const int maxBits = sc->huf_log;
-        uint32_t e = 0, s = 0;                       // plan_read_weights left the per-weight symbol counts in rank_cnt
-        for (int k = 1; k <= maxBits; ++k) {
-            hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s;
-            const uint32_t cnt = sc->rank_cnt[k];
-            if (cnt) hp->lmin = (uint32_t)(maxBits + 1 - k);
-            if (k & 8) p_hi |= (unsigned long long)(s & 0xFFu) << ((k & 7) * 8); else p_lo |= (unsigned long long)(s & 0xFFu) << ((k & 7) * 8);
-            e += cnt << (k - 1); s += cnt;
+        uint32_t e = 0, s = 0, lmin = 0;             // plan_read_weights left the per-weight symbol counts in rank_cnt
+        uint32_t cs[14], cy[14];                     // class starts / first sorted index: built in registers, stored as 7 + 7 words
+        cs[0] = 0; cy[0] = 0;
+#pragma unroll
+        for (int k = 1; k < 14; ++k) {
+            cs[k] = e; cy[k] = s;                    // classes above maxBits: e == 2^maxBits, s == all symbols
+            if (k <= maxBits) {
+                const uint32_t cnt = sc->rank_cnt[k];
+                if (cnt) lmin = (uint32_t)(maxBits + 1 - k);
+                if (k & 8) p_hi |= (unsigned long long)(s & 0xFFu) << ((k & 7) * 8); else p_lo |= (unsigned long long)(s & 0xFFu) << ((k & 7) * 8);
+                e += cnt << (k - 1); s += cnt;
+            }
         }
-        hp->cls_start[0] = 0; hp->cls_sym[0] = 0;
-        for (int k = maxBits + 1; k < 14; ++k) { hp->cls_start[k] = (uint16_t)e; hp->cls_sym[k] = (uint16_t)s; }   // e == 2^maxBits
-        hp->log = (uint32_t)maxBits;
+        uint32_t* const w_start = (uint32_t*)hp->cls_start; uint32_t* const w_sym = (uint32_t*)hp->cls_sym;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) { w_start[i] = cs[2 * i] | (cs[2 * i + 1] << 16); w_sym[i] = cy[2 * i] | (cy[2 * i + 1] << 16); }
+        hp->lmin = lmin; hp->log = (uint32_t)maxBits;
+        nsym = s;
     }
     warp_converge<true>();
+    // The symbols are scattered into the (dead by now) FSE table of the weights in shared memory and leave as whole words:
+    // a byte store per symbol straight into the plan was 512 of the ~800 global store instructions of a chunk, each one 32
+    // sectors wide across the warp (the plans of the 32 chunks of a warp lie 7.6 KB apart).
+    uint8_t* const srt = (uint8_t*)sc->fse_w;
     {
         const int lim = huf ? nw : 0;
         // a position is at most 255 when it is used; the increment past the last symbol of the heaviest class may carry
@@ -427,11 +469,15 @@ __device__ inline int plan_block(bool enable, const uint8_t* chunk, uint32_t bof
                 if (w && i0 + j < lim) {
                     const uint32_t sh = (w & 7u) * 8u;
                     const uint32_t pos = (uint32_t)(((w & 8u) ? p_hi : p_lo) >> sh) & 0xFFu;
-                    hp->sorted[pos] = (uint8_t)(i0 + j);
+                    srt[pos] = (uint8_t)(i0 + j);
                     if (w & 8u) p_hi += 1ull << sh; else p_lo += 1ull << sh;
                 }
             }
         }
+    }
+    if (huf) {
+        uint32_t* const dst = (uint32_t*)hp->sorted;
+        for (uint32_t i = 0; 4 * i < nsym; ++i) dst[i] = sc->fse_w[i];
     }
     if (huf) fp.huf = nhuf++;
     warp_converge<true>();
@@ -544,7 +590,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
 #pragma unroll
                 for (int h = 0; h < PLAN_MAX_HUF; ++h) if ((uint32_t)h == fp.huf) hlog[h] = (uint32_t)sc->huf_log;      // plan_read_weights left it there
             }
-            pl->f[f] = fp;
+            frame_store(&pl->f[f], fp);
         }
         if (st == RNSC_OK) pos += fl;
     }
@@ -584,7 +630,7 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     const uint32_t kl = key_len(P.codec, n);
     uint32_t tot_fcs = 0;
     for (int f = 0; f < nf; ++f) {
-        const FramePlan fp = pl->f[f];
+        FramePlan fp; frame_load(fp, &pl->f[f]);
         uint32_t data;                                         // region offset of the frame's decoded bytes
         if (fp.kind == FK_RAW) data = cbase + fp.data_off;
         else if (fp.kind == FK_COMP && fp.ltype == 0 && fp.nseq == 0) data = cbase + fp.lit_off;
