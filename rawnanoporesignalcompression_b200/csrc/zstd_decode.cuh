@@ -147,7 +147,11 @@ __device__ __forceinline__ uint32_t bwd_bits32(BwdBits& b, uint32_t bit)      //
 {
     const uintptr_t a = (uintptr_t)b.start + (bit >> 3), al = a & ~(uintptr_t)3;
     if (al != b.wa) {
-        if (al + 4 == b.wa) { b.w1 = b.w0; b.w0 = ldg32((const uint32_t*)al); }
+        if (al + 4 == b.wa) {
+            b.w1 = b.w0; b.w0 = ldg32((const uint32_t*)al);
+            // the stream is read towards its start: entering a sector, ask for the one below it (never below the stream's own first sector)
+            if ((al & 28u) == 28u) { const uintptr_t lowest = (uintptr_t)b.start & ~(uintptr_t)31; if (al - 28 > lowest) prefetch_sector((const void*)(al - 60)); }
+        }
         else { b.w0 = ldg32((const uint32_t*)al); b.w1 = ldg32((const uint32_t*)(al + 4)); }
         b.wa = al;
     }
