@@ -65,6 +65,7 @@ struct FastWs {
     uint32_t warp_tot[NTH / 32];
     uint32_t skip_on;                          // this chunk's Huffman tables have skip tables
     uint32_t stash_tag;                        // chunk whose plan words wait in the stash (sub_end/sub_inc, idle between two Huffman stages)
+    uint32_t stash_bad;                        // a thread fetched its share of the stash for another chunk than stash_tag (see fast_huffman): not usable
     Unpack2Ws<NTH> u2;
     PlanHead head;
     HufPlan h[PLAN_MAX_HUF];
@@ -135,6 +136,7 @@ __device__ inline bool bar_named_or(uint32_t id, uint32_t nthreads, bool pred)
 // `nthr` threads (t = 0 .. nthr-1) build this table. The weight class of an entry is found by counting class starts
 // <= the entry in registers (the starts are 14 halfwords, fetched as 7 broadcast words); a group of 8 entries that
 // lies in one class of code length <= L - 3 is one symbol (runs are 2^(w-1) >= 8 entries long and aligned).
+// (Tried: groups inside ONE light class -- 1, 2 or 4 entries per symbol -- without the class search per entry: no change.)
 __device__ __forceinline__ void fast_build_table(uint16_t* tab, const HufPlan* hp, int t, int nthr)
 {
     const uint32_t L = hp->log, size = 1u << L;
@@ -509,11 +511,17 @@ __device__ RNSC_NOINLINE int fast_huffman(FastWs<NTH>* ws, uint8_t* region, cons
         }
     }
     const int r = __syncthreads_or(bad);
-    if (nx != FAST_NONE) {
+    // The one-CTA-per-SM class writes ws->next from inside the Huffman stage (fast_decode_chunk), ordered before the reads
+    // above only for the threads of the writer's own group: a thread of another group may have fetched for the previous value.
+    // Behind the CTA-wide barrier the word is stable: a thread that fetched for another chunk parks nothing and marks the stash
+    // unusable (the next chunk then reads its plan from global memory: slower, never wrong).
+    const uint32_t nx_now = ws->next;
+    if (nx != nx_now) ws->stash_bad = 1u;
+    else if (nx != FAST_NONE) {
 #pragma unroll
         for (int q = 0; q < PF; ++q) { const uint32_t idx = (uint32_t)tid + (uint32_t)q * NTH; if (idx < ST_WORDS) ws->sub_end[idx] = pf[q]; }   // sub_end and sub_inc are contiguous
-        if (tid == 0) ws->stash_tag = nx;
     }
+    if (tid == 0 && nx_now != FAST_NONE) ws->stash_tag = nx_now;
     pc.mark(PH_HUF2);
     return r;
 }
@@ -697,7 +705,7 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
     const int tid = threadIdx.x;
     const ChunkPlan* pl = P.plans + c;
     // ---- stage the compressed chunk (async) while the plan is copied and the tables are built ----
-    const bool parked = ws->stash_tag == c;          // the previous chunk's Huffman stage fetched this chunk's plan
+    const bool parked = ws->stash_tag == c && !ws->stash_bad;   // the previous chunk's Huffman stage fetched this chunk's plan
     const uint32_t* stash = ws->sub_end;
     const PlanHead* hsrc = parked ? (const PlanHead*)stash : &pl->head;
     if (tid == 0) {
@@ -707,10 +715,18 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
         ws->status = RNSC_OK;
         bulk_load(region + REGION_HEAD, gsrc - phase, hsrc->stage_bytes, &ws->mbar);
     }
+    // Next chunk index (classes with several CTAs per SM; the one-CTA class leaves it to a spare warp, below): three dependent
+    // global round trips -- the ticket, the list length, the list entry. Thread 0 takes the ticket here and reads the entry
+    // behind the barrier; the value is only stored once its share of the tables is built, so nobody waits for the round trips
+    // (they used to sit between the barrier and thread 0's table entries, with the rest of the CTA waiting at the next barrier).
+    constexpr bool CHAIN_LATE = NTH == 1024;
+    uint32_t ticket = 0, next_c = FAST_NONE;
+    if (!CHAIN_LATE && tid == 0) ticket = atomicAdd(P.counter, 1u);
     if (tid == 32) {      // where the samples go and how many (read by the splitter inverse)
         ws->n = parked ? stash[ST_N] : P.n[c];
         ws->sample_off = parked ? ((unsigned long long)stash[ST_SOFF + 1] << 32 | stash[ST_SOFF]) : P.sample_off[c];
     }
+    uint2 run_v = make_uint2(0u, 0u); uint32_t run_off = FAST_NONE;      // this thread's run-table entry on its way from the sequence pool
     {
         const uint32_t* s = (const uint32_t*)hsrc; uint32_t* d = (uint32_t*)&ws->head;
         for (uint32_t i = tid; i < sizeof(PlanHead) / 4; i += NTH) d[i] = s[i];
@@ -720,15 +736,29 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
         // run tables of the frames with sequences: {first literal index, shift} of every non-empty literal run. They are
         // first read in the second Huffman pass: with few sequences the one-CTA-per-SM class leaves the (global memory
         // latency of the) copy to its spare last warp, below
-        if (!(NTH == 1024 && hsrc->nseq <= FAST_ORDERED_MAX)) copy_run_tables(hsrc, P.seq_pool, region, tid, NTH);
+        // ... the other classes fetch a handful of runs (C5: the large values' high bytes) into registers here and store them
+        // when the tables are built: the round trip to the sequence pool is not waited for at the barrier below
+        if (hsrc->nseq > FAST_ORDERED_MAX) copy_run_tables(hsrc, P.seq_pool, region, tid, NTH);
+        else if (NTH != 1024) {
+            uint32_t idx = (uint32_t)tid;                         // at most FAST_ORDERED_MAX + 5 runs in all: one per thread
+            for (uint32_t k = 0; k < hsrc->nsop; ++k) {
+                const uint32_t nr = hsrc->sop[k].nruns;
+                if (idx < nr) {
+                    const uint32_t* g = P.seq_pool + (size_t)SEQ_WORDS * hsrc->sop[k].seq_base + SEQ_WORDS * idx;
+                    run_v = make_uint2(g[6], g[7]); run_off = hsrc->sop[k].meta_off + 8u * idx;
+                    break;
+                }
+                idx -= nr;
+            }
+        }
     }
     __syncthreads();
+    if (tid == 0) ws->stash_bad = 0u;                // every thread has read it (`parked`); set again only behind later barriers
     // prefetch the next chunk index while this one is decoded
     // Three dependent global round trips. With four or two CTAs per SM thread 0 takes them here and the other CTAs cover
     // the stall; the one-CTA-per-SM class gives them to its last warp, which the planner keeps free of Huffman sub-sequences
     // (see below), so that nobody waits for them.
-    constexpr bool CHAIN_LATE = NTH == 1024;
-    if (!CHAIN_LATE && tid == 0) { const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
+    if (!CHAIN_LATE && tid == 0) next_c = ticket < *P.count ? P.list[ticket] : FAST_NONE;
     const PlanHead& hd = ws->head;
     {   // all tables at once: the CTA's threads are split evenly over them
         const uint32_t nhuf = hd.nhuf;
@@ -760,6 +790,8 @@ __device__ inline void fast_decode_chunk(FastWs<NTH>* ws, uint8_t* region, const
         for (uint32_t i = tid; i < 256u * LR; i += NTH) rep[i] = one[i / LR];
     }
     for (uint32_t i = 0; i < hd.nfill; ++i) { uint8_t* d = region + hd.fill[i].dst_off; for (uint32_t q = tid; q < hd.fill[i].len; q += NTH) d[q] = (uint8_t)hd.fill[i].value; }
+    if (run_off != FAST_NONE) *(uint2*)(region + run_off) = run_v;
+    if (!CHAIN_LATE && tid == 0) ws->next = next_c;
     mbar_wait(&ws->mbar, parity);
     __syncthreads();
     pc.mark(PH_STAGE);

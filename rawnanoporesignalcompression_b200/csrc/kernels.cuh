@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) k_decode_fast(FastParams P)
     KeyLut* lut = (KeyLut*)(smem + ((sizeof(FastWs<NTH>) + 15) & ~(size_t)15));
     uint8_t* region = (uint8_t*)lut + unpack2_lut_bytes(P.codec);
     const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(&ws->mbar, 1); ws->stash_tag = FAST_NONE; const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
+    if (tid == 0) { mbar_init(&ws->mbar, 1); ws->stash_tag = FAST_NONE; ws->stash_bad = 0u; const uint32_t i = atomicAdd(P.counter, 1u); ws->next = i < *P.count ? P.list[i] : FAST_NONE; }
     unpack2_init<NTH>(P.codec, lut);
     __syncthreads();
     uint32_t parity = 0;

@@ -747,7 +747,10 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
     plan_emit(P, c, cls);
 }
 
-__global__ void __launch_bounds__(PLAN_THREADS) k_plan_chunks(PlanParams P)
+#ifndef RNSC_PLAN_MINCTAS
+#define RNSC_PLAN_MINCTAS 1
+#endif
+__global__ void __launch_bounds__(PLAN_THREADS, RNSC_PLAN_MINCTAS) k_plan_chunks(PlanParams P)
 {
 #ifdef RNSC_PLAN_LOCAL
     PlanScratch local_scratch;                       // thread-private (local memory, L1): occupancy is no longer bound by shared memory
