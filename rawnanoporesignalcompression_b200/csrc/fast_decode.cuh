@@ -353,7 +353,7 @@ __device__ __forceinline__ uint32_t stash_fetch(const FastParams& P, uint32_t c,
 }
 
 // Decodes every Huffman stream of the chunk (ws->head.st[]) from the staged chunk into the region. The threads of one
-// Huffman-coded frame form a group of whole warps (PlanHead::grp_first) that synchronises on its own named barrier
+// Huffman-coded frame (or of one stream of a frame with LZ sequences) form a group of whole warps (PlanHead::grp_mask) that synchronises on its own named barrier
 // between the passes: a frame of short codes (many symbols per bit, long second pass) does not hold up the others, and
 // the CTA meets again only at the end. Returns 0 on success (same value in all threads).
 template <int NTH>
@@ -366,10 +366,14 @@ __device__ RNSC_NOINLINE int fast_huffman(FastWs<NTH>* ws, uint8_t* region, cons
     const uint32_t nst = hd.nst;
     uint32_t j = 0;
     while (j + 1 < nst && (uint32_t)tid >= hd.st_first[j + 1]) ++j;
-    uint32_t g = 0;
-    while (g + 1 < (uint32_t)PLAN_MAX_HUF && (uint32_t)tid >= hd.grp_first[g + 1]) ++g;
-    const bool member = (uint32_t)tid < hd.grp_first[PLAN_MAX_HUF];       // takes part in its group's barriers
-    const uint32_t bar_id = 1u + g, bar_n = hd.grp_first[g + 1] - hd.grp_first[g];
+    // my group: from the last leading stream at or below mine to the next leading stream (PlanHead::grp_mask); the padding
+    // threads behind a group's last sub-sequence were counted into its last stream above
+    const uint32_t gmask = hd.grp_mask;
+    const uint32_t lead = 31u - (uint32_t)__clz((int)((gmask & ((2u << j) - 1u)) | 1u));
+    const uint32_t above = gmask >> (j + 1);
+    const uint32_t nlead = above ? j + 1u + (uint32_t)(__ffs((int)above) - 1) : nst;
+    const bool member = (uint32_t)tid < hd.grp_total;                     // takes part in its group's barriers
+    const uint32_t bar_id = 1u + lead, bar_n = hd.st_first[nlead] - hd.st_first[lead];     // ids 1 .. PLAN_MAX_STREAMS (the hardware has 16)
     const uint32_t t0 = hd.st_first[j], k = (uint32_t)tid - t0;
     const StreamPlan sp = hd.st[j];
     const uint32_t T = sp.tbits, abit = sp.abit, sub = sp.sub;

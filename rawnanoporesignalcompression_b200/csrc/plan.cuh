@@ -108,7 +108,10 @@ struct PlanHead {                // what the fast kernel copies to shared memory
     int32_t view_status;
     uint32_t early;                // bit k: the sequences of sop[k] (raw / RLE literals) are executed by the CTA's last warp while the others decode Huffman streams
     uint32_t zone_off, zone_len;   // region bytes that are dead after the Huffman stage (the largest bitstream area): match resolver scratch
-    uint32_t grp_first[PLAN_MAX_HUF + 1];   // thread groups of the Huffman stage, one per Huffman-coded frame: first thread (a multiple of 32)
+    // Thread groups of the Huffman stage (whole warps that synchronise on a named barrier of their own): bit s of grp_mask =
+    // stream s is the first of a group, whose threads are [st_first[s], st_first[next leading stream]); grp_total = threads
+    // in all groups = st_first[nst]. A group is a Huffman-coded frame, or ONE stream of a frame with LZ sequences.
+    uint32_t grp_mask, grp_total;
     uint32_t lut_off;                       // region offset of the chunk's replicated key-byte table (C4 / C5, key_lut_copies(threads) copies), 0 = none: the single copy in front of the region
     uint32_t slot_off, slot_w;              // symbol slots of the Huffman stage: region offset, 32-bit words per thread (odd, 0 = none): what is left of the class's region
     uint32_t st_first[PLAN_MAX_STREAMS + 1];
@@ -699,10 +702,8 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
         while (used > nw) { uint32_t m = 0; for (uint32_t g = 1; g < ngrp; ++g) if (gw[g] > gw[m]) m = g; --gw[m]; --used; }     // nw >= 7 > ngrp: never below one warp
         if (ngrp) gw[big] += nw - used;
     }
-    uint32_t first = 0, sub_max = PLAN_SUB_MIN;
-    for (uint32_t g = 0; g < PLAN_MAX_HUF; ++g) {
-        hd->grp_first[g] = first;
-        if (g >= ngrp) continue;
+    uint32_t first = 0, sub_max = PLAN_SUB_MIN, grp_mask = 0;
+    for (uint32_t g = 0; g < ngrp; ++g) {
         const uint32_t nt = gw[g] * 32;
         uint32_t sub = nt > gn[g] ? (gt[g] + (nt - gn[g]) - 1) / (nt - gn[g]) : gt[g];
         if (sub < PLAN_SUB_MIN) sub = PLAN_SUB_MIN;
@@ -710,26 +711,42 @@ __device__ inline void plan_chunk(const PlanParams& P, uint32_t c, PlanScratch* 
                                                                 // bitstream (worth its rounding loss only where one CTA has the SM to itself)
         if (sub > sub_max) sub_max = sub;
         uint32_t t = first;
+        grp_mask |= 1u << gs0[g];
         if (gr[g] && gn[g] > 1 && nt > gn[g]) {
             // a frame with LZ sequences: the streams whose literals are cut into many runs (VBZ: the key region, at the start of
-            // the first stream) decode slower in the second pass; threads are dealt out to the streams by cost, not by bits
+            // the first stream) decode slower in the second pass; threads are dealt out to the streams by cost, not by bits.
+            // With a warp or more per stream every stream is a group of its own: a run-dense stream has many threads, i.e. a
+            // short first pass and a long second one, the others the opposite -- behind a common barrier between the passes each
+            // pass lasted as long as its slowest stream (measured on VBZ: the threads of the first stream waited as long again as
+            // their first pass took); alone, a stream's threads go on as soon as their own stream is checked and scanned.
             unsigned long long wsm = 0, wst[4] = {0, 0, 0, 0};
             for (uint32_t k = 0; k < gn[g] && k < 4; ++k) { const uint32_t s = gs0[g] + k;
                 wst[k] = (unsigned long long)P.cost_bit * stb[s] + (unsigned long long)P.cost_sym * stc[s] + (unsigned long long)P.cost_run * sruns[s] + 1; wsm += wst[k]; }
-            for (uint32_t k = 0; k < gn[g] && k < 4; ++k) {
+            const uint32_t nwg = gw[g], ns = gn[g] < 4 ? gn[g] : 4;
+            uint32_t ws4[4] = {0, 0, 0, 0};             // whole warps per stream (own groups), if there are enough
+            const bool split = nwg >= 2 * ns;
+            if (split) {
+                uint32_t used = 0, big = 0;
+                for (uint32_t k = 0; k < ns; ++k) { ws4[k] = (uint32_t)((wst[k] * nwg + wsm / 2) / wsm); if (ws4[k] < 1) ws4[k] = 1; used += ws4[k]; if (wst[k] > wst[big]) big = k; }
+                while (used > nwg) { uint32_t m = 0; for (uint32_t k = 1; k < ns; ++k) if (ws4[k] > ws4[m]) m = k; --ws4[m]; --used; }     // nwg >= 2 ns: never below one warp
+                ws4[big] += nwg - used;
+            }
+            for (uint32_t k = 0; k < ns; ++k) {
                 const uint32_t s = gs0[g] + k;
-                uint32_t ts = (uint32_t)((wst[k] * nt) / wsm); if (ts < 1) ts = 1;
+                uint32_t ts = split ? 32u * ws4[k] : (uint32_t)((wst[k] * nt) / wsm); if (ts < 1) ts = 1;
                 uint32_t ss = (stb[s] + ts - 1) / ts;
                 if (ss < PLAN_SUB_MIN) ss = PLAN_SUB_MIN;
                 if (cls == CLS_B) ss = ((ss + 31u) >> 5 | 1u) << 5;
                 if (ss > sub_max) sub_max = ss;
-                hd->st[s].sub = ss; hd->st_first[s] = t; t += (stb[s] + ss - 1) / ss;
+                hd->st[s].sub = ss; hd->st_first[s] = t;
+                if (split) { grp_mask |= 1u << s; t += ts; }      // the stream's warps, used or not: the next stream starts on a warp of its own
+                else t += (stb[s] + ss - 1) / ss;
             }
         } else
             for (uint32_t s = gs0[g]; s < gs0[g] + gn[g]; ++s) { hd->st[s].sub = sub; hd->st_first[s] = t; t += (stb[s] + sub - 1) / sub; }
         first += nt;
     }
-    hd->grp_first[PLAN_MAX_HUF] = first;
+    hd->grp_mask = grp_mask; hd->grp_total = first;
     for (uint32_t s = nst; s <= PLAN_MAX_STREAMS; ++s) hd->st_first[s] = first;
     const uint32_t sub = sub_max;
     // Symbol slots: the part of the class's region that this chunk does not need is dealt out to the Huffman threads; the
