@@ -554,6 +554,7 @@ struct ZencWs {
     uint32_t pos;                // bytes of the chunk's slot written so far
     uint32_t fail;
     uint16_t code[256];
+    uint8_t len[256];            // code lengths alone: the first pass adds up lengths only (a byte load, no shift)
 };
 
 __global__ void __launch_bounds__(ZE_NT, ZE_EMIT_CTAS) k_zenc_emit(ZencParams P)
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(ZE_NT, ZE_EMIT_CTAS) k_zenc_emit(ZencParams P)
             uint32_t nstr = 1, q = size, sbytes[4] = {0, 0, 0, 0}, tot_bits[4] = {0, 0, 0, 0};
             uint32_t my_bits = 0, my_start = 0, r0 = 0, r1 = 0, my_j = 0;
             if (mode == ZM_HUF) {
-                for (int i = tid; i < 256; i += ZE_NT) ws.code[i] = fr->code[i];
+                for (int i = tid; i < 256; i += ZE_NT) { const uint16_t cw = fr->code[i]; ws.code[i] = cw; ws.len[i] = (uint8_t)(cw >> 11); }
                 __syncthreads();
                 nstr = size >= 256 ? 4u : 1u; q = nstr == 4 ? (size + 3) / 4 : size;
                 const uint32_t G = ZE_NT / nstr;                        // threads per stream (whole warps)
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(ZE_NT, ZE_EMIT_CTAS) k_zenc_emit(ZencParams P)
                 const uint32_t t = (uint32_t)tid % G, s0 = my_j * q, s1 = min(size, s0 + q), per = (s1 - s0 + G - 1) / G;
                 r0 = min(s1, s0 + t * per); r1 = min(s1, r0 + per);
                 uint32_t bits = 0;
-                ze_for_bytes_rev(src, r0, r1, [&](uint32_t sym) { bits += ws.code[sym] >> 11; });
+                ze_for_bytes_rev(src, r0, r1, [&](uint32_t sym) { bits += ws.len[sym]; });
                 my_bits = bits;
                 // exclusive SUFFIX sum over the stream's threads: its last symbol is written first (lowest bits)
                 const uint32_t inc = warp_inclusive_scan(bits);
