@@ -154,7 +154,7 @@ struct rnsc_ctx {
     int entropy_stage = 0;                    // rnsc_compress_batch: 0 = host libzstd level 1 (byte-identical to the reference), 1 = GPU entropy stage
     bool profiling = false;
     uint32_t prof_warp = 0;                   // RNSC_PROF_WARP (tuning): which warp, counted from the end, times the phases
-    uint32_t cost_bit = 1, cost_sym = 12, cost_run = 2000;   // planner's cost model of the Huffman stage (plan.cuh); RNSC_COST_BIT / RNSC_COST_SYM / RNSC_COST_RUN override (tuning)
+    uint32_t cost_bit = 1, cost_sym = 12, cost_run = 1200;   // planner's cost model of the Huffman stage (plan.cuh); RNSC_COST_BIT / RNSC_COST_SYM / RNSC_COST_RUN override (tuning)
     Lane lane[2];
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // the size classes of the fast decoder and the general decoder run concurrently
