@@ -301,24 +301,70 @@ __device__ inline uint32_t plan_read_weights(PlanScratch* sc, PlanBig* bg, const
     return ok ? used : 0;
 }
 
+// The planner's reader of a frame's sequence bitstream (backward, MSB first; same values as BwdBits / bwd_read of
+// zstd_decode.cuh, which the general decoder keeps). The next unread bits stay left-aligned in a 64-bit register window: a
+// read is a funnel shift, and the aligned word below the window is loaded one refill AHEAD, so that nobody waits for it
+// (the word-at-a-time reader was 43 % of the planner's instructions on VBZ frames -- ~2000 sequences, six reads each --
+// and its loads a quarter of the stall samples). Bits below the stream's first byte read as zero; bitpos < 0 says that
+// some were asked for.
+struct PlanBwd {
+    const uint32_t* base;        // the aligned word that holds the stream's first byte
+    uint32_t hi, lo;             // window: `have` unread bits at the top of hi:lo, zeros below them
+    int have, bitpos;            // bitpos: unread bits left in the stream
+    int wnext; uint32_t nextw;   // index of the next word to append (< 0: below the stream) and the word itself
+    uint32_t low_mask;           // bits of word 0 that belong to the stream
+};
+__device__ __forceinline__ uint32_t planbwd_word(const PlanBwd& b, int w) { return w > 0 ? ldg32(b.base + w) : (w == 0 ? ldg32(b.base) & b.low_mask : 0u); }
+__device__ inline int planbwd_init(PlanBwd& b, const uint8_t* p, uint32_t size)
+{
+    b.base = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3); b.hi = b.lo = 0; b.have = 0; b.bitpos = 0; b.wnext = -1; b.nextw = 0; b.low_mask = 0;
+    if (size == 0) return -1;
+    const uint32_t last = ldg8(p + size - 1);
+    if (last == 0) return -1;
+    const uint32_t sh0 = 8u * (uint32_t)((uintptr_t)p & 3);
+    b.low_mask = 0xFFFFFFFFu << sh0;
+    b.bitpos = (int)size * 8 - (8 - highbit32(last));
+    const uint32_t top = (uint32_t)b.bitpos + sh0;            // bit index of the end mark, counted from word 0
+    if (top == 0) return 0;
+    const int w0 = (int)((top - 1) >> 5);                     // the word that holds the highest payload bit
+    const uint32_t k = top - 32u * (uint32_t)w0;              // payload bits in it: 1 .. 32
+    const uint32_t word = planbwd_word(b, w0);
+    b.hi = (k < 32 ? word & ((1u << k) - 1u) : word) << (32 - k);
+    b.have = (int)k; b.wnext = w0 - 1; b.nextw = planbwd_word(b, b.wnext);
+    return 0;
+}
+__device__ __forceinline__ uint32_t planbwd_read(PlanBwd& b, uint32_t n)      // n <= 31
+{
+    if (b.have < 32) {                                        // every unread bit is in hi: append the word below
+        b.hi |= b.nextw >> b.have;
+        b.lo = b.have ? b.nextw << (32 - b.have) : 0u;
+        b.have += 32; --b.wnext;
+        b.nextw = planbwd_word(b, b.wnext);                   // wanted at the next refill only
+    }
+    const uint32_t v = __funnelshift_l(b.hi, 0u, n);          // the top n bits of the window (0 for n == 0)
+    b.hi = __funnelshift_l(b.lo, b.hi, n); b.lo <<= n;
+    b.have -= (int)n; b.bitpos -= (int)n;
+    return v;
+}
+
 // Decodes `nseq` sequences given the three decoding tables (predefined, RLE = one entry with log 0, or built from
 // an FSE description). Returns 0 on success. Single exit (the planner runs one chunk per lane).
 __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32_t nseq, const uint32_t* tll, int ll_log, const uint32_t* tof, int of_log,
                                      const uint32_t* tml, int ml_log, uint32_t regen, uint32_t fcs, uint32_t* out, uint32_t* nruns, uint32_t lit_per_stream, uint32_t* runs4)
 {
     unsigned long long rc = 0;                  // runs per Huffman stream of the literals, four 16-bit counters (saturating use: a cost estimate)
-    BwdBits b;
-    bool bad = bwd_init(b, bs, bs_size) != 0;
+    PlanBwd b;
+    bool bad = planbwd_init(b, bs, bs_size) != 0;
     uint32_t sl = 0, so = 0, sm = 0;
-    if (!bad) { sl = bwd_read(b, ll_log); so = bwd_read(b, of_log); sm = bwd_read(b, ml_log); }
+    if (!bad) { sl = planbwd_read(b, (uint32_t)ll_log); so = planbwd_read(b, (uint32_t)of_log); sm = planbwd_read(b, (uint32_t)ml_log); }
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8, op = 0, lp = 0, nr = 0;
     for (uint32_t i = 0; i < nseq && !bad; ++i) {
         const uint32_t el = tll[sl], eo = tof[so], em = tml[sm];
         const uint32_t llc = el & 0xFF, ofc = eo & 0xFF, mlc = em & 0xFF;
         if (llc > 35 || mlc > 52 || ofc > 31) { bad = true; break; }
-        const uint32_t ofv = (1u << ofc) + bwd_read(b, (int)ofc);
-        const uint32_t ml = kMLBase[mlc] + bwd_read(b, kMLBits[mlc]);
-        const uint32_t ll = kLLBase[llc] + bwd_read(b, kLLBits[llc]);
+        const uint32_t ofv = (1u << ofc) + planbwd_read(b, ofc);
+        const uint32_t ml = kMLBase[mlc] + planbwd_read(b, (uint32_t)kMLBits[mlc]);
+        const uint32_t ll = kLLBase[llc] + planbwd_read(b, (uint32_t)kLLBits[llc]);
         uint32_t offset;
         if (ofv > 3) { offset = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = offset; }
         else {
@@ -332,11 +378,11 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
             }
         }
         if (i + 1 < nseq) {
-            sl = (el >> 16) + bwd_read(b, (int)((el >> 8) & 0xFF));
-            sm = (em >> 16) + bwd_read(b, (int)((em >> 8) & 0xFF));
-            so = (eo >> 16) + bwd_read(b, (int)((eo >> 8) & 0xFF));
+            sl = (el >> 16) + planbwd_read(b, (el >> 8) & 0xFF);
+            sm = (em >> 16) + planbwd_read(b, (em >> 8) & 0xFF);
+            so = (eo >> 16) + planbwd_read(b, (eo >> 8) & 0xFF);
         }
-        if (b.overflow || lp + ll > regen || op + ll + ml > fcs || offset > op + ll) { bad = true; break; }
+        if (b.bitpos < 0 || lp + ll > regen || op + ll + ml > fcs || offset > op + ll) { bad = true; break; }
         out[SEQ_WORDS * i] = ll; out[SEQ_WORDS * i + 1] = ml; out[SEQ_WORDS * i + 2] = offset; out[SEQ_WORDS * i + 3] = lp; out[SEQ_WORDS * i + 4] = op; out[SEQ_WORDS * i + 5] = op - lp;
         if (ll) {      // compact list of the non-empty literal runs (nr <= i)
             out[SEQ_WORDS * nr + 6] = lp; out[SEQ_WORDS * nr + 7] = op - lp; ++nr;
