@@ -356,15 +356,28 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
     PlanBwd b;
     bool bad = planbwd_init(b, bs, bs_size) != 0;
     uint32_t sl = 0, so = 0, sm = 0;
-    if (!bad) { sl = planbwd_read(b, (uint32_t)ll_log); so = planbwd_read(b, (uint32_t)of_log); sm = planbwd_read(b, (uint32_t)ml_log); }
+    // The table entries of sequence i + 1 are fetched as soon as its states are known -- right behind the extra bits of
+    // sequence i, whose offset history, checks and stores then run while the three loads are in flight (the tables of an
+    // FSE-described frame live in the plan's global scratch: an L2 round trip, 13 % of the planner's stall samples on VBZ).
+    uint32_t el = 0, eo = 0, em = 0;
+    if (!bad) {
+        sl = planbwd_read(b, (uint32_t)ll_log); so = planbwd_read(b, (uint32_t)of_log); sm = planbwd_read(b, (uint32_t)ml_log);
+        if (nseq) { el = tll[sl]; eo = tof[so]; em = tml[sm]; }
+    }
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8, op = 0, lp = 0, nr = 0;
     for (uint32_t i = 0; i < nseq && !bad; ++i) {
-        const uint32_t el = tll[sl], eo = tof[so], em = tml[sm];
         const uint32_t llc = el & 0xFF, ofc = eo & 0xFF, mlc = em & 0xFF;
         if (llc > 35 || mlc > 52 || ofc > 31) { bad = true; break; }
         const uint32_t ofv = (1u << ofc) + planbwd_read(b, ofc);
         const uint32_t ml = kMLBase[mlc] + planbwd_read(b, (uint32_t)kMLBits[mlc]);
         const uint32_t ll = kLLBase[llc] + planbwd_read(b, (uint32_t)kLLBits[llc]);
+        uint32_t nel = 0, neo = 0, nem = 0;
+        if (i + 1 < nseq) {
+            sl = (el >> 16) + planbwd_read(b, (el >> 8) & 0xFF);
+            sm = (em >> 16) + planbwd_read(b, (em >> 8) & 0xFF);
+            so = (eo >> 16) + planbwd_read(b, (eo >> 8) & 0xFF);
+            nel = tll[sl]; neo = tof[so]; nem = tml[sm];
+        }
         uint32_t offset;
         if (ofv > 3) { offset = ofv - 3; rep2 = rep1; rep1 = rep0; rep0 = offset; }
         else {
@@ -377,11 +390,6 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
                 rep1 = rep0; rep0 = offset;
             }
         }
-        if (i + 1 < nseq) {
-            sl = (el >> 16) + planbwd_read(b, (el >> 8) & 0xFF);
-            sm = (em >> 16) + planbwd_read(b, (em >> 8) & 0xFF);
-            so = (eo >> 16) + planbwd_read(b, (eo >> 8) & 0xFF);
-        }
         if (b.bitpos < 0 || lp + ll > regen || op + ll + ml > fcs || offset > op + ll) { bad = true; break; }
         out[SEQ_WORDS * i] = ll; out[SEQ_WORDS * i + 1] = ml; out[SEQ_WORDS * i + 2] = offset; out[SEQ_WORDS * i + 3] = lp; out[SEQ_WORDS * i + 4] = op; out[SEQ_WORDS * i + 5] = op - lp;
         if (ll) {      // compact list of the non-empty literal runs (nr <= i)
@@ -390,6 +398,7 @@ __device__ inline int plan_sequences(const uint8_t* bs, uint32_t bs_size, uint32
             rc += 1ull << (16 * sidx);
         }
         op += ll + ml; lp += ll;
+        el = nel; eo = neo; em = nem;
     }
     if (!bad && (b.bitpos != 0 || op + (regen - lp) != fcs)) bad = true;
     if (!bad) {
